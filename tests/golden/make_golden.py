@@ -1,0 +1,183 @@
+"""Generate the committed golden fixtures from the importable parts of pmarlo.
+
+Run once in the build container (needs /root/reference, which does NOT exist
+on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the reference functions that run without deeptime/mdtraj
+ and stores seeded inputs together with the reference outputs:
+
+* counts.npz      -- analysis.discretize._weighted_counts (discretize.py:609-645),
+                     analysis.debug_export._build_transition_counts
+                     (debug_export.py:385-409), analysis.counting.expected_pairs
+* timescales.npz  -- markov_state_model.utils.safe_timescales (utils.py:17-57)
+* preprocess.npz  -- markov_state_model.reduction._preprocess (reduction.py:13-40)
+* tica_xcheck.npz -- features.deeptica.core.trainer_api._estimate_top_eigenvalues
+                     (trainer_api.py:632-656), a non-symmetrised numpy TICA
+                     used only as a loose cross-check of the oracle
+* assign.npz      -- analysis.discretize._KMeansDiscretizer fit/transform
+                     (discretize.py:406-514; sklearn KMeans.predict labels)
+* topologies.npz  -- atom names / residue ids / coordinates (nm) parsed from
+                     data/alanine-dipeptide.pdb and data/chignolin.pdb (model 1)
+"""
+
+from __future__ import annotations
+
+import pathlib
+import sys
+import types
+
+import numpy as np
+
+REF = pathlib.Path("/root/reference")
+sys.path.insert(0, str(REF / "src"))
+OUT = pathlib.Path(__file__).resolve().parent
+
+
+def _parse_pdb(path: pathlib.Path, first_model_only: bool = True):
+    names, resn, resid, chain, xyz = [], [], [], [], []
+    last_key, ridx = None, -1
+    for line in path.read_text().splitlines():
+        if line.startswith("ENDMDL") and first_model_only:
+            break
+        if not line.startswith(("ATOM", "HETATM")):
+            continue
+        name = line[12:16].strip()
+        rn = line[17:20].strip()
+        ch = line[21].strip() or "A"
+        rs = line[22:27].strip()
+        key = (ch, rs, rn)
+        if key != last_key:
+            ridx += 1
+            last_key = key
+        names.append(name)
+        resn.append(rn)
+        resid.append(ridx)
+        chain.append(0)
+        xyz.append([float(line[30:38]), float(line[38:46]), float(line[46:54])])
+    return (np.array(names), np.array(resn), np.array(resid, dtype=np.int32),
+            np.array(chain, dtype=np.int32), (np.array(xyz, dtype=np.float64) / 10.0).astype(np.float32))
+
+
+def make_topologies():
+    a = _parse_pdb(REF / "data" / "alanine-dipeptide.pdb")
+    c = _parse_pdb(REF / "data" / "chignolin.pdb")
+    np.savez_compressed(
+        OUT / "topologies.npz",
+        ala2_names=a[0], ala2_resn=a[1], ala2_resid=a[2], ala2_chain=a[3], ala2_xyz=a[4],
+        chig_names=c[0], chig_resn=c[1], chig_resid=c[2], chig_chain=c[3], chig_xyz=c[4],
+    )
+    print("topologies:", a[4].shape, c[4].shape)
+
+
+def make_counts():
+    from pmarlo.analysis.counting import expected_pairs
+    from pmarlo.analysis.debug_export import _build_transition_counts
+    from pmarlo.analysis.discretize import _weighted_counts
+
+    rng = np.random.default_rng(20260518)
+    out = {}
+    cases = []
+    for ci, (n, K, lag, stride, pneg) in enumerate(
+        [(500, 7, 1, 1, 0.0), (2000, 13, 5, 1, 0.05), (3000, 50, 17, 3, 0.1),
+         (64, 3, 70, 1, 0.0), (1500, 9, 2, 2, 0.3), (1, 2, 1, 1, 0.0)]):
+        labels = rng.integers(0, K, size=n).astype(np.int32)
+        labels[rng.random(n) < pneg] = -1
+        cuts = np.sort(rng.choice(np.arange(1, max(2, n)), size=min(4, max(0, n - 1)), replace=False)) if n > 1 else np.array([], dtype=int)
+        bounds = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+        segments = [(int(bounds[i]), int(bounds[i + 1])) for i in range(len(bounds) - 1)]
+        weights = rng.random(n)
+        C_u, tp_u = _weighted_counts(labels, n_states=K, lag_time=lag, segments=segments, stride=stride)
+        C_w, tp_w = _weighted_counts(labels, n_states=K, lag_time=lag, weights=weights, segments=segments, stride=stride)
+        C_all, tp_all = _weighted_counts(labels, n_states=K, lag_time=lag)
+        dtrajs = [labels[s:e] for s, e in segments]
+        C_sl, n_sl = _build_transition_counts(dtrajs, K, lag, "sliding")
+        C_st, n_st = _build_transition_counts(dtrajs, K, lag, "strided")
+        ep = expected_pairs([e - s for s, e in segments], lag, stride)
+        for k, v in dict(labels=labels, bounds=bounds, weights=weights, K=K, lag=lag, stride=stride,
+                         C_u=C_u, tp_u=tp_u, C_w=C_w, tp_w=tp_w, C_all=C_all, tp_all=tp_all,
+                         C_sl=C_sl, n_sl=n_sl, C_st=C_st, n_st=n_st, ep=ep).items():
+            out[f"c{ci}_{k}"] = np.asarray(v)
+        cases.append(ci)
+    out["n_cases"] = np.asarray(len(cases))
+    np.savez_compressed(OUT / "counts.npz", **out)
+    print("counts: cases", len(cases))
+
+
+def make_timescales():
+    from pmarlo.markov_state_model.utils import safe_timescales
+
+    ev_real = np.array([1.0, 0.999999999999, 0.99, 0.8, 0.5, 1e-3, 1e-13, 0.0, -0.2, 1.2, np.nan, np.inf])
+    ev_cplx = np.array([0.9 + 0.0j, 0.5 + 0.3j, -0.4 + 0.0j, 0.0 + 0.0j, 0.7 - 0.7j, 1.0 + 0.0j])
+    out = {"ev_real": ev_real, "ev_cplx": ev_cplx}
+    for lag in (1, 10, 400):
+        out[f"ts_real_{lag}"] = safe_timescales(lag, ev_real)
+        out[f"ts_cplx_{lag}"] = safe_timescales(lag, ev_cplx)
+    out["ts_empty"] = safe_timescales(5, np.array([]))
+    np.savez_compressed(OUT / "timescales.npz", **out)
+    print("timescales ok")
+
+
+def make_preprocess():
+    from pmarlo.markov_state_model.reduction import _preprocess
+
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((400, 6)) * np.array([1.0, 5.0, 0.01, 100.0, 1.0, 1.0]) + np.array([0, 3, -2, 50, 0, 1.0])
+    X[:, 4] = 2.5  # constant column
+    Xn = X.copy()
+    Xn[rng.random(X.shape) < 0.03] = np.nan
+    Xn[:, 4] = 2.5
+    np.savez_compressed(
+        OUT / "preprocess.npz", X=X, Xn=Xn,
+        P_scale=_preprocess(X, scale=True), P_noscale=_preprocess(X, scale=False),
+        Pn_scale=_preprocess(Xn, scale=True), Pn_noscale=_preprocess(Xn, scale=False),
+        P_1d=_preprocess(X[:, 1], scale=True),
+    )
+    print("preprocess ok")
+
+
+def make_tica_xcheck():
+    from pmarlo.features.deeptica.core.trainer_api import _estimate_top_eigenvalues
+
+    rng = np.random.default_rng(11)
+    N, rho, lag = 60000, np.array([0.97, 0.9, 0.6, 0.2]), 4
+    x = np.zeros((N, 4))
+    e = rng.standard_normal((N, 4))
+    for t in range(1, N):
+        x[t] = rho * x[t - 1] + np.sqrt(1 - rho ** 2) * e[t]
+    A = rng.standard_normal((4, 4))
+    X = (x @ A).astype(np.float64)
+    idx_t = np.arange(0, N - lag)
+    idx_tau = idx_t + lag
+    cfg = types.SimpleNamespace(n_out=4)
+    ev = np.asarray(_estimate_top_eigenvalues(X, idx_t, idx_tau, cfg))
+    np.savez_compressed(OUT / "tica_xcheck.npz", X=X.astype(np.float32), lag=lag, rho=rho, ref_eigs=ev)
+    print("tica xcheck eigs", ev, rho ** lag)
+
+
+def make_assign():
+    from pmarlo.analysis.discretize import _KMeansDiscretizer
+
+    rng = np.random.default_rng(3)
+    centers0 = rng.standard_normal((12, 5)) * 4
+    X = centers0[rng.integers(0, 12, 3000)] + rng.standard_normal((3000, 5))
+    Xt = centers0[rng.integers(0, 12, 1000)] + rng.standard_normal((1000, 5))
+    disc = _KMeansDiscretizer(12, random_state=0, apply_whitening=True)
+    disc.fit(X)
+    lab_train = disc.transform(X)
+    lab_test = disc.transform(Xt)
+    np.savez_compressed(
+        OUT / "assign.npz", X=X, Xt=Xt, mean=disc.scaler_mean_, std=disc.scaler_std_,
+        centers=disc.centers, lab_train=lab_train, lab_test=lab_test,
+    )
+    print("assign ok", np.bincount(lab_train))
+
+
+if __name__ == "__main__":
+    make_topologies()
+    make_counts()
+    make_timescales()
+    make_preprocess()
+    make_tica_xcheck()
+    make_assign()
