@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the end-to-end MSM pipeline on B200 (BASELINE.json metric).
+
+One "step" = one pass of the whole hot path (featurize -> z-score -> TICA fit +
+project -> k-means Lloyd -> lagged counts -> reversible MLE -> leading
+eigenvalues -> implied timescales) over this rank's shard of synthetic
+protein-scale trajectories (config C4 of BASELINE.json / SURVEY.md section 8d:
+33-residue backbone = 99 atoms, 256 features = cos/sin of 32 phi + 32 psi + the
+first 128 C-alpha pair distances, z-score, TICA lag 20 -> 10 dims, k-means 1000
+states with 20 Lloyd iterations from seeded initial centres, MSM lag 20).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # CPU reference arm (oracle port)
+
+Prints ONE JSON line (rank 0).  `value` has the coordinates resident in HBM when
+the timed region starts; `e2e` goes through the host-buffer API with the
+host->device copy of the coordinates and the device->host read of the result
+inside the timed region.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import tempfile
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+N_RES = 33
+N_DIST = 128
+FRAMES_PER_TRAJ = 125_000
+TICA_LAG, TICA_DIM, N_STATES, KMEANS_ITERS, MSM_LAG, N_TIMESCALES = 20, 10, 1000, 20, 20, 5
+METRIC = "frames/sec end-to-end MSM pipeline"
+UNIT = "frames/s"
+
+
+# ----------------------------------------------------------------------------- workload
+@dataclass
+class Workload:
+    xyz: "object"            # torch (N, 99, 3) float32 on the device
+    segs: "object"           # pmarlo_b200.shards.Segments
+    plan: "object"           # FeaturePlan (256 columns)
+    top: "object"
+
+
+def c4_plan():
+    from pmarlo_b200.features import ca_pairs_all, plan_concat, plan_distances, plan_phi_psi_block
+    from tests.synth import backbone_topology
+
+    top = backbone_topology(N_RES)
+    pairs = ca_pairs_all(top.select_name("CA"))[:N_DIST]
+    plan = plan_concat([plan_phi_psi_block(top), plan_distances(pairs)])
+    assert plan.n_cols == 256, plan.n_cols
+    return top, plan, pairs
+
+
+def bench_config(n_states=N_STATES, kmeans_iters=KMEANS_ITERS, gram_impl=0):
+    from pmarlo_b200.pipeline import PipelineConfig
+
+    return PipelineConfig(tica_lag=TICA_LAG, tica_dim=TICA_DIM, preprocess="standard", n_states=n_states,
+                          kmeans_max_iter=kmeans_iters, kmeans_tolerance=None, msm_lag=MSM_LAG,
+                          n_timescales=N_TIMESCALES, mle_maxerr=1e-8, mle_maxiter=1_000_000,
+                          gram_impl=gram_impl, seed=4)
+
+
+def synth_xyz_device(n_traj, frames_per_traj, device, seed, rho=0.9995, sigma=0.03, chunk=2048):
+    """AR(1) internal motion (rho) around a random-coil 33-residue backbone, generated on the
+    device chunk by chunk: x_t = rho^t (x_0 + sum_{s<=t} rho^-s e_s) inside a chunk."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    A = 3 * N_RES
+    steps = torch.randn((A, 3), generator=g, device=device, dtype=torch.float64)
+    steps /= steps.norm(dim=1, keepdim=True)
+    base = torch.cumsum(0.15 * steps, dim=0).to(torch.float32)
+    out = torch.empty((n_traj, frames_per_traj, A, 3), dtype=torch.float32, device=device)
+    state = sigma * torch.randn((n_traj, 1, A, 3), generator=g, device=device, dtype=torch.float32)
+    amp = sigma * (1 - rho * rho) ** 0.5
+    for s in range(0, frames_per_traj, chunk):
+        n = min(chunk, frames_per_traj - s)
+        t = torch.arange(1, n + 1, device=device, dtype=torch.float32).view(1, n, 1, 1)
+        e = amp * torch.randn((n_traj, n, A, 3), generator=g, device=device, dtype=torch.float32)
+        x = (rho ** t) * (state + torch.cumsum(e * (rho ** (-t)), dim=1))
+        out[:, s:s + n] = x
+        state = x[:, -1:].clone()
+    out += base
+    return out.view(n_traj * frames_per_traj, A, 3)
+
+
+def make_workload(n_traj, frames_per_traj, device, seed) -> Workload:
+    from pmarlo_b200.shards import Segments
+
+    top, plan, _ = c4_plan()
+    xyz = synth_xyz_device(n_traj, frames_per_traj, device, seed)
+    return Workload(xyz, Segments.from_lengths([frames_per_traj] * n_traj), plan, top)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample_inputs(n_traj, frames_per_traj, seed):
+    """Host copy of a bounded sample of the same synthetic workload (numpy AR(1))."""
+    from tests.synth import backbone_trajectories
+
+    return backbone_trajectories(N_RES, n_traj, frames_per_traj, seed, rho=0.9995, sigma=0.03)
+
+
+def run_cpu_pipeline(trajs, n_states=N_STATES, kmeans_iters=KMEANS_ITERS):
+    from oracle import featurize as ofeat
+    from oracle import pipeline as opipe
+    from tests.synth import backbone_topology
+
+    top = backbone_topology(N_RES)
+    phi = ofeat.dihedral_quads(top.names, top.resid, top.chainid, "phi")
+    psi = ofeat.dihedral_quads(top.names, top.resid, top.chainid, "psi")
+    pairs = ofeat.ca_pairs_all(ofeat.ca_indices(top.names))[:N_DIST]
+    return opipe.run(trajs, phi, psi, pairs, tica_lag=TICA_LAG, tica_dim=TICA_DIM, n_states=n_states,
+                     kmeans_iters=kmeans_iters, msm_lag=MSM_LAG, n_timescales=N_TIMESCALES, seed=4)
+
+
+def cpu_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_cpu(sample_traj, sample_frames, repeats=1):
+    trajs = cpu_sample_inputs(sample_traj, sample_frames, seed=4)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        res = run_cpu_pipeline(trajs)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return res.n_frames / best, best, res
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = cpu_threads()
+    n_traj, n_frames = 2, args.cpu_sample_frames // 2
+    trajs = cpu_sample_inputs(n_traj, n_frames, seed=4)
+    for _ in range(args.warmup):
+        run_cpu_pipeline(trajs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = run_cpu_pipeline(trajs)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = res.n_frames / dt
+    sample = (f"{n_traj} trajectories x {n_frames} frames of the C4 workload per step (same shapes, K={N_STATES}, "
+              f"{KMEANS_ITERS} Lloyd iterations), numpy/scipy BLAS + sklearn Lloyd on {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_traj * n_frames, cpu=True),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stages_s": res.stage_seconds,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, frames_per_gpu, cpu=False):
+    return {
+        "workload": ("C4 synthetic protein-scale: 33-residue backbone (99 atoms) -> 256 features "
+                     "(cos/sin of 32 phi + 32 psi, 128 CA distances), z-score, TICA lag 20 -> 10 dims, "
+                     "k-means K=1000 x 20 Lloyd iterations, counts + reversible MLE + top-6 eigenvalues at lag 20"),
+        "frames_per_gpu": int(frames_per_gpu), "frames_per_trajectory": FRAMES_PER_TRAJ if not cpu else None,
+        "n_features": 256, "n_states": N_STATES, "kmeans_iters": KMEANS_ITERS, "tica_lag": TICA_LAG,
+        "msm_lag": MSM_LAG, "parallelism": f"frame shards x{args.gpus}, allreduce of partial sums",
+        "l2_policy": "inputs (>= 1.4 GB of coordinates per step) larger than the 126 MB L2",
+    }
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from pmarlo_b200 import _lib
+    from pmarlo_b200.distributed import Comm
+    from pmarlo_b200.pipeline import StageTimer, estimate_msm_from_host, run_pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    comm = Comm()
+    _lib.load()
+
+    n_traj = max(1, args.frames_per_gpu // FRAMES_PER_TRAJ)
+    fpt = FRAMES_PER_TRAJ if args.frames_per_gpu >= FRAMES_PER_TRAJ else args.frames_per_gpu
+    frames = n_traj * fpt
+    wl = make_workload(n_traj, fpt, device, seed=4000 + rank)
+    cfg = bench_config(gram_impl=args.gram_impl)
+
+    def sync():
+        torch.cuda.synchronize(device)
+        comm.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident timing -------------------------------------------------
+    timer = StageTimer(True)
+    for _ in range(args.warmup):
+        run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, read_back=True)
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        res = run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, timer=timer, read_back=True)
+    ev1.record()
+    sync()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+    comm.allreduce_max(ms)
+    ms_per_step = float(ms.item()) / args.steps
+    value = frames * world / (ms_per_step * 1e-3)
+    stages = {k: v / args.steps for k, v in timer.totals_ms().items()}
+    counts = timer.counts()
+
+    # ---- end to end through the host-buffer API ---------------------------------
+    host = torch.empty(wl.xyz.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(wl.xyz)
+    del wl.xyz
+    torch.cuda.empty_cache()
+    lengths = [fpt] * n_traj
+    for _ in range(max(1, min(2, args.warmup))):
+        out = estimate_msm_from_host(host, lengths, wl.plan, cfg, comm)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        out = estimate_msm_from_host(host, lengths, wl.plan, cfg, comm)
+    e1.record()
+    sync()
+    ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    comm.allreduce_max(ems)
+    e2e_ms = float(ems.item()) / args.e2e_steps
+    e2e_value = frames * world / (e2e_ms * 1e-3)
+    h2d = int(host.numel() * 4)
+    d2h = int(out["d2h_bytes"])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    roof = roofline(stages, counts, frames, cfg, peaks, args)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, secs, _ = time_cpu(2, args.cpu_sample_frames // 2)
+        cpu = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+               "sample": f"2 trajectories x {args.cpu_sample_frames // 2} frames of the same workload "
+                         f"(K={N_STATES}, {KMEANS_ITERS} Lloyd iterations), {secs:.1f} s of oracle work"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 features / 3xTF32-or-fp32 Gram with fp64 flush / f64 MSM",
+        "data": "synthetic", "config": workload_config(args, frames),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "stages_ms": stages, "kmeans_iters_run": int(res.kmeans_iters),
+        "mle_iters": int(res.mle_info[0].item()), "timescales": [None if not np.isfinite(t) else float(t)
+                                                                for t in (res.timescales if res.timescales is not None else [])],
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def roofline(stages, counts, frames, cfg, peaks, args):
+    """Roofline of the dominant kernel, from the CUDA-event time of its launches inside the
+    timed region.  Algorithmic work per frame (DESIGN.md section 5 / SURVEY.md 8d)."""
+    kernels_alg = {
+        # name: (bound, bytes or flops per frame per launch)
+        "featurize": ("hbm", 12 * 3 * N_RES + 4 * 256),
+        "col_moments": ("hbm", 4 * 256),
+        "gram": ("tensor", 2 * 256 * 256),            # one d x d rank-1 update per frame per launch
+        "project": ("hbm", 4 * 256 + 4 * cfg.tica_dim),
+        "kmeans_assign": ("tensor", 2 * cfg.tica_dim * cfg.n_states),
+        "count": ("hbm", 4),
+    }
+    cand = {k: stages.get(k, 0.0) for k in kernels_alg}
+    top = max(cand, key=cand.get)
+    bound, per_frame = kernels_alg[top]
+    n_launch = max(1, counts.get(top, 1))
+    ms_per_launch = cand[top] * args.steps / n_launch if n_launch else 0.0
+    work = per_frame * frames
+    if bound == "hbm":
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = work / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch else 0.0
+        unit = "GB/s"
+        src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"
+    else:
+        # fp32-exact tensor work is issued as TF32 (3 passes for the split): peak = measured bf16 / 2
+        key = "bf16_tflops_sustained"
+        peak = float(peaks.get(key, 1400.0)) / 2.0
+        achieved = work / (ms_per_launch * 1e-3) / 1e12 if ms_per_launch else 0.0
+        unit = "TFLOP/s"
+        src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 rate; kernel timed inside a long step)"
+               if peaks else "fallback 1.4 PFLOP/s / 2")
+    return {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+            "frac": achieved / peak if peak else None, "traffic": None, "ms_per_launch": ms_per_launch,
+            "launches_per_step": n_launch / args.steps, "algorithmic_per_frame": per_frame, "peak_source": src,
+            "share_of_step": cand[top] / max(1e-9, sum(v for k, v in stages.items() if k in TOP_LEVEL_STAGES))}
+
+
+TOP_LEVEL_STAGES = ("featurize", "tica_fit", "project", "kmeans", "count", "mle", "eig")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=1_250_000,
+                    help="frames of this rank's shard (C4: 10 M frames over 8 GPUs = 1.25 M per GPU)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-frames", type=int, default=40_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gram-impl", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("note: fewer than 3 warm-up steps", file=sys.stderr)
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,147 @@
+// common.cuh -- shared helpers for the libpmb200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pmb200.h"
+
+#ifndef __CUDA_ARCH_FEAT_SM100_ALL
+#if defined(__CUDA_ARCH__)
+#error "libpmb200 must be compiled with -gencode arch=compute_100a,code=sm_100a"
+#endif
+#endif
+
+namespace pmb {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline cudaStream_t as_stream(pmb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define PMB_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      pmb::set_error(__VA_ARGS__);        \
+      return PMB_EINVAL;                  \
+    }                                     \
+  } while (0)
+
+#define PMB_CUDA(expr)                                                         \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) {                                                   \
+      pmb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                     __FILE__, __LINE__);                                      \
+      return PMB_ECUDA;                                                        \
+    }                                                                          \
+  } while (0)
+
+#define PMB_LAUNCH_CHECK()                                                     \
+  do {                                                                         \
+    cudaError_t _e = cudaGetLastError();                                       \
+    if (_e != cudaSuccess) {                                                   \
+      pmb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                      \
+      return PMB_ECUDA;                                                        \
+    }                                                                          \
+    pmb::count_launch();                                                       \
+  } while (0)
+
+// ---------------------------------------------------------------- device side
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// mbarrier + 1-D bulk (TMA) copies -------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost transaction traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// global -> shared bulk copy completing on an mbarrier (bytes % 16 == 0, 16B aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared -> global bulk store (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// streaming loads (read once: do not pollute L1)
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream_f(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace pmb

@@ -1,0 +1,318 @@
+// eig.cu -- K9: leading eigenvalues of a reversible transition matrix.
+//
+// A = D^{1/2} T D^{-1/2} (D = diag(pi)) is symmetric for a reversible T, so its
+// spectrum is real; states with pi_i = 0 (outside the active set) contribute a
+// zero row/column and therefore only zero eigenvalues, which sort last.
+//  * K <= kEigJacobiMaxK: A is formed explicitly and handed to the batched
+//    one-sided Jacobi solver of tica.cu (one CTA per matrix) -- the ITS sweep
+//    path, one CTA per lag time;
+//  * larger K: Lanczos with full (two-pass classical Gram-Schmidt)
+//    re-orthogonalisation in ONE cooperative kernel: the mat-vec streams T once
+//    per step (8 K^2 bytes, HBM/L2-bound), the Ritz values of the m x m
+//    tridiagonal matrix come from Sturm-sequence bisection (one thread per
+//    eigenvalue).  Convergence flag: the k leading Ritz values of T_m and of
+//    T_{m - m/8} agree to 1e-10.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace pmb {
+
+constexpr int kEigJacobiMaxK = 256;
+constexpr int kLanThreads = 256;
+
+int sym_eigvals_launch(double* A, int n, int batch, double* evals, double* scratch, int* order,
+                       cudaStream_t st);  // tica.cu
+
+__global__ void eig_build_sym_kernel(const double* __restrict__ T, const double* __restrict__ pi, int K,
+                                     double* __restrict__ A) {
+  const size_t b = blockIdx.z;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K || j >= K) return;
+  const double pi_i = pi[b * K + i], pi_j = pi[b * K + j];
+  double v = 0.0;
+  if (pi_i > 0.0 && pi_j > 0.0) {
+    const double si = sqrt(pi_i), sj = sqrt(pi_j);
+    const double a = si * T[b * K * K + (size_t)i * K + j] / sj;
+    const double at = sj * T[b * K * K + (size_t)j * K + i] / si;
+    v = 0.5 * (a + at);
+  }
+  A[b * K * K + (size_t)i * K + j] = v;
+}
+
+__global__ void eig_take_topk_kernel(const double* __restrict__ full, int K, int k, double* __restrict__ out,
+                                     long long* __restrict__ info) {
+  const size_t b = blockIdx.x;
+  for (int t = threadIdx.x; t < k; t += blockDim.x) out[b * k + t] = (t < K) ? full[b * K + t] : 0.0;
+  if (threadIdx.x == 0) { info[2 * b] = 0; info[2 * b + 1] = 1; }
+}
+
+// number of eigenvalues of the tridiagonal (a, b) of size m that are < x
+__device__ __forceinline__ int sturm_count(const double* a, const double* b, int m, double x, double tiny) {
+  int cnt = 0;
+  double d = a[0] - x;
+  if (d == 0.0) d = -tiny;
+  cnt += d < 0.0;
+  for (int i = 1; i < m; ++i) {
+    d = a[i] - x - (b[i - 1] * b[i - 1]) / d;
+    if (d == 0.0) d = -tiny;
+    cnt += d < 0.0;
+  }
+  return cnt;
+}
+
+// all eigenvalues (ascending) of the m x m tridiagonal; thread t -> eigenvalue t
+__device__ void tridiag_bisect(const double* a, const double* b, int m, double* out) {
+  double lo = 1e300, hi = -1e300;
+  for (int i = 0; i < m; ++i) {
+    const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < m ? fabs(b[i]) : 0.0);
+    lo = fmin(lo, a[i] - r);
+    hi = fmax(hi, a[i] + r);
+  }
+  const double span = fmax(fabs(lo), fabs(hi));
+  const double tiny = 2.3e-308 + 1e-30 * span;
+  lo -= 1e-12 * span + 1e-300;
+  hi += 1e-12 * span + 1e-300;
+  for (int t = threadIdx.x; t < m; t += blockDim.x) {
+    double l = lo, h = hi;
+    for (int it = 0; it < 200; ++it) {
+      const double mid = 0.5 * (l + h);
+      if (mid <= l || mid >= h) break;
+      if (sturm_count(a, b, m, mid, tiny) > t) h = mid; else l = mid;
+    }
+    out[t] = 0.5 * (l + h);
+  }
+}
+
+struct LanParams {
+  const double* T;
+  const double* pi;
+  int K, k, m;
+  double* evals;       // k
+  long long* info;     // 2
+  double* V;           // (m+1) x K
+  double* w;           // K
+  double* z;           // K
+  double* h;           // 2 x (m+1)
+  double* alpha;       // m
+  double* beta;        // m
+  double* part;        // gridDim.x
+  double* ritz;        // 2 x m
+};
+
+__device__ __forceinline__ double grid_sum_partials(const double* part, int n) {
+  double r = 0.0;
+  for (int i = 0; i < n; ++i) r += __ldcg(part + i);
+  return r;
+}
+
+__global__ void __launch_bounds__(kLanThreads) lanczos_kernel(LanParams p) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double s_red[32];
+  __shared__ int s_order[1024];
+  const int K = p.K, tid = threadIdx.x, lane = tid & 31;
+  const int gtid = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
+  const int gwarp = gtid >> 5, nwarps = gthreads >> 5;
+
+  auto block_partial = [&](double v) {  // deterministic per-CTA sum -> part[blockIdx.x]
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double r = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += s_red[w];
+      p.part[blockIdx.x] = r;
+    }
+  };
+
+  // v0: deterministic, supported on the active states
+  double acc = 0.0;
+  for (int e = gtid; e < K; e += gthreads) {
+    const double v = (p.pi[e] > 0.0) ? 1.0 + 0.5 * sin(0.7548776662466927 * (double)(e + 1)) : 0.0;
+    p.w[e] = v;
+    acc = fma(v, v, acc);
+  }
+  block_partial(acc);
+  grid.sync();
+  double nrm = sqrt(grid_sum_partials(p.part, gridDim.x));
+  if (!(nrm > 0.0)) {
+    if (gtid == 0) { p.info[0] = 0; p.info[1] = -1; }
+    for (int t = gtid; t < p.k; t += gthreads) p.evals[t] = 0.0;
+    return;
+  }
+  for (int e = gtid; e < K; e += gthreads) {
+    const double v = __ldcg(p.w + e) / nrm;
+    p.V[e] = v;
+    const double pe = p.pi[e];
+    p.z[e] = pe > 0.0 ? v / sqrt(pe) : 0.0;
+  }
+  grid.sync();
+
+  int m_eff = 0;
+  for (int j = 0; j < p.m; ++j) {
+    // A: w = D^{1/2} T z
+    for (int i = gwarp; i < K; i += nwarps) {
+      const double pe = p.pi[i];
+      double s = 0.0;
+      if (pe > 0.0) {
+        const double* Trow = p.T + (size_t)i * K;
+        for (int c = lane; c < K; c += 32) s = fma(Trow[c], __ldcg(p.z + c), s);
+        s = warp_sum(s) * sqrt(pe);
+      }
+      if (lane == 0) p.w[i] = s;
+    }
+    grid.sync();
+    double a_j = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      double* h = p.h + (size_t)pass * (p.m + 1);
+      // B: h_i = v_i . w
+      for (int i = gwarp; i <= j; i += nwarps) {
+        const double* vi = p.V + (size_t)i * K;
+        double s = 0.0;
+        for (int c = lane; c < K; c += 32) s = fma(__ldcg(vi + c), __ldcg(p.w + c), s);
+        s = warp_sum(s);
+        if (lane == 0) h[i] = s;
+      }
+      grid.sync();
+      // C: w -= sum_i h_i v_i  (+ partial |w|^2 on the second pass)
+      double nn = 0.0;
+      for (int e = gtid; e < K; e += gthreads) {
+        double v = __ldcg(p.w + e);
+        for (int i = 0; i <= j; ++i) v = fma(-__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), v);
+        p.w[e] = v;
+        nn = fma(v, v, nn);
+      }
+      a_j += __ldcg(h + j);
+      if (pass == 1) block_partial(nn);
+      grid.sync();
+    }
+    const double b_j = sqrt(grid_sum_partials(p.part, gridDim.x));
+    if (gtid == 0) { p.alpha[j] = a_j; p.beta[j] = b_j; }
+    m_eff = j + 1;
+    if (!(b_j > 1e-13) || j + 1 == p.m) break;  // invariant subspace / done (uniform across the grid)
+    double* vn = p.V + (size_t)(j + 1) * K;
+    for (int e = gtid; e < K; e += gthreads) {
+      const double v = __ldcg(p.w + e) / b_j;
+      vn[e] = v;
+      const double pe = p.pi[e];
+      p.z[e] = pe > 0.0 ? v / sqrt(pe) : 0.0;
+    }
+    grid.sync();
+  }
+  grid.sync();
+  if (blockIdx.x != 0) return;
+  // Ritz values of T_m and of a shorter recurrence, CTA 0 only
+  const int m2 = m_eff - (m_eff / 8 > 1 ? m_eff / 8 : 1);
+  double* r1 = p.ritz;
+  double* r2 = p.ritz + p.m;
+  for (int i = tid; i < m_eff; i += blockDim.x) { r1[i] = 0.0; r2[i] = 0.0; }
+  __syncthreads();
+  tridiag_bisect(p.alpha, p.beta, m_eff, r1);
+  if (m2 >= 1) tridiag_bisect(p.alpha, p.beta, m2, r2);
+  __syncthreads();
+  // top-k by magnitude of each set (m_eff <= 1024 guaranteed by the launcher)
+  auto rank = [&](const double* vals, int n, int* order) {
+    for (int jj = tid; jj < n; jj += blockDim.x) {
+      const double aj = fabs(vals[jj]);
+      int rk = 0;
+      for (int i = 0; i < n; ++i) {
+        const double ai = fabs(vals[i]);
+        rk += (ai > aj) || (ai == aj && i < jj);
+      }
+      order[rk] = jj;
+    }
+    __syncthreads();
+  };
+  rank(r1, m_eff, s_order);
+  int ok = 1;
+  for (int t = tid; t < p.k; t += blockDim.x) p.evals[t] = (t < m_eff) ? r1[s_order[t]] : 0.0;
+  __syncthreads();
+  if (m2 >= 1) {
+    rank(r2, m2, s_order);
+    for (int t = tid; t < p.k && t < m2; t += blockDim.x) {
+      const double a = p.evals[t], b = r2[s_order[t]];
+      if (fabs(a - b) > 1e-10 * fmax(1.0, fabs(a))) ok = 0;
+    }
+  }
+  ok = __syncthreads_and(ok);
+  if (m_eff >= K || m_eff < p.m) ok = 1;  // exhausted the (active) space: Ritz values are exact
+  if (tid == 0) { p.info[0] = m_eff; p.info[1] = ok; }
+}
+
+static int lanczos_steps(int K, int k, int max_steps) {
+  int m = max_steps > 0 ? max_steps : (10 * k > 200 ? 10 * k : 200);
+  if (m > K) m = K;
+  if (m > 1024) m = 1024;
+  return m;
+}
+
+}  // namespace pmb
+
+extern "C" size_t pmb_eig_rev_topk_ws_bytes(int K, int k, int batch, int max_steps) {
+  using namespace pmb;
+  if (K <= 0 || k <= 0 || batch <= 0) return 0;
+  if (K <= kEigJacobiMaxK)
+    return ((size_t)batch * K * K + 2 * (size_t)batch * K) * sizeof(double) + (size_t)batch * K * sizeof(int) + 64;
+  const int m = lanczos_steps(K, k, max_steps);
+  return ((size_t)(m + 1) * K + 2 * (size_t)K + 2 * (size_t)(m + 1) + 4 * (size_t)m + 1024) * sizeof(double);
+}
+
+extern "C" int pmb_eig_rev_topk(const double* T, const double* pi, int K, int k, int batch, int max_steps,
+                                double* evals, int64_t* info, void* ws, size_t ws_bytes,
+                                pmb_stream_t stream) {
+  using namespace pmb;
+  PMB_REQUIRE(K > 0 && k > 0 && batch > 0, "pmb_eig_rev_topk: bad sizes");
+  PMB_REQUIRE(T && pi && evals && info && ws, "pmb_eig_rev_topk: null pointer");
+  if (ws_bytes < pmb_eig_rev_topk_ws_bytes(K, k, batch, max_steps)) {
+    set_error("pmb_eig_rev_topk: workspace too small");
+    return PMB_EWORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (K <= kEigJacobiMaxK) {
+    double* A = static_cast<double*>(ws);
+    double* full = A + (size_t)batch * K * K;
+    double* scratch = full + (size_t)batch * K;
+    int* order = reinterpret_cast<int*>(scratch + (size_t)batch * K);
+    dim3 b(16, 16), g((K + 15) / 16, (K + 15) / 16, batch);
+    eig_build_sym_kernel<<<g, b, 0, st>>>(T, pi, K, A);
+    PMB_LAUNCH_CHECK();
+    int rc = sym_eigvals_launch(A, K, batch, full, scratch, order, st);
+    if (rc != PMB_OK) return rc;
+    eig_take_topk_kernel<<<batch, 128, 0, st>>>(full, K, k, evals, reinterpret_cast<long long*>(info));
+    PMB_LAUNCH_CHECK();
+    return PMB_OK;
+  }
+  const int m = lanczos_steps(K, k, max_steps);
+  int dev = 0, sms = 0, per_sm = 0;
+  PMB_CUDA(cudaGetDevice(&dev));
+  PMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_kernel, kLanThreads, 0));
+  PMB_REQUIRE(per_sm >= 1, "pmb_eig_rev_topk: kernel does not fit on an SM");
+  int grid = (K + (kLanThreads / 32) - 1) / (kLanThreads / 32);
+  if (grid > sms) grid = sms;
+  for (int b = 0; b < batch; ++b) {
+    LanParams p;
+    p.T = T + (size_t)b * K * K;
+    p.pi = pi + (size_t)b * K;
+    p.K = K; p.k = k; p.m = m;
+    p.evals = evals + (size_t)b * k;
+    p.info = reinterpret_cast<long long*>(info) + 2 * b;
+    double* base = static_cast<double*>(ws);
+    p.V = base;
+    p.w = p.V + (size_t)(m + 1) * K;
+    p.z = p.w + K;
+    p.h = p.z + K;
+    p.alpha = p.h + 2 * (size_t)(m + 1);
+    p.beta = p.alpha + m;
+    p.ritz = p.beta + m;
+    p.part = p.ritz + 2 * (size_t)m;
+    void* args[] = {&p};
+    PMB_CUDA(cudaLaunchCooperativeKernel((void*)lanczos_kernel, dim3(grid), dim3(kLanThreads), args, 0, st));
+    count_launch();
+  }
+  return PMB_OK;
+}

@@ -1,0 +1,368 @@
+// mle.cu -- K8: reversible maximum-likelihood transition matrix (fixed point on
+// the row-sum vector, matrix-free).
+//
+//   S = C + C^T, c_i = sum_j C_ij, x^0 = rowsum(S)/sum(S)
+//   q_i = c_i / x_i
+//   u_i = sum_j S_ij / (q_i + q_j);  x' = u / sum(u)
+//   err = max_i |x_i - x'_i| / (0.5 (x_i + x'_i));  stop err <= maxerr or maxiter
+//   T_ij = (S_ij / (q_i + q_j)) / rs_i,  pi = rs / sum(rs)   with rs from the final x
+//
+// Only the K-vector x feeds back, so one iteration is ONE streaming pass over S
+// (8 K^2 bytes, fp64).  Two kernels:
+//  * one CTA per problem (batched; K <= kMleCtaMaxK): x, q, u live in shared
+//    memory, S is re-read from L2, barriers are __syncthreads -- this is the
+//    ITS sweep path (one CTA per lag time);
+//  * one cooperative grid per problem (large K): rows are spread over all SMs,
+//    u goes through a global double buffer and ONE grid barrier per iteration;
+//    every CTA recomputes the normalisation and the error in the same order, so
+//    all CTAs take the same branch without a second barrier.
+// All reductions have a fixed order: results are bit-reproducible run to run.
+// A state with active[i] == 0 is excluded (T_ii = 1, pi_i = 0), which is how the
+// caller restricts the estimate to the largest connected set without
+// re-packing the count matrix.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace pmb {
+
+constexpr int kMleThreads = 1024;
+constexpr int kMleCtaMaxK = 2048;
+constexpr int kMleGridThreads = 512;
+
+struct MleParams {
+  const double* C;        // batch x K x K
+  const uint8_t* active;  // batch x K or nullptr
+  int K;
+  double alpha;           // pseudocount added to every cell of the active block
+  double maxerr;
+  long long maxiter;
+  double* T;              // batch x K x K
+  double* pi;             // batch x K
+  long long* info;        // batch x 2
+  double* S;              // batch x K x K workspace
+  double* cvec;           // batch x K workspace
+  double* ubuf;           // 2 x K (grid kernel only)
+};
+
+// deterministic CTA-wide sum / max; every thread gets the result
+__device__ __forceinline__ double cta_sum(double v, double* s_red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < nw; ++w) r += s_red[w];
+  return r;
+}
+__device__ __forceinline__ double cta_max(double v, double* s_red) {
+  v = warp_max(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < nw; ++w) r = fmax(r, s_red[w]);
+  return r;
+}
+
+// S = mask(C + C^T), c = masked row sums of C.  grid: (ceil(K/32), ceil(K/32), batch)
+__global__ void mle_prepare_kernel(MleParams p) {
+  __shared__ double tile[32][33];
+  const int K = p.K;
+  const size_t base = (size_t)blockIdx.z * K * K;
+  const uint8_t* act = p.active ? p.active + (size_t)blockIdx.z * K : nullptr;
+  const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj + r, j = bi + tx;  // transposed block
+    tile[r][tx] = (i < K && j < K) ? p.C[base + (size_t)i * K + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi + r, j = bj + tx;
+    if (i < K && j < K) {
+      const bool on = !act || (act[i] && act[j]);
+      p.S[base + (size_t)i * K + j] =
+          on ? (p.C[base + (size_t)i * K + j] + p.alpha) + (tile[tx][r] + p.alpha) : 0.0;
+    }
+  }
+}
+__global__ void mle_rowsum_kernel(MleParams p) {
+  const int K = p.K;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= K) return;
+  const size_t base = (size_t)blockIdx.y * K * K;
+  const uint8_t* act = p.active ? p.active + (size_t)blockIdx.y * K : nullptr;
+  double acc = 0.0;
+  if (!act || act[warp])
+    for (int j = lane; j < K; j += 32)
+      if (!act || act[j]) acc += p.C[base + (size_t)warp * K + j] + p.alpha;
+  acc = warp_sum(acc);
+  if (lane == 0) p.cvec[(size_t)blockIdx.y * K + warp] = acc;
+}
+
+__device__ __forceinline__ double row_apply(const double* __restrict__ Srow, const double* q, double qi,
+                                            int K, int lane) {
+  double acc = 0.0;
+  for (int j = lane; j < K; j += 32) {
+    const double s = Srow[j];
+    if (s != 0.0) acc += s / (qi + q[j]);
+  }
+  return warp_sum(acc);
+}
+
+// ---------------------------------------------------------------- one CTA per problem
+__global__ void __launch_bounds__(kMleThreads) mle_cta_kernel(MleParams p) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double s_red[32];
+  const int K = p.K;
+  double* x = sm;
+  double* q = sm + K;
+  double* u = sm + 2 * K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const size_t b = blockIdx.x;
+  const double* S = p.S + b * K * K;
+  const double* c = p.cvec + b * K;
+  const uint8_t* act = p.active ? p.active + b * K : nullptr;
+
+  // x0 = rowsum(S) / sum(S); validity
+  int bad = 0;
+  for (int i = warp; i < K; i += nw) {
+    double acc = 0.0;
+    for (int j = lane; j < K; j += 32) acc += S[(size_t)i * K + j];
+    acc = warp_sum(acc);
+    if (lane == 0) u[i] = acc;
+  }
+  __syncthreads();
+  double part = 0.0;
+  for (int i = tid; i < K; i += blockDim.x) {
+    part += u[i];
+    const bool on = !act || act[i];
+    if (on && !(c[i] > 0.0)) bad = 1;
+  }
+  const double tot = cta_sum(part, s_red);
+  bad = __syncthreads_or(bad);
+  if (bad || !(tot > 0.0)) {
+    if (tid == 0) { p.info[2 * b] = 0; p.info[2 * b + 1] = -1; }
+    return;
+  }
+  for (int i = tid; i < K; i += blockDim.x) x[i] = u[i] / tot;
+  __syncthreads();
+
+  long long it = 0;
+  double err = 1.7976931348623157e308;
+  while (it < p.maxiter && err > p.maxerr) {
+    for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] / x[i] : 0.0;
+    __syncthreads();
+    for (int i = warp; i < K; i += nw) {
+      double r = 0.0;
+      if (x[i] > 0.0) r = row_apply(S + (size_t)i * K, q, q[i], K, lane);
+      if (lane == 0) u[i] = r;
+    }
+    __syncthreads();
+    part = 0.0;
+    for (int i = tid; i < K; i += blockDim.x) part += u[i];
+    const double norm = cta_sum(part, s_red);
+    double e = 0.0;
+    for (int i = tid; i < K; i += blockDim.x) {
+      const double xo = x[i], xn = u[i] / norm;
+      if (xo > 0.0 || xn > 0.0) e = fmax(e, fabs(xo - xn) / (0.5 * (xo + xn)));
+      x[i] = xn;
+    }
+    err = cta_max(e, s_red);
+    ++it;
+  }
+  // final application with the converged x
+  for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] / x[i] : 0.0;
+  __syncthreads();
+  double* T = p.T + b * K * K;
+  for (int i = warp; i < K; i += nw) {
+    const bool on = x[i] > 0.0;
+    double rs = 0.0;
+    if (on) rs = row_apply(S + (size_t)i * K, q, q[i], K, lane);
+    if (lane == 0) u[i] = rs;
+    const double qi = q[i];
+    for (int j = lane; j < K; j += 32) {
+      double t;
+      if (on && rs > 0.0) {
+        const double s = S[(size_t)i * K + j];
+        t = (s != 0.0) ? (s / (qi + q[j])) / rs : 0.0;
+      } else {
+        t = (i == j) ? 1.0 : 0.0;
+      }
+      T[(size_t)i * K + j] = t;
+    }
+  }
+  __syncthreads();
+  part = 0.0;
+  for (int i = tid; i < K; i += blockDim.x) part += u[i];
+  const double rtot = cta_sum(part, s_red);
+  for (int i = tid; i < K; i += blockDim.x) p.pi[b * K + i] = u[i] / rtot;
+  if (tid == 0) { p.info[2 * b] = it; p.info[2 * b + 1] = (err <= p.maxerr) ? 1 : 0; }
+}
+
+// ---------------------------------------------------------------- cooperative grid, one problem
+__global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double s_red[32];
+  const int K = p.K;
+  double* x = sm;
+  double* q = sm + K;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + tid) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const double* S = p.S;
+  const double* c = p.cvec;
+  const uint8_t* act = p.active;
+  double* u0 = p.ubuf;
+  double* u1 = p.ubuf + K;
+
+  for (int i = gwarp; i < K; i += nwarps) {
+    double acc = 0.0;
+    for (int j = lane; j < K; j += 32) acc += S[(size_t)i * K + j];
+    acc = warp_sum(acc);
+    if (lane == 0) u0[i] = acc;
+  }
+  grid.sync();
+  double part = 0.0;
+  int bad = 0;
+  for (int i = tid; i < K; i += blockDim.x) {
+    part += u0[i];
+    const bool on = !act || act[i];
+    if (on && !(c[i] > 0.0)) bad = 1;
+  }
+  const double tot = cta_sum(part, s_red);
+  bad = __syncthreads_or(bad);
+  if (bad || !(tot > 0.0)) {  // uniform across the grid: every CTA sees the same data
+    if (blockIdx.x == 0 && tid == 0) { p.info[0] = 0; p.info[1] = -1; }
+    return;
+  }
+  for (int i = tid; i < K; i += blockDim.x) x[i] = u0[i] / tot;
+  __syncthreads();
+
+  long long it = 0;
+  double err = 1.7976931348623157e308;
+  double* ucur = u1;
+  while (it < p.maxiter && err > p.maxerr) {
+    for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] / x[i] : 0.0;
+    __syncthreads();
+    for (int i = gwarp; i < K; i += nwarps) {
+      double r = 0.0;
+      if (x[i] > 0.0) r = row_apply(S + (size_t)i * K, q, q[i], K, lane);
+      if (lane == 0) ucur[i] = r;
+    }
+    grid.sync();
+    part = 0.0;
+    for (int i = tid; i < K; i += blockDim.x) part += __ldcg(ucur + i);
+    const double norm = cta_sum(part, s_red);
+    double e = 0.0;
+    for (int i = tid; i < K; i += blockDim.x) {
+      const double xo = x[i], xn = __ldcg(ucur + i) / norm;
+      if (xo > 0.0 || xn > 0.0) e = fmax(e, fabs(xo - xn) / (0.5 * (xo + xn)));
+      x[i] = xn;
+    }
+    err = cta_max(e, s_red);
+    ++it;
+    ucur = (ucur == u1) ? u0 : u1;
+  }
+  for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] / x[i] : 0.0;
+  __syncthreads();
+  for (int i = gwarp; i < K; i += nwarps) {
+    const bool on = x[i] > 0.0;
+    double rs = 0.0;
+    if (on) rs = row_apply(S + (size_t)i * K, q, q[i], K, lane);
+    if (lane == 0) ucur[i] = rs;
+    const double qi = q[i];
+    for (int j = lane; j < K; j += 32) {
+      double t;
+      if (on && rs > 0.0) {
+        const double s = S[(size_t)i * K + j];
+        t = (s != 0.0) ? (s / (qi + q[j])) / rs : 0.0;
+      } else {
+        t = (i == j) ? 1.0 : 0.0;
+      }
+      p.T[(size_t)i * K + j] = t;
+    }
+  }
+  grid.sync();
+  part = 0.0;
+  for (int i = tid; i < K; i += blockDim.x) part += __ldcg(ucur + i);
+  const double rtot = cta_sum(part, s_red);
+  for (int i = blockIdx.x * blockDim.x + tid; i < K; i += gridDim.x * blockDim.x)
+    p.pi[i] = __ldcg(ucur + i) / rtot;
+  if (blockIdx.x == 0 && tid == 0) { p.info[0] = it; p.info[1] = (err <= p.maxerr) ? 1 : 0; }
+}
+
+}  // namespace pmb
+
+extern "C" size_t pmb_mle_rev_ws_bytes(int K, int batch) {
+  if (K <= 0 || batch <= 0) return 0;
+  return ((size_t)batch * K * K + (size_t)batch * K + 2 * (size_t)K) * sizeof(double) + 64;
+}
+
+extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int batch, double alpha, double maxerr,
+                           int64_t maxiter, double* T, double* pi, int64_t* info, void* ws,
+                           size_t ws_bytes, pmb_stream_t stream) {
+  using namespace pmb;
+  PMB_REQUIRE(K > 0 && batch > 0 && maxiter >= 0 && alpha >= 0.0, "pmb_mle_rev: bad sizes");
+  PMB_REQUIRE(C && T && pi && info && ws, "pmb_mle_rev: null pointer");
+  if (ws_bytes < pmb_mle_rev_ws_bytes(K, batch)) {
+    set_error("pmb_mle_rev: workspace too small (%zu < %zu)", ws_bytes, pmb_mle_rev_ws_bytes(K, batch));
+    return PMB_EWORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  MleParams p;
+  p.C = C; p.active = active; p.K = K; p.alpha = alpha; p.maxerr = maxerr; p.maxiter = maxiter;
+  p.T = T; p.pi = pi; p.info = reinterpret_cast<long long*>(info);
+  p.S = static_cast<double*>(ws);
+  p.cvec = p.S + (size_t)batch * K * K;
+  p.ubuf = p.cvec + (size_t)batch * K;
+  {
+    dim3 g((K + 31) / 32, (K + 31) / 32, batch), b(32, 8);
+    mle_prepare_kernel<<<g, b, 0, st>>>(p);
+    PMB_LAUNCH_CHECK();
+    dim3 g2((K * 32 + 255) / 256, batch);
+    mle_rowsum_kernel<<<g2, 256, 0, st>>>(p);
+    PMB_LAUNCH_CHECK();
+  }
+  const bool use_cta = (K <= kMleCtaMaxK) && (batch > 1 || K <= 384);
+  if (use_cta) {
+    const size_t smem = (size_t)3 * K * sizeof(double);
+    PMB_CUDA(cudaFuncSetAttribute(mle_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mle_cta_kernel<<<batch, kMleThreads, smem, st>>>(p);
+    PMB_LAUNCH_CHECK();
+    return PMB_OK;
+  }
+  const size_t smem = (size_t)2 * K * sizeof(double);
+  PMB_REQUIRE(smem <= 200 * 1024, "pmb_mle_rev: K=%d too large", K);
+  PMB_CUDA(cudaFuncSetAttribute(mle_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mle_grid_kernel, kMleGridThreads, smem));
+  PMB_REQUIRE(per_sm >= 1, "pmb_mle_rev: kernel does not fit on an SM");
+  int dev = 0, sms = 0;
+  PMB_CUDA(cudaGetDevice(&dev));
+  PMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int warps_per_cta = kMleGridThreads / 32;
+  int grid = (K + warps_per_cta - 1) / warps_per_cta;
+  if (grid > sms * per_sm) grid = sms * per_sm;
+  if (grid > sms) grid = sms;  // one CTA per SM keeps the barrier cheap
+  for (int b = 0; b < batch; ++b) {
+    MleParams pb = p;
+    pb.active = active ? active + (size_t)b * K : nullptr;
+    pb.T = T + (size_t)b * K * K;
+    pb.pi = pi + (size_t)b * K;
+    pb.info = p.info + 2 * b;
+    pb.S = p.S + (size_t)b * K * K;
+    pb.cvec = p.cvec + (size_t)b * K;
+    void* args[] = {&pb};
+    PMB_CUDA(cudaLaunchCooperativeKernel((void*)mle_grid_kernel, dim3(grid), dim3(kMleGridThreads), args,
+                                         smem, st));
+    count_launch();
+  }
+  return PMB_OK;
+}

@@ -1,0 +1,158 @@
+"""End-to-end MSM estimation on a frame shard, device resident.
+
+featurize -> (scaler) -> TICA fit + project -> k-means (Lloyd) -> lagged counts
+-> reversible MLE -> leading eigenvalues -> implied timescales: the chain
+``compute_features -> reduce_features -> cluster_microstates ->
+build_msm_from_labels`` of src/pmarlo/api/conformations.py:192-200 (call stack
+(A) of SURVEY.md section 3), with the trajectories ("shards") dealt to one
+process per GPU and the small partials summed over ranks.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import kernels
+from .clustering import lloyd_device
+from .distributed import Comm
+from .features import FeaturePlan, featurize_device
+from .msm import msm_from_counts_device, safe_timescales
+from .reduction import TICA, TicaModel
+from .shards import Segments
+from .timing import NULL_TIMER, StageTimer
+
+__all__ = ["PipelineConfig", "PipelineResult", "StageTimer", "run_pipeline", "seeded_initial_centers",
+           "estimate_msm_from_host"]
+
+
+@dataclass
+class PipelineConfig:
+    tica_lag: int = 10
+    tica_dim: int = 2
+    preprocess: str | None = "standard"
+    n_states: int = 100
+    kmeans_max_iter: int = 500
+    kmeans_tolerance: float | None = 1e-5     # None: run exactly kmeans_max_iter iterations
+    msm_lag: int = 10
+    n_timescales: int = 5
+    dirichlet_alpha: float = 1e-3             # src/pmarlo/constants.py:44
+    mle_maxerr: float = 1e-8
+    mle_maxiter: int = 1_000_000
+    gram_impl: int = 0
+    seed: int = 0
+
+
+@dataclass
+class PipelineResult:
+    features: torch.Tensor | None
+    tica: TicaModel | None
+    Y: torch.Tensor
+    centers: torch.Tensor
+    labels: torch.Tensor
+    counts: torch.Tensor
+    T: torch.Tensor
+    pi: torch.Tensor
+    active: torch.Tensor
+    mle_info: torch.Tensor
+    eigenvalues: torch.Tensor
+    timescales: np.ndarray | None = None
+    kmeans_iters: int = 0
+    extra: dict = field(default_factory=dict)
+
+
+def seeded_initial_centers(Y: torch.Tensor, K: int, seed: int, comm: Comm) -> torch.Tensor:
+    """K distinct frames of rank 0's shard chosen by a seeded permutation, broadcast
+    to every rank (the ``initial_centers=`` kwarg of clustering.py:243-250)."""
+    centers = torch.empty((K, int(Y.shape[1])), dtype=torch.float64, device=Y.device)
+    if comm.rank == 0:
+        n = int(Y.shape[0])
+        if n < K:
+            raise ValueError(f"rank 0 holds {n} frames, fewer than n_states={K}")
+        g = torch.Generator(device="cpu")
+        g.manual_seed(int(seed))
+        idx = torch.randperm(n, generator=g)[:K].sort().values.to(Y.device)
+        centers.copy_(Y.index_select(0, idx).to(torch.float64))
+    comm.broadcast(centers, src=0)
+    return centers
+
+
+def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | None, cfg: PipelineConfig,
+                 comm: Comm | None = None, features: torch.Tensor | None = None,
+                 initial_centers: torch.Tensor | None = None, timer: StageTimer | None = None,
+                 read_back: bool = True) -> PipelineResult:
+    """Run the whole path on this rank's shard.  Either ``xyz`` (+ ``plan``) or
+    precomputed ``features`` (N,d) float32 must be given; with ``cfg.tica_dim <= 0``
+    the features are clustered directly (config C2: 2-D Mueller-Brown data)."""
+    comm = comm if comm is not None else Comm()
+    timer = timer if timer is not None else NULL_TIMER
+    dev = (xyz if xyz is not None else features).device
+    off = segs.device(dev)
+
+    if features is None:
+        with timer.stage("featurize"):
+            features = featurize_device(xyz, plan)
+    X = features
+
+    tica_model = None
+    if cfg.tica_dim > 0:
+        with timer.stage("tica_fit"):
+            est = TICA(cfg.tica_lag, cfg.tica_dim, preprocess=cfg.preprocess, comm=comm, gram_impl=cfg.gram_impl)
+            tica_model = est.fit_device(X, segs, off, timer=timer)
+        with timer.stage("project"):
+            Y = est.transform_device(tica_model, X, out_f64=False)
+    else:
+        Y = X
+
+    with timer.stage("kmeans"):
+        if initial_centers is None:
+            initial_centers = seeded_initial_centers(Y, cfg.n_states, cfg.seed, comm)
+        labels = torch.empty((int(Y.shape[0]),), dtype=torch.int32, device=dev)
+        res = lloyd_device(Y, initial_centers, cfg.kmeans_max_iter, cfg.kmeans_tolerance, comm, labels=labels,
+                           timer=timer)
+        # final labels against the final centres (model.transform, clustering.py:609)
+        with timer.stage("kmeans_assign"):
+            kernels.kmeans_assign(Y, res.centers, labels=labels)
+
+    with timer.stage("count"):
+        C = torch.zeros((cfg.n_states, cfg.n_states), dtype=torch.int64, device=dev)
+        kernels.count_lagged(labels, off, cfg.n_states, cfg.msm_lag, 1, out=C)
+        comm.allreduce_sum(C)
+
+    with timer.stage("mle"):
+        T, pi, info, active = msm_from_counts_device(C, alpha=cfg.dirichlet_alpha, maxerr=cfg.mle_maxerr,
+                                                     maxiter=cfg.mle_maxiter)
+    with timer.stage("eig"):
+        k = min(cfg.n_timescales + 1, cfg.n_states)
+        ev, ev_info = kernels.eig_rev_topk(T, pi, k)
+
+    ts = None
+    if read_back:
+        ts = safe_timescales(cfg.msm_lag, ev.cpu().numpy()[1:])
+    return PipelineResult(features=X, tica=tica_model, Y=Y, centers=res.centers, labels=labels, counts=C,
+                          T=T, pi=pi, active=active, mle_info=info, eigenvalues=ev, timescales=ts,
+                          kmeans_iters=res.n_iter, extra={"eig_info": ev_info})
+
+
+def estimate_msm_from_host(xyz_host, lengths, plan: FeaturePlan, cfg: PipelineConfig, comm: Comm | None = None,
+                           device=None) -> dict:
+    """The call a user of the host-buffer API makes: coordinates of this rank's
+    trajectories in (pinned) host memory -> timescales, eigenvalues, stationary
+    vector and MLE diagnostics as numpy arrays.  The host->device copy of the
+    coordinates and the device->host read of the results happen inside."""
+    device = device if device is not None else kernels.require_cuda()
+    if isinstance(xyz_host, np.ndarray):
+        xyz_host = torch.from_numpy(np.ascontiguousarray(xyz_host, dtype=np.float32))
+    xyz = xyz_host.to(device, non_blocking=True)
+    segs = Segments.from_lengths(lengths)
+    if segs.n_frames != int(xyz.shape[0]):
+        raise ValueError("lengths do not add up to the number of frames")
+    res = run_pipeline(xyz, segs, plan, cfg, comm, read_back=False)
+    ev = res.eigenvalues.cpu().numpy()
+    pi = res.pi.cpu().numpy()
+    info = res.mle_info.cpu().numpy()
+    ts = safe_timescales(cfg.msm_lag, ev[1:])
+    return {"timescales": ts, "eigenvalues": ev, "stationary_distribution": pi, "mle_info": info,
+            "d2h_bytes": int(ev.nbytes + pi.nbytes + info.nbytes)}

@@ -1,0 +1,218 @@
+"""Preprocessing + TICA behind pmarlo's signatures (K2-K5 on the device).
+
+Mirrors
+* ``_preprocess`` / ``tica_reduce(X, lag, n_components, scale)``
+      src/pmarlo/markov_state_model/reduction.py:13-40,77-110
+* ``reduce_features(X, method, lag, n_components)``   src/pmarlo/api/features.py:468-481
+* ``FeaturesMixin._maybe_apply_tica(n_components_hint, lag)``
+      src/pmarlo/markov_state_model/_features.py:181-231
+* ``train_cv_model(features, lag_time, n_components, method="tica")``  src/pmarlo/cv/__init__.py:42-50
+
+deeptime ``TICA(lagtime, dim)`` semantics (defaults epsilon=1e-6,
+scaling="kinetic_map", reversible symmetrised covariances, no Bessel): one pass
+of column moments, two tensor/SIMT Gram passes over the conditioned data, an
+fp64 assembly that undoes the conditioning exactly, a Jacobi eigen-solve on the
+device, and a bandwidth-bound projection.  The scaler (mean-impute + z-score)
+is folded into the projection operands, so the features are read three times
+and never rewritten.
+"""
+
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import kernels
+from .distributed import Comm
+from .shards import Segments, concat_to_device
+from .timing import NULL_TIMER
+
+logger = logging.getLogger("pmarlo")
+
+__all__ = ["TicaModel", "TICA", "tica_reduce", "reduce_features", "maybe_apply_tica", "train_cv_model",
+           "preprocess"]
+
+
+@dataclass
+class TicaModel:
+    """Fitted model; every tensor lives on the device."""
+
+    lag: int
+    dim: int
+    n_frames: int
+    n_pairs: int
+    moments: torch.Tensor      # (6,d)
+    stats: torch.Tensor        # (3,d): mean, scale, sample std
+    C00: torch.Tensor          # (d,d) in preprocessed units
+    C0t: torch.Tensor
+    mu: torch.Tensor           # pair mean (preprocessed units)
+    eigenvalues: torch.Tensor  # (d,), sorted by magnitude; entries >= rank are 0
+    eigenvectors: torch.Tensor  # (d,d) unscaled generalized eigenvectors R (columns)
+    rank_dev: torch.Tensor     # int32[1]
+    a: torch.Tensor            # projection offset (raw units)
+    nanfill: torch.Tensor      # imputation value per column
+    W: torch.Tensor            # (d, dim) projection matrix (raw units)
+
+    @property
+    def rank(self) -> int:
+        return int(self.rank_dev.item())
+
+    @property
+    def output_dim(self) -> int:
+        return min(self.dim, self.rank)
+
+
+class TICA:
+    """``preprocess``: "standard" (mean-impute + z-score, reduction.py:13-40 with
+    scale=True), "center" (scale=False) or None (raw features, _features.py:181-231)."""
+
+    def __init__(self, lagtime: int, dim: int | None = None, epsilon: float = 1e-6,
+                 scaling: str | None = "kinetic_map", preprocess: str | None = None,
+                 comm: Comm | None = None, gram_impl: int = 0):
+        if int(lagtime) < 1:
+            raise ValueError("lagtime must be >= 1")
+        if scaling not in (None, "kinetic_map", "km"):
+            raise ValueError(f"unsupported scaling {scaling!r}")
+        if preprocess not in (None, "standard", "center"):
+            raise ValueError(f"unsupported preprocess {preprocess!r}")
+        self.lagtime, self.dim, self.epsilon = int(lagtime), dim, float(epsilon)
+        self.scaling, self.preprocess = scaling, preprocess
+        self.comm = comm if comm is not None else Comm()
+        self.gram_impl = int(gram_impl)
+
+    def fit_device(self, X: torch.Tensor, segs: Segments, seg_offsets_dev: torch.Tensor | None = None,
+                   timer=NULL_TIMER) -> TicaModel:
+        n_local, d = int(X.shape[0]), int(X.shape[1])
+        comm, lag = self.comm, self.lagtime
+        dev = X.device
+        off = seg_offsets_dev if seg_offsets_dev is not None else segs.device(dev)
+        n = comm.sum_int(n_local, dev)
+        n_pairs = comm.sum_int(segs.n_pairs(lag), dev)
+        if n_pairs <= 0:
+            raise ValueError("no trajectory longer than the lag time")
+        mask = kernels.pair_mask(off, n_local, lag)
+        shift = None
+        if comm.size > 1:
+            shift = torch.nan_to_num(X[0].to(torch.float64), nan=0.0).contiguous()
+            comm.broadcast(shift, src=0)
+        with timer.stage("col_moments"):
+            moments = kernels.col_moments(X, mask, shift)
+        if comm.size > 1:
+            comm.allreduce_sum(moments)
+            moments[1].copy_(shift)
+        semantic = 0 if self.preprocess is None else 1
+        with_std = 1 if self.preprocess == "standard" else 0
+        stats, cond = kernels.scaler_from_moments(moments, n, semantic, with_std)
+        G = torch.empty((2, d, d), dtype=torch.float64, device=dev)
+        with timer.stage("gram"):
+            kernels.gram(X, mask, lag, 0, cond, self.gram_impl, out=G[0])
+        with timer.stage("gram"):
+            kernels.gram(X, mask, lag, 1, cond, self.gram_impl, out=G[1])
+        comm.allreduce_sum(G)
+        C00, C0t, mu = kernels.tica_covariances(G[0], G[1], moments, stats, cond, n, n_pairs, semantic)
+        with timer.stage("tica_solve"):
+            evals, evecs, rank = kernels.tica_solve(C00, C0t, self.epsilon)
+        dim = d if self.dim is None else int(self.dim)
+        dim = max(1, min(dim, d))
+        a, nanfill, W = kernels.tica_finalize(evals, evecs, moments, stats, mu, dim,
+                                              self.scaling in ("kinetic_map", "km"))
+        return TicaModel(lag, dim, n, n_pairs, moments, stats, C00, C0t, mu, evals, evecs, rank, a,
+                         nanfill, W)
+
+    @staticmethod
+    def transform_device(model: TicaModel, X: torch.Tensor, out_f64: bool = False,
+                         out: torch.Tensor | None = None) -> torch.Tensor:
+        return kernels.project(X, model.a, model.nanfill, model.W, out_f64=out_f64, out=out)
+
+    # numpy convenience (list of per-trajectory arrays, like deeptime's fit(list))
+    def fit(self, trajs: Sequence[np.ndarray]) -> TicaModel:
+        dev = kernels.require_cuda()
+        X, segs = concat_to_device(trajs, dev)
+        return self.fit_device(X, segs)
+
+    def fit_transform(self, trajs: Sequence[np.ndarray]) -> tuple[list[np.ndarray], TicaModel]:
+        dev = kernels.require_cuda()
+        X, segs = concat_to_device(trajs, dev)
+        model = self.fit_device(X, segs)
+        Y = self.transform_device(model, X, out_f64=True)[:, : model.output_dim]
+        return segs.split(Y.cpu().numpy()), model
+
+
+def _as_2d(X) -> tuple[np.ndarray, bool]:
+    Xp = np.asarray(X, dtype=float)
+    if Xp.ndim == 1:
+        return Xp.reshape(-1, 1), True
+    return Xp, False
+
+
+def preprocess(X: np.ndarray, scale: bool = True) -> np.ndarray:
+    """``_preprocess`` (reduction.py:13-40): mean-impute NaNs, centre, optional z-score."""
+    Xp, squeeze = _as_2d(X)
+    if Xp.size == 0:
+        return np.zeros_like(np.asarray(X, dtype=float))
+    dev = kernels.require_cuda()
+    Xd = torch.from_numpy(np.ascontiguousarray(Xp, dtype=np.float32)).to(dev)
+    moments = kernels.col_moments(Xd)
+    stats, _ = kernels.scaler_from_moments(moments, Xd.shape[0], 1, 1 if scale else 0)
+    d = Xd.shape[1]
+    eye = torch.eye(d, dtype=torch.float64, device=dev)
+    nv, sh, s1 = moments[0], moments[1], moments[2]
+    nanfill = torch.where(nv > 0, sh + s1 / torch.clamp(nv, min=1.0), torch.zeros_like(sh))
+    W = (eye / stats[1][:, None]).contiguous()
+    out = kernels.project(Xd, stats[0].contiguous(), nanfill.contiguous(), W, out_f64=True)
+    res = out.cpu().numpy()
+    return res.reshape(-1) if squeeze else res
+
+
+def tica_reduce(X: np.ndarray, lag: int = 1, n_components: int = 2, scale: bool = True) -> np.ndarray:
+    """Drop-in for ``pmarlo.markov_state_model.reduction.tica_reduce``."""
+    Xp, _ = _as_2d(X)
+    est = TICA(lagtime=lag, dim=n_components, preprocess="standard" if scale else "center")
+    dev = kernels.require_cuda()
+    Xd = torch.from_numpy(np.ascontiguousarray(Xp, dtype=np.float32)).to(dev)
+    segs = Segments.from_lengths([Xd.shape[0]])
+    model = est.fit_device(Xd, segs)
+    Y = est.transform_device(model, Xd, out_f64=True)[:, : model.output_dim]
+    return np.asarray(Y.cpu().numpy(), dtype=float)
+
+
+def reduce_features(X: np.ndarray, method: str = "tica", lag: int = 10, n_components: int = 2) -> np.ndarray:
+    """Drop-in for ``pmarlo.api.features.reduce_features`` (TICA branch; PCA / VAMP
+    are outside the north-star path and are not silently emulated)."""
+    if method == "tica":
+        return tica_reduce(X, lag=lag, n_components=n_components)
+    if method in ("pca", "vamp"):
+        raise NotImplementedError(f"reduce_features(method={method!r}) is outside the B200 hot path")
+    raise ValueError(f"Unknown reduction method: {method}")
+
+
+def maybe_apply_tica(features: np.ndarray, lengths: Sequence[int], n_components_hint: int | None, lag: int):
+    """``FeaturesMixin._maybe_apply_tica``: fit on the list of trajectories, dim
+    clamped to [2,5], the last ``lag`` frames of every trajectory dropped.
+    Returns ``(Y, n_components, kept_lengths)``."""
+    if features is None or n_components_hint is None:
+        return features, None, list(lengths)
+    n_components = int(max(2, min(5, n_components_hint)))
+    lag_eff = int(max(1, lag or 1))
+    dev = kernels.require_cuda()
+    Xd = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32)).to(dev)
+    segs = Segments.from_lengths(lengths)
+    if segs.n_frames != Xd.shape[0]:
+        raise ValueError("lengths do not add up to the number of feature rows")
+    est = TICA(lagtime=lag_eff, dim=n_components, preprocess=None)
+    model = est.fit_device(Xd, segs)
+    Y = est.transform_device(model, Xd, out_f64=True)[:, : model.output_dim].cpu().numpy()
+    keep, new_segs = segs.drop_tail(int(max(0, lag)))
+    logger.info("Total projected arrays stored: %d", len(lengths))
+    return Y[keep], n_components, [int(v) for v in new_segs.lengths]
+
+
+def train_cv_model(features: Sequence[np.ndarray], lag_time: int, n_components: int = 2, method: str = "tica"):
+    """TICA branch of ``pmarlo.cv.train_cv_model`` (cv/__init__.py:42-50)."""
+    if method != "tica":
+        raise NotImplementedError("only method='tica' is on the B200 hot path")
+    return TICA(lagtime=lag_time, dim=n_components).fit(list(features))

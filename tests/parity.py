@@ -1,0 +1,175 @@
+"""Stage-by-stage parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Used by the ``-m gpu`` tests and by ``__graft_entry__.smoke()``.  Tolerances (the
+bar of BASELINE.json's north_star): labels and counts bit-exact given identical
+centroids; covariances, TICA eigenvalues, T, pi, eigenvalues and timescales within
+1e-6 relative of the fp64 oracle; fp32 features (mdtraj computes in fp32) within
+1e-4 rad / 2e-6 relative.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+import oracle
+from pmarlo_b200 import kernels
+from pmarlo_b200.clustering import lloyd_device
+from pmarlo_b200.features import featurize_device, plan_concat, plan_distances, plan_phi_psi, plan_phi_psi_block
+from pmarlo_b200.features import ca_pairs_all
+from pmarlo_b200.msm import msm_from_counts_device, safe_timescales
+from pmarlo_b200.reduction import TICA
+from pmarlo_b200.shards import Segments, concat_to_device
+from tests import synth
+
+REL = 1e-6          # north_star tolerance for fp64 quantities
+ANGLE_ABS = 1e-4    # fp32 atan2 of fp32 coordinates vs fp64 oracle, radians
+DIST_REL = 2e-6     # fp32 sqrt of fp32 differences
+
+
+def rel_err(a, b) -> float:
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(float(np.max(np.abs(b))), 1e-300)
+    return float(np.max(np.abs(a - b))) / scale
+
+
+def angle_err(a, b) -> float:
+    d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))
+    return float(np.max(np.minimum(d, 2 * np.pi - d))) if d.size else 0.0
+
+
+def check_featurize(trajs, top) -> dict:
+    dev = torch.device("cuda")
+    xyz = np.concatenate(trajs, axis=0)
+    xd = torch.from_numpy(xyz).to(dev)
+    ca = top.select_name("CA")
+    pairs = ca_pairs_all(ca)[:40]
+    plan = plan_concat([plan_phi_psi(top), plan_phi_psi_block(top), plan_distances(pairs)])
+    got = featurize_device(xd, plan).cpu().numpy()
+    names, resid, chain = top.names, top.resid, top.chainid
+    phi = oracle.featurize.compute_dihedrals(xyz, oracle.featurize.dihedral_quads(names, resid, chain, "phi"))
+    psi = oracle.featurize.compute_dihedrals(xyz, oracle.featurize.dihedral_quads(names, resid, chain, "psi"))
+    ang = np.concatenate([phi, psi], axis=1)
+    na = ang.shape[1]
+    blk = oracle.featurize.phi_psi_block_features(xyz, names, resid, chain)
+    dist = oracle.featurize.compute_distances(xyz, pairs)
+    e_ang = angle_err(got[:, :na], ang)
+    e_trig = float(np.max(np.abs(got[:, na:na + blk.shape[1]] - blk)))
+    e_dist = rel_err(got[:, na + blk.shape[1]:], dist)
+    assert e_ang <= ANGLE_ABS, f"dihedral angles off by {e_ang}"
+    assert e_trig <= ANGLE_ABS, f"cos/sin off by {e_trig}"
+    assert e_dist <= DIST_REL, f"distances off by {e_dist}"
+    assert np.all(got[:, :na] > -np.pi - 1e-6) and np.all(got[:, :na] <= np.pi + 1e-6)
+    return {"angle_abs": e_ang, "trig_abs": e_trig, "dist_rel": e_dist}
+
+
+def check_tica(feats, lag: int, dim: int, preprocess, gram_impl: int = 0) -> tuple[dict, torch.Tensor, Segments]:
+    dev = torch.device("cuda")
+    X, segs = concat_to_device(feats, dev)
+    est = TICA(lag, dim, preprocess=preprocess, gram_impl=gram_impl)
+    model = est.fit_device(X, segs)
+    Y = est.transform_device(model, X, out_f64=True)
+    # oracle on the same float32 inputs
+    flat = np.concatenate([np.asarray(f, dtype=np.float64) for f in feats], axis=0)
+    if preprocess is None:
+        prepped = [np.asarray(f, dtype=np.float64) for f in feats]
+    else:
+        Z = oracle.tica.preprocess(flat, scale=(preprocess == "standard"))
+        prepped = segs.split(Z)
+    om = oracle.tica.tica_fit(prepped, lag)
+    rep = {
+        "C00_rel": rel_err(model.C00.cpu().numpy(), om.C00),
+        "C0t_rel": rel_err(model.C0t.cpu().numpy(), om.C0t),
+        "mu_abs": float(np.max(np.abs(model.mu.cpu().numpy() - om.mean))),
+        "n_pairs": model.n_pairs,
+    }
+    assert model.n_pairs == om.n_pairs
+    assert model.rank == om.rank, (model.rank, om.rank)
+    r = om.rank
+    ev = model.eigenvalues.cpu().numpy()[:r]
+    rep["eval_rel"] = float(np.max(np.abs(ev - om.eigenvalues[:r]) / np.maximum(np.abs(om.eigenvalues[:r]), 1e-3)))
+    m = min(dim, r)
+    Yo = np.concatenate([oracle.tica.tica_transform(om, p, m) for p in prepped], axis=0)
+    rep["Y_rel"] = rel_err(Y.cpu().numpy()[:, :m], Yo)
+    assert rep["C00_rel"] <= REL and rep["C0t_rel"] <= REL, rep
+    assert rep["mu_abs"] <= REL, rep
+    assert rep["eval_rel"] <= REL, rep
+    assert rep["Y_rel"] <= 5e-6, rep   # eigenvector conditioning: gap-dependent, looser than eigenvalues
+    return rep, Y[:, :m].to(torch.float32).contiguous(), segs
+
+
+def check_kmeans(Y: torch.Tensor, K: int, n_iter: int, seed: int) -> tuple[dict, torch.Tensor]:
+    Yh = Y.cpu().numpy().astype(np.float64)
+    rng = np.random.default_rng(seed)
+    c0 = Yh[np.sort(rng.choice(Yh.shape[0], size=K, replace=False))]
+    # (a) labels bit-exact given identical centroids
+    cd = torch.from_numpy(c0).to(Y.device)
+    nre = torch.zeros((1,), dtype=torch.int64, device=Y.device)
+    lab = kernels.kmeans_assign(Y, cd, n_rechecked=nre)
+    lab_o, dmin_o = oracle.kmeans.assign(Yh, c0)
+    n_bad = int(np.count_nonzero(lab.cpu().numpy().astype(np.int64) != lab_o))
+    assert n_bad == 0, f"{n_bad} labels differ from the fp64 argmin"
+    # (b) fixed number of Lloyd iterations: centres track the oracle
+    res = lloyd_device(Y, cd, max_iter=n_iter, tolerance=None)
+    co = c0.copy()
+    for _ in range(n_iter):
+        lo, _ = oracle.kmeans.assign(Yh, co)
+        co, _ = oracle.kmeans._update(Yh, lo, co)
+    c_rel = rel_err(res.centers.cpu().numpy(), co)
+    final = kernels.kmeans_assign(Y, res.centers)
+    lab_f, _ = oracle.kmeans.assign(Yh, res.centers.cpu().numpy())
+    n_bad_f = int(np.count_nonzero(final.cpu().numpy().astype(np.int64) != lab_f))
+    assert n_bad_f == 0, f"{n_bad_f} final labels differ"
+    assert c_rel <= REL, f"Lloyd centres off by {c_rel}"
+    return {"labels_mismatch": n_bad + n_bad_f, "centers_rel": c_rel,
+            "rechecked_frac": float(nre.item()) / max(1, Y.shape[0])}, final
+
+
+def check_counts_msm(labels: torch.Tensor, segs: Segments, K: int, lag: int, n_ts: int) -> dict:
+    dev = labels.device
+    C = kernels.count_lagged(labels, segs.device(dev), K, lag)
+    dtrajs = segs.split(labels.cpu().numpy())
+    Co = oracle.counts.count_lagged(dtrajs, K, lag)
+    assert np.array_equal(C.cpu().numpy(), Co), "count matrix differs"
+    assert int(Co.sum()) == segs.n_pairs(lag)
+    T, pi, info, act = msm_from_counts_device(C, maxerr=1e-12)
+    Ca, active = oracle.msm.ensure_connected_counts(Co.astype(float))
+    To, pio, it_o = oracle.msm.mle_rev(Ca, maxerr=1e-12)
+    Tf, pif = oracle.msm.expand_results(K, active, To, pio)
+    rep = {"T_rel": rel_err(T.cpu().numpy(), Tf), "pi_rel": rel_err(pi.cpu().numpy(), pif),
+           "mle_iters": int(info[0].item()), "mle_iters_oracle": int(it_o)}
+    assert int(info[1].item()) == 1, "MLE did not converge"
+    assert rep["T_rel"] <= REL and rep["pi_rel"] <= REL, rep
+    oracle.msm.check_transition_matrix(T.cpu().numpy(), pi.cpu().numpy())
+    k = min(n_ts + 1, K)
+    ev, _ = kernels.eig_rev_topk(T, pi, k)
+    evo = oracle.msm.eigenvalues_rev(To, pio, k)
+    evh = ev.cpu().numpy()
+    rep["eig_rel"] = float(np.max(np.abs(evh - evo) / np.maximum(np.abs(evo), 1e-3)))
+    assert rep["eig_rel"] <= REL, (rep, evh, evo)
+    ts, tso = safe_timescales(lag, evh[1:]), oracle.msm.safe_timescales(lag, evo[1:])
+    ok = np.isfinite(tso)
+    assert np.array_equal(np.isfinite(ts), ok)
+    # timescales amplify eigenvalue error by 1/((1-lambda)) near 1; compare through the eigenvalues' bar
+    rep["ts_rel"] = float(np.max(np.abs(ts[ok] - tso[ok]) / np.abs(tso[ok]))) if ok.any() else 0.0
+    assert rep["ts_rel"] <= 1e-5, rep
+    return rep
+
+
+def run_and_check_small(seed: int = 1, n_traj: int = 4, n_frames: int = 600, n_res: int = 8,
+                        K: int = 12, lag: int = 5) -> dict:
+    """One tiny end-to-end pass, every stage checked against the oracle."""
+    top = synth.backbone_topology(n_res)
+    trajs = synth.backbone_trajectories(n_res, n_traj, n_frames, seed)
+    report = {"featurize": check_featurize(trajs, top)}
+    dev = torch.device("cuda")
+    plan = plan_phi_psi_block(top)
+    feats_d = featurize_device(torch.from_numpy(np.concatenate(trajs, axis=0)).to(dev), plan)
+    segs = Segments.from_lengths([t.shape[0] for t in trajs])
+    feats = segs.split(feats_d.cpu().numpy())
+    rep, Y, segs = check_tica(feats, lag, 3, "standard")
+    report["tica"] = rep
+    rep, labels = check_kmeans(Y, K, 5, seed)
+    report["kmeans"] = rep
+    report["msm"] = check_counts_msm(labels, segs, K, lag, 4)
+    return report

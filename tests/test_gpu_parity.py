@@ -1,0 +1,433 @@
+"""Parity of the CUDA path (through the C ABI of libpmb200.so) against the CPU
+oracle and the committed golden vectors.  Run on the B200 box: ``pytest -m gpu``."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import parity, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from pmarlo_b200 import load_library
+
+    load_library()
+    torch.cuda.set_device(0)
+    yield
+    torch.cuda.synchronize()
+
+
+def dev():
+    return torch.device("cuda")
+
+
+# ----------------------------------------------------------------------------- featurize
+@pytest.mark.parametrize("n_res,n_traj,n_frames", [(4, 1, 7), (8, 3, 257), (33, 2, 1500)])
+def test_featurize_vs_oracle(n_res, n_traj, n_frames):
+    top = synth.backbone_topology(n_res)
+    trajs = synth.backbone_trajectories(n_res, n_traj, n_frames, seed=n_res)
+    parity.check_featurize(trajs, top)
+
+
+def test_featurize_analytic_geometries():
+    """Planar cis/trans = 0 / pi, +-90 degree constructions."""
+    from pmarlo_b200.features import FeaturePlan, featurize_device
+
+    def frame(angle):
+        # atoms 0,1,2 in the xy plane; atom 3 rotated by `angle` about the 1->2 axis
+        p0, p1, p2 = [1.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.0, 0.0, 1.0]
+        p3 = [np.cos(angle), np.sin(angle), 1.0]
+        return [p0, p1, p2, p3]
+
+    angles = np.array([0.0, np.pi, np.pi / 2, -np.pi / 2, 0.3, -2.5, 3.0])
+    xyz = np.asarray([frame(a) for a in angles], dtype=np.float32) * 0.15
+    plan = FeaturePlan(np.asarray([[0, 0, 1, 2, 3, 0, 1, 2]], dtype=np.int32), 3)
+    got = featurize_device(torch.from_numpy(xyz).to(dev()), plan).cpu().numpy()
+    ref = oracle.featurize.compute_dihedrals(xyz, np.asarray([[0, 1, 2, 3]]))[:, 0]
+    assert parity.angle_err(got[:, 0], ref) < 1e-6
+    # sign convention (IUPAC, as mdtraj): the construction above yields angle = +a
+    assert parity.angle_err(got[:, 0], angles) < 1e-6
+    np.testing.assert_allclose(got[:, 1], np.cos(ref), atol=1e-6)
+    np.testing.assert_allclose(got[:, 2], np.sin(ref), atol=1e-6)
+    assert np.all(got[:, 0] > -np.pi) and np.all(got[:, 0] <= np.float32(np.pi))
+
+
+def test_featurize_trajectory_api(topologies):
+    """Drop-in signatures on the two reference topologies (ala2: 1 phi + 1 psi; chignolin: 45 CA pairs)."""
+    from pmarlo_b200 import Trajectory, Topology, compute_features, featurize_trajectory, trig_expand_periodic
+
+    for key, n_ang, n_ca in (("ala2", 2, 1), ("chig", 18, 10)):
+        t = topologies[key]
+        top = Topology(t["names"], t["resid"], t["chain"])
+        rng = np.random.default_rng(5)
+        xyz = (t["xyz"][None] + rng.normal(scale=0.01, size=(50,) + t["xyz"].shape)).astype(np.float32)
+        traj = Trajectory(xyz, top)
+        X = featurize_trajectory(traj, "phi_psi")
+        ref = oracle.featurize.featurize_trajectory(xyz, t["names"], t["resid"], t["chain"], "phi_psi")
+        assert X.shape == ref.shape == (50, n_ang) and X.dtype == np.float32
+        assert parity.angle_err(X, ref) < parity.ANGLE_ABS
+        if n_ca >= 2:
+            D = featurize_trajectory(traj, "ca_distances")
+            Dref = oracle.featurize.featurize_trajectory(xyz, t["names"], t["resid"], t["chain"], "ca_distances")
+            assert D.shape == (50, n_ca * (n_ca - 1) // 2)
+            assert parity.rel_err(D, Dref) < parity.DIST_REL
+        else:
+            with pytest.raises(ValueError):
+                featurize_trajectory(traj, "ca_distances")
+        Xc, cols, per = compute_features(traj, ["phi_psi"])
+        assert Xc.shape == X.shape and len(cols) == n_ang and per.all()
+        assert cols[0].startswith("phi:res") and cols[-1].startswith("psi:res")
+        Xe, mapping = trig_expand_periodic(Xc, per)
+        Xeo, mo = oracle.featurize.trig_expand_periodic(Xc.astype(np.float64), per)
+        np.testing.assert_array_equal(mapping, mo)
+        np.testing.assert_allclose(Xe, Xeo, atol=1e-12)
+    with pytest.raises(ValueError):
+        featurize_trajectory(traj, "nope")
+    with pytest.raises(ValueError):
+        trig_expand_periodic(np.zeros((3, 2)), np.array([True]))
+
+
+# ----------------------------------------------------------------------------- TICA
+@pytest.mark.parametrize("d,lag,dim,pre", [(4, 10, 2, "standard"), (12, 3, 5, None), (37, 7, 10, "center"),
+                                            (81, 10, 10, "standard"), (256, 20, 10, "standard")])
+def test_tica_vs_oracle(d, lag, dim, pre):
+    n_traj = 3 if d < 200 else 2
+    feats = synth.ar1_features(n_traj, 4000 if d < 200 else 6000, d, seed=d, offset=3.0)
+    feats[1] = feats[1][: 4000 - 333]          # ragged shards
+    if d == 12:
+        feats.append(feats[0][:lag])           # a shard no longer than the lag contributes no pair
+    parity.check_tica(feats, lag, dim, pre)
+
+
+def test_tica_nan_imputation_and_constant_column(golden):
+    from pmarlo_b200.reduction import preprocess, tica_reduce
+
+    z = golden("preprocess")
+    for key_in, key_out, scale in (("X", "P_scale", True), ("X", "P_noscale", False),
+                                   ("Xn", "Pn_scale", True), ("Xn", "Pn_noscale", False)):
+        X32 = z[key_in].astype(np.float32)
+        got = preprocess(X32, scale=scale)
+        ref = oracle.tica.preprocess(X32.astype(np.float64), scale=scale)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=2e-6 * max(1.0, np.abs(ref).max()))
+        # the golden vectors were made from float64 inputs: float32 rounding of the inputs is the only gap
+        np.testing.assert_allclose(got, z[key_out], rtol=0, atol=5e-6 * max(1.0, np.abs(z[key_out]).max()))
+    Xn = z["Xn"].astype(np.float32)
+    Y = tica_reduce(Xn, lag=2, n_components=2, scale=True)
+    Yo = oracle.tica.tica_reduce(Xn.astype(np.float64), lag=2, n_components=2, scale=True)
+    assert Y.shape == Yo.shape and Y.dtype == np.float64
+    assert parity.rel_err(Y, Yo) < 5e-6
+
+
+def test_tica_ar1_spectrum(golden):
+    """Analytic pin: TICA eigenvalues of independent AR(1) processes are rho^lag; the reference's own
+    numpy estimator (golden ref_eigs) agrees to O(1/N)."""
+    from pmarlo_b200.reduction import TICA
+
+    z = golden("tica_xcheck")
+    X, lag, rho = z["X"], int(z["lag"]), z["rho"]
+    model = TICA(lag, 4, preprocess=None).fit([X])
+    ev = model.eigenvalues.cpu().numpy()[:4]
+    np.testing.assert_allclose(np.sort(ev)[::-1], np.sort(rho ** lag)[::-1], atol=0.03)
+    np.testing.assert_allclose(np.sort(ev)[::-1], np.sort(z["ref_eigs"])[::-1], atol=5e-3)
+    om = oracle.tica.tica_fit([X.astype(np.float64)], lag)
+    assert np.max(np.abs(ev - om.eigenvalues[:4]) / np.abs(om.eigenvalues[:4])) < parity.REL
+
+
+def test_maybe_apply_tica_drops_lag_frames():
+    from pmarlo_b200.reduction import maybe_apply_tica
+
+    feats = synth.ar1_features(3, 500, 6, seed=2)
+    lengths = [f.shape[0] for f in feats]
+    flat = np.concatenate(feats)
+    Y, ncomp, kept = maybe_apply_tica(flat, lengths, 9, 7)
+    Yo, nco = oracle.tica.maybe_apply_tica(flat.astype(np.float64), lengths, 9, 7)
+    assert ncomp == nco == 5 and kept == [493] * 3
+    assert Y.shape == Yo.shape and parity.rel_err(Y, Yo) < 5e-6
+
+
+# ----------------------------------------------------------------------------- k-means
+@pytest.mark.parametrize("D,K,n", [(2, 200, 20000), (3, 17, 5000), (10, 1000, 30000), (10, 3000, 8000),
+                                   (16, 64, 4000), (64, 300, 3000)])
+def test_kmeans_vs_oracle(D, K, n):
+    feats = synth.ar1_features(1, n, D, seed=D * 7 + K)[0]
+    Y = torch.from_numpy(feats).to(dev())
+    parity.check_kmeans(Y, K, 3, seed=K)
+
+
+def test_assign_ties_duplicates_and_float64():
+    """Duplicate centres and exact ties: the FIRST minimum wins, as np.argmin does."""
+    from pmarlo_b200 import kernels
+
+    rng = np.random.default_rng(0)
+    c = rng.normal(size=(9, 4))
+    c[5] = c[2]                                   # duplicate centre
+    Y = np.concatenate([c, 0.5 * (c[0] + c[1])[None], rng.normal(size=(500, 4))])   # midpoint tie
+    for dt in (np.float32, np.float64):
+        Yd = torch.from_numpy(Y.astype(dt)).to(dev())
+        cd = torch.from_numpy(c.astype(dt).astype(np.float64)).to(dev())
+        lab = kernels.kmeans_assign(Yd, cd).cpu().numpy()
+        ref, _ = oracle.kmeans.assign(Y.astype(dt).astype(np.float64), c.astype(dt).astype(np.float64))
+        np.testing.assert_array_equal(lab, ref)
+        assert lab[5] == 2 and lab[2] == 2
+
+
+def test_assign_golden_matches_reference_discretizer(golden):
+    """Labels of pmarlo's own _KMeansDiscretizer (sklearn predict, analysis/discretize.py:493) on its
+    whitened inputs, reproduced from the committed centres."""
+    from pmarlo_b200 import kernels
+
+    z = golden("assign")
+    for X, lab in ((z["X"], z["lab_train"]), (z["Xt"], z["lab_test"])):
+        Xs = ((X - z["mean"]) / z["std"])
+        got = kernels.kmeans_assign(torch.from_numpy(Xs).to(dev()), torch.from_numpy(z["centers"]).to(dev()))
+        np.testing.assert_array_equal(got.cpu().numpy(), lab)
+
+
+def test_cluster_microstates_api():
+    from pmarlo_b200.clustering import cluster_microstates, cluster_microstates_labels
+
+    rng = np.random.default_rng(4)
+    blobs = rng.normal(size=(8, 3)) * 10
+    Y = (blobs[rng.integers(0, 8, 4000)] + rng.normal(size=(4000, 3))).astype(np.float64)
+    res = cluster_microstates(Y, method="kmeans", n_states=8, random_state=42)
+    assert res.n_states == 8 and len(np.unique(res.labels)) == 8 and res.centers.shape == (8, 3)
+    # reproducible under a fixed seed; explicit initial centres track the oracle bit-for-bit
+    res2 = cluster_microstates(Y, method="kmeans", n_states=8, random_state=42)
+    np.testing.assert_array_equal(res.labels, res2.labels)
+    c0 = Y[:8].copy()
+    r3 = cluster_microstates(Y, method="kmeans", n_states=8, initial_centers=c0)
+    lo, co, nu, inertia, _ = oracle.kmeans.cluster_microstates(Y, 8, c0)
+    np.testing.assert_array_equal(r3.labels, lo)
+    np.testing.assert_allclose(r3.centers, co, rtol=1e-9, atol=1e-9)
+    # n_init restarts keep the lowest inertia; labels-only wrapper
+    r4 = cluster_microstates(Y, method="kmeans", n_states=8, random_state=1, n_init=3)
+    assert len(np.unique(r4.labels)) == 8
+    assert cluster_microstates_labels(Y, "kmeans", 8).shape == (4000,)
+    # error behaviour of the reference
+    assert cluster_microstates(np.empty((0, 3)), n_states=4).n_states == 0
+    with pytest.raises(ValueError):
+        cluster_microstates(Y[:, 0], n_states=3)
+    with pytest.raises(ValueError):
+        cluster_microstates(Y, n_states=0)
+    with pytest.raises(TypeError):
+        cluster_microstates(Y, n_states=3, bogus=1)
+    with pytest.raises(TypeError):
+        cluster_microstates(Y, method="kmeans", n_states=3, batch_size=10)
+    with pytest.raises(ValueError):
+        cluster_microstates(Y, n_states=3, n_init=2, fixed_seed=1)
+
+
+# ----------------------------------------------------------------------------- counts
+def test_counts_golden(golden):
+    """Bit-exact against pmarlo's own _weighted_counts / _build_transition_counts outputs."""
+    from pmarlo_b200 import kernels
+
+    z = golden("counts")
+    for ci in range(int(z["n_cases"])):
+        g = lambda k: z[f"c{ci}_{k}"]  # noqa: E731
+        labels = torch.from_numpy(g("labels")).to(dev())
+        K, lag, stride = int(g("K")), int(g("lag")), int(g("stride"))
+        off = torch.from_numpy(g("bounds")).to(dev())
+        C = kernels.count_lagged(labels, off, K, lag, stride).cpu().numpy()
+        np.testing.assert_array_equal(C, g("C_u").astype(np.int64))
+        assert int(C.sum()) == int(g("tp_u"))
+        whole = torch.tensor([0, labels.numel()], dtype=torch.int64, device=dev())
+        np.testing.assert_array_equal(kernels.count_lagged(labels, whole, K, lag, 1).cpu().numpy(),
+                                      g("C_all").astype(np.int64))
+        np.testing.assert_array_equal(kernels.count_lagged(labels, off, K, lag, 1).cpu().numpy(),
+                                      g("C_sl").astype(np.int64))
+        np.testing.assert_array_equal(kernels.count_lagged(labels, off, K, lag, lag).cpu().numpy(),
+                                      g("C_st").astype(np.int64))
+        w = torch.from_numpy(g("weights")).to(dev())
+        Cw = kernels.count_lagged_weighted(labels, w, off, K, lag, stride).cpu().numpy()
+        np.testing.assert_allclose(Cw, g("C_w"), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("K,n,lag", [(5, 300000, 1), (100, 6_000_000, 10), (200, 50000, 100), (1000, 400000, 20),
+                                     (5000, 300000, 20)])
+def test_counts_vs_oracle(K, n, lag):
+    from pmarlo_b200 import kernels
+    from pmarlo_b200.msm import dtrajs_to_device
+
+    dtrajs = synth.metastable_dtrajs(5, n // 5, K, seed=K) if n <= 400000 else None
+    if dtrajs is None:   # big case: vectorised labels (python chain generation would take minutes)
+        rng = np.random.default_rng(K)
+        dtrajs = [rng.integers(0, K, size=n // 5).astype(np.int32) for _ in range(5)]
+    dtrajs[1][::97] = -1
+    dtrajs[2][5::101] = K + 3
+    labels, segs = dtrajs_to_device(dtrajs, dev())
+    C = kernels.count_lagged(labels, segs.device(dev()), K, lag).cpu().numpy()
+    np.testing.assert_array_equal(C, oracle.counts.count_lagged(dtrajs, K, lag))
+
+
+def test_count_transitions_api_split_mode():
+    from pmarlo_b200.msm import count_transitions
+
+    dtrajs = synth.metastable_dtrajs(3, 800, 6, seed=3)
+    dtrajs[0][100] = -1
+    dtrajs[2][::50] = 9
+    C = count_transitions(dtrajs, n_states=6, lag=4, split_invalid=True)
+    # labels >= n_states enlarge the matrix exactly as deeptime's estimator does (max label + 1)
+    Co = oracle.counts.count_lagged(dtrajs, 10, 4, mode="split")
+    np.testing.assert_array_equal(C, Co.astype(float))
+    assert count_transitions([], lag=3).shape == (0, 0)
+
+
+# ----------------------------------------------------------------------------- MSM
+@pytest.mark.parametrize("K,stay", [(2, 0.9), (3, 0.5), (40, 0.9), (200, 0.95), (600, 0.9)])
+def test_msm_vs_oracle(K, stay):
+    from pmarlo_b200.msm import dtrajs_to_device
+
+    dtrajs = synth.metastable_dtrajs(4, 20000 if K < 300 else 60000, K, seed=K + 1, stay=stay)
+    labels, segs = dtrajs_to_device(dtrajs, dev())
+    parity.check_counts_msm(labels, segs, K, 3, 5)
+
+
+def test_two_state_chain_known_answer():
+    """tests/unit/markov_state_model/test_two_state_msm.py:6-22: p=0.1 -> t2 = -1/ln 0.8 within 10 %."""
+    from pmarlo_b200 import build_msm_from_labels
+    from pmarlo_b200.msm import eigenvalues_rev, safe_timescales
+
+    rng = np.random.default_rng(0)
+    s = np.zeros(200000, dtype=np.int32)
+    flips = rng.random(s.size) < 0.1
+    for t in range(1, s.size):
+        s[t] = s[t - 1] ^ int(flips[t])
+    T, pi = build_msm_from_labels([s], n_states=2, lag=1)
+    np.testing.assert_allclose(T.sum(axis=1), 1.0, atol=1e-12)
+    np.testing.assert_allclose(pi @ T, pi, atol=1e-10)
+    ev = eigenvalues_rev(T, pi, 2)
+    t2 = safe_timescales(1, ev[1:])[0]
+    assert abs(t2 - (-1.0 / np.log(0.8))) / (-1.0 / np.log(0.8)) < 0.1
+
+
+def test_build_simple_msm_api():
+    from pmarlo_b200 import build_simple_msm
+
+    dtrajs = synth.metastable_dtrajs(3, 5000, 7, seed=9)
+    dtrajs[0][::40] = -1                         # unassigned frames are ignored
+    T, pi = build_simple_msm(dtrajs, n_states=9, lag=2)   # states 7, 8 never visited
+    To, pio = oracle.msm.build_simple_msm(dtrajs, n_states=9, lag=2)
+    assert T.shape == (9, 9)
+    assert parity.rel_err(T, To) < 1e-6 and parity.rel_err(pi, pio) < 1e-6
+    assert T[7, 7] == 1.0 and T[8, 8] == 1.0 and pi[7] == 0.0 and pi[8] == 0.0
+    # detailed balance of the reversible estimate
+    F = pi[:, None] * T
+    np.testing.assert_allclose(F, F.T, atol=1e-12)
+    Te, pe = build_simple_msm([], lag=3)
+    assert Te.shape == (0, 0) and pe.shape == (0,)
+
+
+def test_mle_batched_with_active_masks():
+    """One CTA per problem: different lags, each restricted to its own connected set."""
+    from pmarlo_b200 import kernels
+    from pmarlo_b200.msm import dtrajs_to_device, largest_connected_set
+
+    K = 30
+    dtrajs = synth.metastable_dtrajs(3, 4000, K, seed=12, stay=0.97)
+    labels, segs = dtrajs_to_device(dtrajs, dev())
+    lags = [1, 5, 25, 100]
+    Cs, acts = [], []
+    for lag in lags:
+        C = kernels.count_lagged(labels, segs.device(dev()), K, lag)
+        Cs.append(C.to(torch.float64))
+        Ch = C.cpu().numpy().copy()
+        if lag == 25:                            # force a non-trivial mask: drop states 0 and 3
+            Ch[[0, 3], :] = 0
+            Ch[:, [0, 3]] = 0
+        a = np.zeros(K, dtype=np.uint8)
+        a[largest_connected_set(Ch)] = 1
+        acts.append(a)
+    assert acts[2][0] == 0 and acts[2].sum() >= 2
+    act = torch.from_numpy(np.stack(acts)).to(dev())
+    T, pi, info = kernels.mle_rev(torch.stack(Cs), act, alpha=0.0, maxerr=1e-12)
+    for b in range(len(lags)):
+        idx = np.flatnonzero(acts[b])
+        Cb = Cs[b].cpu().numpy()[np.ix_(idx, idx)]
+        if np.any(Cb.sum(axis=1) <= 0):
+            assert int(info[b, 1].item()) == -1
+            continue
+        To, pio, _ = oracle.msm.mle_rev(Cb, maxerr=1e-12)
+        Tf, pif = oracle.msm.expand_results(K, idx, To, pio)
+        assert parity.rel_err(T[b].cpu().numpy(), Tf) < 1e-6
+        assert parity.rel_err(pi[b].cpu().numpy(), pif) < 1e-6
+
+
+def test_eigenvalues_lanczos_large_K():
+    """K > 256 takes the Lanczos path; compare with eigvalsh of the oracle."""
+    from pmarlo_b200 import kernels
+
+    K = 700
+    dtrajs = synth.metastable_dtrajs(4, 80000, K, seed=77, stay=0.9)
+    C = oracle.counts.count_lagged(dtrajs, K, 2).astype(float)
+    Ca, active = oracle.msm.ensure_connected_counts(C)
+    To, pio, _ = oracle.msm.mle_rev(Ca, maxerr=1e-12)
+    T = torch.from_numpy(To).to(dev())
+    pi = torch.from_numpy(pio).to(dev())
+    ev, info = kernels.eig_rev_topk(T, pi, 10)
+    evo = oracle.msm.eigenvalues_rev(To, pio, 10)
+    assert int(info[0].item()) > 0, "expected the Lanczos path"
+    np.testing.assert_allclose(ev.cpu().numpy(), evo, rtol=1e-6, atol=1e-9)
+
+
+def test_implied_timescales_sweep():
+    from pmarlo_b200 import implied_timescales
+
+    K = 20
+    dtrajs = synth.metastable_dtrajs(4, 6000, K, seed=5, stay=0.95)
+    lags = [1, 2, 5, 10, 20, 50]
+    res = implied_timescales(dtrajs, lags, n_states=K, n_timescales=4, maxerr=1e-12)
+    ref = oracle.msm.its_rev_mle(dtrajs, K, lags, 4, maxerr=1e-12)
+    assert res.timescales.shape == ref.shape == (6, 4)
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(res.timescales), ok)
+    np.testing.assert_allclose(res.timescales[ok], ref[ok], rtol=1e-5)
+
+
+def test_safe_timescales_golden(golden):
+    from pmarlo_b200 import safe_timescales
+
+    z = golden("timescales")
+    for lag in (1, 10, 400):
+        np.testing.assert_array_equal(safe_timescales(lag, z["ev_real"]), z[f"ts_real_{lag}"])
+        np.testing.assert_array_equal(safe_timescales(lag, z["ev_cplx"]), z[f"ts_cplx_{lag}"])
+
+
+# ----------------------------------------------------------------------------- end to end
+def test_pipeline_small_end_to_end():
+    parity.run_and_check_small(seed=3, n_traj=5, n_frames=900, n_res=10, K=20, lag=4)
+
+
+def test_pipeline_properties_at_scale():
+    """Size-independent properties on a bench-sized shard (1.25 M frames x 99 atoms -> 256 features):
+    pair bookkeeping, row-stochastic T, pi T = pi, detailed balance, labels in range, counts total."""
+    from pmarlo_b200.pipeline import PipelineConfig, run_pipeline
+    from pmarlo_b200.shards import Segments
+    import bench
+
+    wl = bench.make_workload(n_traj=4, frames_per_traj=50_000, device=dev(), seed=4)
+    cfg = bench.bench_config(n_states=300, kmeans_iters=3)
+    res = run_pipeline(wl.xyz, wl.segs, wl.plan, cfg)
+    K = cfg.n_states
+    C = res.counts.cpu().numpy()
+    assert int(C.sum()) == wl.segs.n_pairs(cfg.msm_lag)
+    lab = res.labels.cpu().numpy()
+    assert lab.min() >= 0 and lab.max() < K
+    T, pi = res.T.cpu().numpy(), res.pi.cpu().numpy()
+    np.testing.assert_allclose(T.sum(axis=1), 1.0, atol=1e-12)
+    np.testing.assert_allclose(pi @ T, pi, atol=1e-10)
+    F = pi[:, None] * T
+    np.testing.assert_allclose(F, F.T, atol=1e-12)
+    ev = res.eigenvalues.cpu().numpy()
+    assert abs(ev[0] - 1.0) < 1e-9 and np.all(np.abs(ev) <= 1 + 1e-9)
+    # labels are the exact argmin for the final centres (checked on a slice with the oracle)
+    sl = slice(0, 20000)
+    lo, _ = oracle.kmeans.assign(res.Y[sl].cpu().numpy().astype(np.float64), res.centers.cpu().numpy())
+    np.testing.assert_array_equal(lab[sl], lo)

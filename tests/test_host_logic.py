@@ -1,0 +1,170 @@
+"""Host-side logic of the product (no GPU): shard bookkeeping, atom index plans,
+regularisation and timescale formulas against the oracle and the golden vectors."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import oracle
+from pmarlo_b200 import features as F
+from pmarlo_b200 import msm
+from pmarlo_b200.shards import Segments, partition_trajectories
+from pmarlo_b200.topology import Topology, load_pdb
+from tests import synth
+
+
+def test_segments_pairs_match_expected_pairs():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        lengths = rng.integers(0, 60, size=rng.integers(1, 6)).tolist()
+        lag, step = int(rng.integers(0, 30)), int(rng.integers(1, 5))
+        s = Segments.from_lengths(lengths)
+        assert s.n_pairs(lag, step) == oracle.counts.expected_pairs(lengths, lag, step)
+    s = Segments.from_lengths([5, 0, 7])
+    assert s.n_frames == 12 and s.lengths.tolist() == [5, 0, 7]
+    idx, s2 = s.drop_tail(3)
+    assert idx.tolist() == [0, 1, 5, 6, 7, 8] and s2.lengths.tolist() == [2, 0, 4]
+    with pytest.raises(ValueError):
+        Segments.from_lengths([3, -1])
+
+
+def test_partition_is_balanced_and_complete():
+    lengths = [125_000] * 80
+    parts = partition_trajectories(lengths, 8)
+    assert sorted(i for p in parts for i in p) == list(range(80))
+    assert all(len(p) == 10 for p in parts)
+    ragged = [371, 372] * 17 + [371]
+    parts = partition_trajectories(ragged, 4)
+    loads = [sum(ragged[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= 372
+    assert sorted(i for p in parts for i in p) == list(range(35))
+    assert partition_trajectories([5], 3) == [[0], [], []]
+
+
+def test_plans_match_oracle_indices(topologies):
+    for key in ("ala2", "chig"):
+        t = topologies[key]
+        top = Topology(t["names"], t["resid"], t["chain"])
+        for kind in ("phi", "psi"):
+            np.testing.assert_array_equal(F.dihedral_quads(top, kind),
+                                          oracle.featurize.dihedral_quads(t["names"], t["resid"], t["chain"], kind))
+        ca = top.select_name("CA")
+        np.testing.assert_array_equal(ca, oracle.featurize.ca_indices(t["names"]))
+        if len(ca) >= 2:
+            np.testing.assert_array_equal(F.ca_pairs_all(ca), oracle.featurize.ca_pairs_all(ca))
+            np.testing.assert_array_equal(F.ca_pairs_stride3(ca, None), oracle.featurize.ca_pairs_stride3(ca, None))
+            np.testing.assert_array_equal(F.ca_pairs_stride3(ca, 2), oracle.featurize.ca_pairs_stride3(ca, 2))
+
+
+def test_plan_layouts():
+    top = synth.backbone_topology(5)
+    ang = F.plan_phi_psi(top)
+    assert ang.n_cols == 8 and ang.periodic.all() and ang.columns[0] == "phi:res1" and ang.columns[4] == "psi:res0"
+    blk = F.plan_phi_psi_block(top)
+    # [cos phi | sin phi | cos psi | sin psi]
+    assert blk.n_cols == 16
+    assert blk.units[0, 6] == 0 and blk.units[0, 7] == 4 and blk.units[4, 6] == 8 and blk.units[4, 7] == 12
+    inter = F.plan_phi_psi_interleaved(top)
+    assert inter.units[1, 6] == 2 and inter.units[1, 7] == 3
+    both = F.plan_concat([blk, F.plan_distances(np.array([[1, 4], [1, 7]]))])
+    assert both.n_cols == 18 and both.units[-1, 5] == 17 and both.units[-1, 6] == -1
+    assert F.parse_feature_spec("phi_psi") == ("phi_psi", {})
+    assert F.parse_feature_spec("distance([3, 9])") == ("distance", {"indices": [3, 9]})
+    assert F.parse_feature_spec("dist:atompair(2,5)") == ("distance_pair", {"i": 2, "j": 5})
+
+
+def test_load_pdb_roundtrip(tmp_path):
+    lines = []
+    top = synth.backbone_topology(3)
+    xyz = synth.backbone_trajectories(3, 1, 2, seed=0)[0]
+    for m in range(2):
+        lines.append(f"MODEL     {m + 1}")
+        for i, n in enumerate(top.names):
+            x, y, z = xyz[m, i] * 10.0
+            lines.append(f"ATOM  {i + 1:5d} {n:<4s} ALA A{top.resid[i] + 1:4d}    {x:8.3f}{y:8.3f}{z:8.3f}  1.00  0.00")
+        lines.append("ENDMDL")
+    p = tmp_path / "t.pdb"
+    p.write_text("\n".join(lines) + "\n")
+    traj = load_pdb(str(p))
+    assert traj.n_frames == 2 and traj.n_atoms == 9
+    np.testing.assert_allclose(traj.xyz, xyz, atol=1e-4)
+    np.testing.assert_array_equal(traj.topology.resid, top.resid)
+
+
+def test_ensure_connected_counts_and_expand():
+    C = np.array([[5, 1, 0, 0], [2, 7, 0, 0], [0, 0, 0, 0], [0, 1, 0, 3]], dtype=float)
+    res = msm.ensure_connected_counts(C)
+    Co, act = oracle.msm.ensure_connected_counts(C)
+    np.testing.assert_array_equal(res.active, act)
+    np.testing.assert_array_equal(res.counts, Co)
+    assert res.active.tolist() == [0, 1, 3] and res.counts[0, 2] == pytest.approx(1e-3)
+    empty = msm.ensure_connected_counts(np.zeros((3, 3)))
+    assert empty.counts.shape == (0, 0) and empty.active.size == 0
+    with pytest.raises(ValueError):
+        msm.ensure_connected_counts(np.zeros((2, 3)))
+
+
+def test_safe_timescales_golden(golden):
+    z = golden("timescales")
+    for lag in (1, 10, 400):
+        np.testing.assert_array_equal(msm.safe_timescales(lag, z["ev_real"]), z[f"ts_real_{lag}"])
+        np.testing.assert_array_equal(msm.safe_timescales(lag, z["ev_cplx"]), z[f"ts_cplx_{lag}"])
+    assert msm.safe_timescales(5, np.array([])).shape == (0,)
+
+
+def test_check_transition_matrix_and_split():
+    T = np.array([[0.9, 0.1], [0.2, 0.8]])
+    pi = np.array([2 / 3, 1 / 3])
+    msm.check_transition_matrix(T, pi)
+    with pytest.raises(ValueError):
+        msm.check_transition_matrix(np.array([[1.0 + 1e-13, -1e-13], [0.2, 0.8]]), pi)
+    with pytest.raises(ValueError):
+        msm.check_transition_matrix(T, np.array([0.5, 0.5]))
+    d = [np.array([0, 1, -1, 2, 2, 7, 1]), np.array([-1, -1]), np.array([], dtype=int)]
+    got = msm.split_at_invalid(d, 3)
+    ref = oracle.counts.split_at_invalid(d, 3)
+    assert len(got) == len(ref) == 3
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a, b)
+    assert msm.infer_n_states(d) == 8 and msm.infer_n_states(d, 4) == 4 and msm.infer_n_states([np.array([-1])]) == 0
+    lcs = msm.largest_connected_set(np.array([[1, 1, 0], [1, 1, 0], [0, 1, 1]]))
+    assert lcs.tolist() == [0, 1]
+
+
+def test_lloyd_host_loop_matches_oracle_semantics(monkeypatch):
+    """The stopping rule of lloyd_device (cost of iteration i measured by the assign pass of
+    iteration i+1) reproduces oracle.kmeans.lloyd; kernels are replaced by numpy stand-ins."""
+    import torch
+
+    from pmarlo_b200 import clustering, kernels
+
+    rng = np.random.default_rng(1)
+    Y = np.concatenate([rng.normal(size=(200, 2)) + c for c in ([0, 0], [6, 0], [0, 6])])
+    c0 = Y[[0, 250, 500]].copy()
+
+    def fake_assign(Yt, centers, labels=None, sums=None, counts=None, inertia=None, n_rechecked=None):
+        lab, dmin = oracle.kmeans.assign(Yt.numpy(), centers.numpy())
+        labels.copy_(torch.from_numpy(lab.astype(np.int32)))
+        if sums is not None:
+            s = np.zeros(tuple(sums.shape))
+            np.add.at(s, lab, Yt.numpy())
+            sums += torch.from_numpy(s)
+            counts += torch.from_numpy(np.bincount(lab, minlength=counts.numel()))
+            inertia += float(dmin.sum())
+        return labels
+
+    def fake_update(centers, sums, counts, shift2=None):
+        nz = counts > 0
+        centers[nz] = sums[nz] / counts[nz].to(torch.float64)[:, None]
+
+    monkeypatch.setattr(kernels, "kmeans_assign", fake_assign)
+    monkeypatch.setattr(kernels, "kmeans_update", fake_update)
+    for max_iter, tol in ((500, 1e-5), (1, 1e-5), (3, 0.0)):
+        res = clustering.lloyd_device(torch.from_numpy(Y), torch.from_numpy(c0), max_iter=max_iter, tolerance=tol)
+        co, it, cost, conv = oracle.kmeans.lloyd(Y, c0, max_iter=max_iter, tolerance=tol)
+        assert res.n_iter == it and res.converged == conv
+        np.testing.assert_allclose(res.centers.numpy(), co, rtol=1e-12)
+        assert res.cost == pytest.approx(cost, rel=1e-12)
+    res = clustering.lloyd_device(torch.from_numpy(Y), torch.from_numpy(c0), max_iter=4, tolerance=None)
+    assert res.n_iter == 4 and res.cost is None
