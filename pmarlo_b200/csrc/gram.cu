@@ -4,10 +4,12 @@
 //   mode 1: G = sum_g (mask_g & 1) v_g v_g^T,  v_g = z_g - z_{g+lag}  (-> X0^T Xt + Xt^T X0)
 //   z = NaN ? 0 : (x - shift) * scale        (fp32 conditioning, undone exactly in fp64 later)
 //
-// Precision plan (north star: covariances within 1e-6 of the fp64 oracle):
-// products are exact fp32 FMAs of conditioned (|z| ~ 1) data, accumulated in
-// fp32 registers over at most kFlushFrames frames, then folded into a CTA-private
-// fp64 tile; a second kernel adds the CTA tiles in a fixed order (deterministic).
+// Precision plan (north star: covariances within 1e-6 of the fp64 oracle, and
+// TICA eigenvectors amplify covariance error by 1/gap): products are fp32 FMAs
+// of conditioned (|z| ~ 1) data, accumulated in fp32 registers over only
+// kFoldFrames = 32 frames starting from zero, then folded into fp64 REGISTER
+// accumulators (one F2F + DADD per 32 FFMAs); each CTA writes its fp64 tile once
+// and a second kernel adds the CTA tiles in a fixed order (deterministic).
 //
 // Tiling: 128x128 output tile per CTA (only tiles on/above the diagonal), 8x8
 // micro-tile per thread, 8-frame shared-memory stages with register prefetch,
@@ -20,7 +22,7 @@ namespace pmb {
 constexpr int kGT = 128;            // tile edge
 constexpr int kGBK = 8;             // frames per stage
 constexpr int kGThreads = 256;
-constexpr int kFlushFrames = 512;   // fp32 accumulation extent
+constexpr int kFoldFrames = 32;     // fp32 accumulation extent before the fp64 fold
 constexpr int kGramTargetCtas = 2 * kNumSMs;
 
 struct GramParams {
@@ -58,7 +60,7 @@ __device__ __forceinline__ float4 cond4(float4 x, float4 sh, float4 sc) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kGThreads, 2) gram_simt_kernel(GramParams p) {
+__global__ void __launch_bounds__(kGThreads, 1) gram_simt_kernel(GramParams p) {
   __shared__ __align__(16) float As[2][kGBK][kGT];
   __shared__ __align__(16) float Bs[2][kGBK][kGT];
 
@@ -95,13 +97,13 @@ __global__ void __launch_bounds__(kGThreads, 2) gram_simt_kernel(GramParams p) {
   const int n_stages = g_begin < g_end ? (int)((g_end - g_begin + kGBK - 1) / kGBK) : 0;
 
   float acc[8][8];
+  double dacc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) { acc[i][j] = 0.f; dacc[i][j] = 0.0; }
 
   double* P = p.part + ((size_t)blockIdx.x * p.n_chunks + blockIdx.y) * (kGT * kGT);
-  bool first_flush = true;
 
   float4 pa, pb;
   float pw;
@@ -134,32 +136,14 @@ __global__ void __launch_bounds__(kGThreads, 2) gram_simt_kernel(GramParams p) {
         make_float4(pa.x * pw, pa.y * pw, pa.z * pw, pa.w * pw);
     *reinterpret_cast<float4*>(&Bs[buf][fr][c4]) = pb;
   };
-  auto flush = [&]() {
+  auto fold = [&]() {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int jh = 0; jh < 2; ++jh) {
-        const int col = jh * 64 + tx * 4;
-        double2* dst = reinterpret_cast<double2*>(P + row * kGT + col);
-        double2 v0, v1;
-        if (first_flush) {
-          v0 = make_double2(0.0, 0.0);
-          v1 = v0;
-        } else {
-          v0 = dst[0];
-          v1 = dst[1];
-        }
-        v0.x += (double)acc[i][jh * 4 + 0];
-        v0.y += (double)acc[i][jh * 4 + 1];
-        v1.x += (double)acc[i][jh * 4 + 2];
-        v1.y += (double)acc[i][jh * 4 + 3];
-        dst[0] = v0;
-        dst[1] = v1;
-        acc[i][jh * 4 + 0] = acc[i][jh * 4 + 1] = acc[i][jh * 4 + 2] = acc[i][jh * 4 + 3] = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        dacc[i][j] += (double)acc[i][j];
+        acc[i][j] = 0.f;
       }
-    }
-    first_flush = false;
   };
 
   int buf = 0;
@@ -187,9 +171,19 @@ __global__ void __launch_bounds__(kGThreads, 2) gram_simt_kernel(GramParams p) {
     if (has_next) stash(buf ^ 1);
     __syncthreads();
     buf ^= 1;
-    if (((s + 1) % (kFlushFrames / kGBK)) == 0 || !has_next) flush();
+    if (((s + 1) % (kFoldFrames / kGBK)) == 0 || !has_next) fold();
   }
-  if (first_flush) flush();  // empty chunk: write zeros so the reduction can read it
+  // one write of the CTA's fp64 tile (zeros for an empty chunk)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      double2* dst = reinterpret_cast<double2*>(P + row * kGT + jh * 64 + tx * 4);
+      dst[0] = make_double2(dacc[i][jh * 4 + 0], dacc[i][jh * 4 + 1]);
+      dst[1] = make_double2(dacc[i][jh * 4 + 2], dacc[i][jh * 4 + 3]);
+    }
+  }
 }
 
 // G[i][j] = sum over chunks (fixed order); lower triangle mirrored.
@@ -260,7 +254,7 @@ extern "C" int pmb_gram(const float* X, int64_t n, int d, int64_t ld, const uint
   const int nt = gram_tiles(d);
   int nc = gram_chunks(d);
   int64_t chunk = (n + nc - 1) / nc;
-  chunk = ((chunk + kFlushFrames - 1) / kFlushFrames) * kFlushFrames;
+  chunk = ((chunk + kFoldFrames - 1) / kFoldFrames) * kFoldFrames;
   nc = (int)((n + chunk - 1) / chunk);
   p.n_chunks = nc;
   p.chunk = chunk;

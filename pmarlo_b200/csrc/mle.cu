@@ -12,10 +12,18 @@
 //  * one CTA per problem (batched; K <= kMleCtaMaxK): x, q, u live in shared
 //    memory, S is re-read from L2, barriers are __syncthreads -- this is the
 //    ITS sweep path (one CTA per lag time);
-//  * one cooperative grid per problem (large K): rows are spread over all SMs,
-//    u goes through a global double buffer and ONE grid barrier per iteration;
-//    every CTA recomputes the normalisation and the error in the same order, so
-//    all CTAs take the same branch without a second barrier.
+//  * one cooperative grid per problem (large K): rows are spread over all SMs
+//    (a CTA's rows of S stay L1-resident across iterations), u goes through a
+//    global double buffer and a flag-based all-gather instead of a grid barrier:
+//    every CTA publishes "generation g written" in its own flag word
+//    (st.release), the consumers poll the 148 flags in parallel (ld.acquire) and
+//    then read u from L2 -- one L2 round trip after the slowest producer.  Every
+//    CTA recomputes the normalisation and the error in the same order, so all
+//    CTAs take the same branch.  The launch is cooperative only to guarantee
+//    co-residency of the CTAs that poll one another.
+// The K^2 divisions per iteration use an fp32-seeded reciprocal with two fp64
+// Newton steps (<= 1.5 ulp from the IEEE quotient; the fixed point is a
+// contraction, so iterates track the reference's to ~1e-13).
 // All reductions have a fixed order: results are bit-reproducible run to run.
 // A state with active[i] == 0 is excluded (T_ii = 1, pi_i = 0), which is how the
 // caller restricts the estimate to the largest connected set without
@@ -30,7 +38,7 @@ namespace pmb {
 
 constexpr int kMleThreads = 1024;
 constexpr int kMleCtaMaxK = 2048;
-constexpr int kMleGridThreads = 512;
+constexpr int kMleGridThreads = 256;
 
 struct MleParams {
   const double* C;        // batch x K x K
@@ -45,7 +53,22 @@ struct MleParams {
   double* S;              // batch x K x K workspace
   double* cvec;           // batch x K workspace
   double* ubuf;           // 2 x K (grid kernel only)
+  unsigned long long* flags;  // gridDim.x generation counters, 16 words apart (grid kernel only)
 };
+
+constexpr int kFlagStride = 16;  // 128 B between the flag words of different CTAs
+
+// 1/d for d > 0: fp32 seed + two Newton steps in fp64 (falls back to the IEEE
+// quotient outside the fp32 exponent range).
+__device__ __forceinline__ double fast_rcp(double d) {
+  if (!(d > 1e-30 && d < 1e30)) return 1.0 / d;
+  double r = (double)__frcp_rn(__double2float_rn(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
 
 // deterministic CTA-wide sum / max; every thread gets the result
 __device__ __forceinline__ double cta_sum(double v, double* s_red) {
@@ -107,12 +130,16 @@ __global__ void mle_rowsum_kernel(MleParams p) {
 
 __device__ __forceinline__ double row_apply(const double* __restrict__ Srow, const double* q, double qi,
                                             int K, int lane) {
-  double acc = 0.0;
-  for (int j = lane; j < K; j += 32) {
-    const double s = Srow[j];
-    if (s != 0.0) acc += s / (qi + q[j]);
+  double acc0 = 0.0, acc1 = 0.0;
+  int j = lane;
+  for (; j + 32 < K; j += 64) {
+    const double s0 = Srow[j], s1 = Srow[j + 32];
+    const double r0 = fast_rcp(qi + q[j]), r1 = fast_rcp(qi + q[j + 32]);
+    acc0 = fma(s0, r0, acc0);
+    acc1 = fma(s1, r1, acc1);
   }
-  return warp_sum(acc);
+  if (j < K) acc0 = fma(Srow[j], fast_rcp(qi + q[j]), acc0);
+  return warp_sum(acc0 + acc1);
 }
 
 // ---------------------------------------------------------------- one CTA per problem
@@ -206,8 +233,33 @@ __global__ void __launch_bounds__(kMleThreads) mle_cta_kernel(MleParams p) {
 }
 
 // ---------------------------------------------------------------- cooperative grid, one problem
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// publish generation g of this CTA's rows, then wait until every CTA has published it
+__device__ __forceinline__ void gather_sync(unsigned long long* flags, unsigned long long gen) {
+  __syncthreads();  // all row results of this CTA are written
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release_u64(flags + (size_t)blockIdx.x * kFlagStride, gen);
+  }
+  for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
+    const unsigned long long* f = flags + (size_t)c * kFlagStride;
+    unsigned int spins = 0;
+    while (ld_acquire_u64(f) < gen) {
+      if (++spins > (1u << 24)) __trap();  // a lost CTA must not hang the GPU
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double sm[];
   __shared__ double s_red[32];
   const int K = p.K;
@@ -216,23 +268,28 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
   const int tid = threadIdx.x, lane = tid & 31;
   const int gwarp = (blockIdx.x * blockDim.x + tid) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const double* S = p.S;
-  const double* c = p.cvec;
+  const double* __restrict__ S = p.S;
+  const double* __restrict__ c = p.cvec;
   const uint8_t* act = p.active;
-  double* u0 = p.ubuf;
-  double* u1 = p.ubuf + K;
+  unsigned long long gen = 0;
 
-  for (int i = gwarp; i < K; i += nwarps) {
-    double acc = 0.0;
-    for (int j = lane; j < K; j += 32) acc += S[(size_t)i * K + j];
-    acc = warp_sum(acc);
-    if (lane == 0) u0[i] = acc;
+  // generation 1: row sums of S
+  {
+    double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
+    for (int i = gwarp; i < K; i += nwarps) {
+      double acc = 0.0;
+      for (int j = lane; j < K; j += 32) acc += S[(size_t)i * K + j];
+      acc = warp_sum(acc);
+      if (lane == 0) ub[i] = acc;
+    }
+    ++gen;
+    gather_sync(p.flags, gen);
   }
-  grid.sync();
+  const double* ucur = p.ubuf + (size_t)(gen & 1) * K;
   double part = 0.0;
   int bad = 0;
   for (int i = tid; i < K; i += blockDim.x) {
-    part += u0[i];
+    part += __ldcg(ucur + i);
     const bool on = !act || act[i];
     if (on && !(c[i] > 0.0)) bad = 1;
   }
@@ -242,21 +299,23 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     if (blockIdx.x == 0 && tid == 0) { p.info[0] = 0; p.info[1] = -1; }
     return;
   }
-  for (int i = tid; i < K; i += blockDim.x) x[i] = u0[i] / tot;
+  for (int i = tid; i < K; i += blockDim.x) x[i] = __ldcg(ucur + i) / tot;
   __syncthreads();
 
   long long it = 0;
   double err = 1.7976931348623157e308;
-  double* ucur = u1;
   while (it < p.maxiter && err > p.maxerr) {
     for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] / x[i] : 0.0;
     __syncthreads();
+    double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
     for (int i = gwarp; i < K; i += nwarps) {
       double r = 0.0;
       if (x[i] > 0.0) r = row_apply(S + (size_t)i * K, q, q[i], K, lane);
-      if (lane == 0) ucur[i] = r;
+      if (lane == 0) ub[i] = r;
     }
-    grid.sync();
+    ++gen;
+    gather_sync(p.flags, gen);
+    ucur = ub;
     part = 0.0;
     for (int i = tid; i < K; i += blockDim.x) part += __ldcg(ucur + i);
     const double norm = cta_sum(part, s_red);
@@ -268,33 +327,34 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     }
     err = cta_max(e, s_red);
     ++it;
-    ucur = (ucur == u1) ? u0 : u1;
   }
   for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] / x[i] : 0.0;
   __syncthreads();
+  double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
   for (int i = gwarp; i < K; i += nwarps) {
     const bool on = x[i] > 0.0;
     double rs = 0.0;
     if (on) rs = row_apply(S + (size_t)i * K, q, q[i], K, lane);
-    if (lane == 0) ucur[i] = rs;
+    if (lane == 0) ub[i] = rs;
     const double qi = q[i];
     for (int j = lane; j < K; j += 32) {
       double t;
       if (on && rs > 0.0) {
         const double s = S[(size_t)i * K + j];
-        t = (s != 0.0) ? (s / (qi + q[j])) / rs : 0.0;
+        t = (s != 0.0) ? (s * fast_rcp(qi + q[j])) / rs : 0.0;
       } else {
         t = (i == j) ? 1.0 : 0.0;
       }
       p.T[(size_t)i * K + j] = t;
     }
   }
-  grid.sync();
+  ++gen;
+  gather_sync(p.flags, gen);
   part = 0.0;
-  for (int i = tid; i < K; i += blockDim.x) part += __ldcg(ucur + i);
+  for (int i = tid; i < K; i += blockDim.x) part += __ldcg(ub + i);
   const double rtot = cta_sum(part, s_red);
   for (int i = blockIdx.x * blockDim.x + tid; i < K; i += gridDim.x * blockDim.x)
-    p.pi[i] = __ldcg(ucur + i) / rtot;
+    p.pi[i] = __ldcg(ub + i) / rtot;
   if (blockIdx.x == 0 && tid == 0) { p.info[0] = it; p.info[1] = (err <= p.maxerr) ? 1 : 0; }
 }
 
@@ -302,7 +362,8 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
 
 extern "C" size_t pmb_mle_rev_ws_bytes(int K, int batch) {
   if (K <= 0 || batch <= 0) return 0;
-  return ((size_t)batch * K * K + (size_t)batch * K + 2 * (size_t)K) * sizeof(double) + 64;
+  return ((size_t)batch * K * K + (size_t)batch * K + 2 * (size_t)K) * sizeof(double) + 64 +
+         (size_t)256 * pmb::kFlagStride * sizeof(unsigned long long);
 }
 
 extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int batch, double alpha, double maxerr,
@@ -322,6 +383,7 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
   p.S = static_cast<double*>(ws);
   p.cvec = p.S + (size_t)batch * K * K;
   p.ubuf = p.cvec + (size_t)batch * K;
+  p.flags = reinterpret_cast<unsigned long long*>(p.ubuf + 2 * (size_t)K);
   {
     dim3 g((K + 31) / 32, (K + 31) / 32, batch), b(32, 8);
     mle_prepare_kernel<<<g, b, 0, st>>>(p);
@@ -350,7 +412,8 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
   const int warps_per_cta = kMleGridThreads / 32;
   int grid = (K + warps_per_cta - 1) / warps_per_cta;
   if (grid > sms * per_sm) grid = sms * per_sm;
-  if (grid > sms) grid = sms;  // one CTA per SM keeps the barrier cheap
+  if (grid > sms) grid = sms;  // one CTA per SM
+  if (grid > 256) grid = 256;  // flag words reserved in the workspace
   for (int b = 0; b < batch; ++b) {
     MleParams pb = p;
     pb.active = active ? active + (size_t)b * K : nullptr;
@@ -359,6 +422,7 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
     pb.info = p.info + 2 * b;
     pb.S = p.S + (size_t)b * K * K;
     pb.cvec = p.cvec + (size_t)b * K;
+    PMB_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)256 * kFlagStride * sizeof(unsigned long long), st));
     void* args[] = {&pb};
     PMB_CUDA(cudaLaunchCooperativeKernel((void*)mle_grid_kernel, dim3(grid), dim3(kMleGridThreads), args,
                                          smem, st));

@@ -19,7 +19,7 @@ namespace pmb {
 
 constexpr int kJacThreads = 1024;
 constexpr int kJacMaxSweeps = 40;
-constexpr double kJacTol = 1e-15;
+constexpr double kJacTol = 4.5e-16;  // x sqrt(n): rounding noise of an n-term dot product (cf. LAPACK dgesvj)
 
 // ------------------------------------------------------------ Jacobi (device)
 // W: n x n (rows = vectors), V: n x n or nullptr.  Returns number of sweeps.
@@ -56,7 +56,7 @@ __device__ int jacobi_onesided(double* __restrict__ W, double* __restrict__ V, i
         a = warp_sum(a);
         b = warp_sum(b);
         g = warp_sum(g);
-        if (fabs(g) <= kJacTol * sqrt(a * b) || g == 0.0) continue;
+        if (fabs(g) <= kJacTol * sqrt((double)n) * sqrt(a * b) || g == 0.0) continue;
         rotated = 1;
         const double zeta = (b - a) / (2.0 * g);
         const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
