@@ -121,7 +121,8 @@ PMB_API int pmb_tica_covariances(const double* G0, const double* G1, const doubl
  * Replaces deeptime.numeric.eig_corr / spd_inv_split (scipy eigh/schur) behind
  * TICA.fit: C00 = V S V^T, drop |s| <= eps, L = V S^-1/2, eigh(L^T C0t L),
  * sort by |lambda| desc, canonical signs.  evals: d, evecs: d x d (first
- * `rank` columns valid, NOT kinetic-map scaled), rank: 1 int32. */
+ * `rank` columns valid, NOT kinetic-map scaled), rank: int32[4] = {rank, Jacobi
+ * sweeps of the C00 problem, sweeps of the reduced problem, reserved}. */
 PMB_API size_t pmb_tica_solve_ws_bytes(int d);
 PMB_API int pmb_tica_solve(const double* C00, const double* C0t, int d, double eps,
                    double* evals, double* evecs, int32_t* rank,
@@ -185,6 +186,13 @@ PMB_API int pmb_count_lagged_weighted(const int32_t* labels, const double* weigh
  * active[i] = (rowsum_i + colsum_i > eps).  Cf: K x K fp64, active: K bytes. */
 PMB_API int pmb_counts_active(const int64_t* C, int K, double eps, double* Cf, uint8_t* active,
                       pmb_stream_t stream);
+
+/* Self-test of the tcgen05 plumbing (descriptor encodings, TMEM round trip): one
+ * 128 x N x Kdim TF32 tile product.  mode 0: A (128 x Kdim), B (N x Kdim) row-major
+ * (K-major, no swizzle: the k-means score layout); mode 1: A (Kdim x 128),
+ * B (Kdim x N) row-major (MN-major, 128 B swizzle: the Gram layout).  D: 128 x N fp32. */
+PMB_API int pmb_tc_selftest(const float* A, const float* B, int N, int Kdim, int mode, float* D,
+                            pmb_stream_t stream);
 
 /* ---- K8 reversible maximum-likelihood MSM -----------------------------------------
  * Replaces deeptime MaximumLikelihoodMSM(reversible=True).fit(counts)

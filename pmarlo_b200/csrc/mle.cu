@@ -259,6 +259,9 @@ __device__ __forceinline__ void gather_sync(unsigned long long* flags, unsigned 
   __syncthreads();
 }
 
+// REG: one row per warp with K <= 1024: the warp keeps its row of S in registers (32 doubles per
+// lane) for the whole iteration, so an iteration touches no memory but the K-vector exchange.
+template <bool REG>
 __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double s_red[32];
@@ -268,6 +271,28 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
   const int tid = threadIdx.x, lane = tid & 31;
   const int gwarp = (blockIdx.x * blockDim.x + tid) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  double sreg[32];
+  if constexpr (REG) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const int j = lane + 32 * t;
+      sreg[t] = (gwarp < K && j < K) ? p.S[(size_t)gwarp * K + j] : 0.0;
+    }
+  }
+  auto apply_row = [&](int i, const double* qv, double qi) -> double {
+    if constexpr (REG) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 32; t += 2) {
+        const int j0 = lane + 32 * t, j1 = j0 + 32;
+        if (j0 < K) a0 = fma(sreg[t], fast_rcp(qi + qv[j0]), a0);
+        if (j1 < K) a1 = fma(sreg[t + 1], fast_rcp(qi + qv[j1]), a1);
+      }
+      return warp_sum(a0 + a1);
+    } else {
+      return row_apply(p.S + (size_t)i * K, qv, qi, K, lane);
+    }
+  };
   const double* __restrict__ S = p.S;
   const double* __restrict__ c = p.cvec;
   const uint8_t* act = p.active;
@@ -305,12 +330,12 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
   long long it = 0;
   double err = 1.7976931348623157e308;
   while (it < p.maxiter && err > p.maxerr) {
-    for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] / x[i] : 0.0;
+    for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] * fast_rcp(x[i]) : 0.0;
     __syncthreads();
     double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
     for (int i = gwarp; i < K; i += nwarps) {
       double r = 0.0;
-      if (x[i] > 0.0) r = row_apply(S + (size_t)i * K, q, q[i], K, lane);
+      if (x[i] > 0.0) r = apply_row(i, q, q[i]);
       if (lane == 0) ub[i] = r;
     }
     ++gen;
@@ -318,11 +343,11 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     ucur = ub;
     part = 0.0;
     for (int i = tid; i < K; i += blockDim.x) part += __ldcg(ucur + i);
-    const double norm = cta_sum(part, s_red);
+    const double rnorm = 1.0 / cta_sum(part, s_red);
     double e = 0.0;
     for (int i = tid; i < K; i += blockDim.x) {
-      const double xo = x[i], xn = __ldcg(ucur + i) / norm;
-      if (xo > 0.0 || xn > 0.0) e = fmax(e, fabs(xo - xn) / (0.5 * (xo + xn)));
+      const double xo = x[i], xn = __ldcg(ucur + i) * rnorm;
+      if (xo > 0.0 || xn > 0.0) e = fmax(e, fabs(xo - xn) * fast_rcp(0.5 * (xo + xn)));
       x[i] = xn;
     }
     err = cta_max(e, s_red);
@@ -334,7 +359,7 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
   for (int i = gwarp; i < K; i += nwarps) {
     const bool on = x[i] > 0.0;
     double rs = 0.0;
-    if (on) rs = row_apply(S + (size_t)i * K, q, q[i], K, lane);
+    if (on) rs = apply_row(i, q, q[i]);
     if (lane == 0) ub[i] = rs;
     const double qi = q[i];
     for (int j = lane; j < K; j += 32) {
@@ -402,9 +427,10 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
   }
   const size_t smem = (size_t)2 * K * sizeof(double);
   PMB_REQUIRE(smem <= 200 * 1024, "pmb_mle_rev: K=%d too large", K);
-  PMB_CUDA(cudaFuncSetAttribute(mle_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PMB_CUDA(cudaFuncSetAttribute(mle_grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PMB_CUDA(cudaFuncSetAttribute(mle_grid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mle_grid_kernel, kMleGridThreads, smem));
+  PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mle_grid_kernel<true>, kMleGridThreads, smem));
   PMB_REQUIRE(per_sm >= 1, "pmb_mle_rev: kernel does not fit on an SM");
   int dev = 0, sms = 0;
   PMB_CUDA(cudaGetDevice(&dev));
@@ -424,7 +450,9 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
     pb.cvec = p.cvec + (size_t)b * K;
     PMB_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)256 * kFlagStride * sizeof(unsigned long long), st));
     void* args[] = {&pb};
-    PMB_CUDA(cudaLaunchCooperativeKernel((void*)mle_grid_kernel, dim3(grid), dim3(kMleGridThreads), args,
+    const bool reg = (K <= 1024) && ((long long)grid * warps_per_cta >= K);
+    PMB_CUDA(cudaLaunchCooperativeKernel(reg ? (void*)mle_grid_kernel<true> : (void*)mle_grid_kernel<false>,
+                                         dim3(grid), dim3(kMleGridThreads), args,
                                          smem, st));
     count_launch();
   }

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kJacThreads) tica_solve_kernel(
     ws.V[i] = (r == c) ? 1.0 : 0.0;
   }
   __syncthreads();
-  jacobi_onesided(ws.W, ws.V, d, &s_flag);
+  const int sweeps1 = jacobi_onesided(ws.W, ws.V, d, &s_flag);
   for (int j = tid; j < d; j += nt) {
     double acc = 0.0;
     for (int e = 0; e < d; ++e) acc = fma(ws.V[(size_t)j * d + e], ws.W[(size_t)j * d + e], acc);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kJacThreads) tica_solve_kernel(
   __syncthreads();
   const int m = s_m;
   if (m == 0) {
-    if (tid == 0) *rank_out = 0;
+    if (tid == 0) { rank_out[0] = 0; rank_out[1] = sweeps1; rank_out[2] = 0; }
     for (size_t i = tid; i < dd; i += nt) evecs[i] = 0.0;
     for (int j = tid; j < d; j += nt) evals[j] = 0.0;
     return;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kJacThreads) tica_solve_kernel(
   const double sigma = 1.0625 * inf_norm(ws.W, m, s_red) + 1e-300;
   for (int j = tid; j < m; j += nt) ws.W[(size_t)j * m + j] += sigma;
   __syncthreads();
-  jacobi_onesided(ws.W, ws.V, m, &s_flag);
+  const int sweeps2 = jacobi_onesided(ws.W, ws.V, m, &s_flag);
   for (int j = tid; j < m; j += nt) {
     double acc = 0.0;
     for (int e = 0; e < m; ++e) acc = fma(ws.V[(size_t)j * m + e], ws.W[(size_t)j * m + e], acc);
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kJacThreads) tica_solve_kernel(
     evals[k] = ws.s[ws.order[k]];
   }
   for (int k = m + tid; k < d; k += nt) evals[k] = 0.0;
-  if (tid == 0) *rank_out = m;
+  if (tid == 0) { rank_out[0] = m; rank_out[1] = sweeps1; rank_out[2] = sweeps2; }
 }
 
 // ------------------------------------------------------------ batched eigenvalues

@@ -137,7 +137,7 @@ def tica_solve(C00: torch.Tensor, C0t: torch.Tensor, eps: float = 1e-6):
     dev = C00.device
     evals = torch.empty((d,), dtype=torch.float64, device=dev)
     evecs = torch.empty((d, d), dtype=torch.float64, device=dev)
-    rank = torch.zeros((1,), dtype=torch.int32, device=dev)
+    rank = torch.zeros((4,), dtype=torch.int32, device=dev)
     L = _lib.lib()
     ws = _ws(L.pmb_tica_solve_ws_bytes(d), dev)
     check(L.pmb_tica_solve(ptr(C00.contiguous()), ptr(C0t.contiguous()), d, float(eps), ptr(evals),
@@ -317,6 +317,21 @@ def eig_rev_topk(T: torch.Tensor, pi: torch.Tensor, k: int, max_steps: int = 0):
     if squeeze:
         return evals[0], info[0]
     return evals, info
+
+
+def tc_selftest(A: torch.Tensor, B: torch.Tensor, mode: int) -> torch.Tensor:
+    """One 128 x N x Kdim TF32 tile product through tcgen05 (see pmb200.h)."""
+    _dev(A, torch.float32, "A")
+    _dev(B, torch.float32, "B")
+    A, B = A.contiguous(), B.contiguous()
+    if mode == 0:
+        kdim, n = int(A.shape[1]), int(B.shape[0])
+    else:
+        kdim, n = int(A.shape[0]), int(B.shape[1])
+    D = torch.empty((128, n), dtype=torch.float32, device=A.device)
+    check(_lib.lib().pmb_tc_selftest(ptr(A), ptr(B), n, kdim, int(mode), ptr(D), stream_handle(A.device)),
+          "pmb_tc_selftest")
+    return D
 
 
 def as_numpy(t: torch.Tensor) -> np.ndarray:

@@ -59,7 +59,7 @@ class TicaModel:
 
     @property
     def rank(self) -> int:
-        return int(self.rank_dev.item())
+        return int(self.rank_dev[0].item())
 
     @property
     def output_dim(self) -> int:
