@@ -271,8 +271,9 @@ def gpu_arm(args):
 
     # ---- device-resident timing -------------------------------------------------
     timer = StageTimer(True)
+    bufs: dict = {}
     for _ in range(args.warmup):
-        run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, read_back=True)
+        run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, read_back=True, buffers=bufs)
     sync()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -281,7 +282,7 @@ def gpu_arm(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        res = run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, timer=timer, read_back=True)
+        res = run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, timer=timer, read_back=True, buffers=bufs)
     ev1.record()
     sync()
     launches = _lib.launch_count() - l0
@@ -300,12 +301,12 @@ def gpu_arm(args):
     torch.cuda.empty_cache()
     lengths = [fpt] * n_traj
     for _ in range(max(1, min(2, args.warmup))):
-        out = estimate_msm_from_host(host, lengths, wl.plan, cfg, comm)
+        out = estimate_msm_from_host(host, lengths, wl.plan, cfg, comm, buffers=bufs)
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.e2e_steps):
-        out = estimate_msm_from_host(host, lengths, wl.plan, cfg, comm)
+        out = estimate_msm_from_host(host, lengths, wl.plan, cfg, comm, buffers=bufs)
     e1.record()
     sync()
     ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -344,6 +345,7 @@ def gpu_arm(args):
                 "ms_per_step": e2e_ms},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "stages_ms": stages, "kmeans_iters_run": int(res.kmeans_iters),
+        "tica_rank_sweeps": [int(v) for v in res.tica.rank_dev.tolist()],
         "mle_iters": int(res.mle_info[0].item()), "timescales": [None if not np.isfinite(t) else float(t)
                                                                 for t in (res.timescales if res.timescales is not None else [])],
     }

@@ -242,19 +242,29 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// publish generation g of this CTA's rows, then wait until every CTA has published it
+// publish generation g of this CTA's rows, then wait until every CTA has published it.
+// Only warp 0 polls (relaxed loads; one fence after the loop): polling with acquire loads from
+// every thread costs a memory barrier per poll and floods L2.
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void gather_sync(unsigned long long* flags, unsigned long long gen) {
   __syncthreads();  // all row results of this CTA are written
-  if (threadIdx.x == 0) {
-    __threadfence();
-    st_release_u64(flags + (size_t)blockIdx.x * kFlagStride, gen);
-  }
-  for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
-    const unsigned long long* f = flags + (size_t)c * kFlagStride;
-    unsigned int spins = 0;
-    while (ld_acquire_u64(f) < gen) {
-      if (++spins > (1u << 24)) __trap();  // a lost CTA must not hang the GPU
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      st_release_u64(flags + (size_t)blockIdx.x * kFlagStride, gen);
     }
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += 32) {
+      const unsigned long long* f = flags + (size_t)c * kFlagStride;
+      unsigned int spins = 0;
+      while (ld_relaxed_u64(f) < gen) {
+        if (++spins > (1u << 24)) __trap();  // a lost CTA must not hang the GPU
+      }
+    }
+    __threadfence();  // acquire side: order the u reads below after the flag observations
   }
   __syncthreads();
 }
@@ -268,9 +278,11 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
   const int K = p.K;
   double* x = sm;
   double* q = sm + K;
+  double* cs = sm + 2 * K;   // row sums of the (regularised) counts, staged once
   const int tid = threadIdx.x, lane = tid & 31;
   const int gwarp = (blockIdx.x * blockDim.x + tid) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = tid; i < K; i += blockDim.x) cs[i] = p.cvec[i];
   double sreg[32];
   if constexpr (REG) {
 #pragma unroll
@@ -330,7 +342,7 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
   long long it = 0;
   double err = 1.7976931348623157e308;
   while (it < p.maxiter && err > p.maxerr) {
-    for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] * fast_rcp(x[i]) : 0.0;
+    for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? cs[i] * fast_rcp(x[i]) : 0.0;
     __syncthreads();
     double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
     for (int i = gwarp; i < K; i += nwarps) {
@@ -353,7 +365,7 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     err = cta_max(e, s_red);
     ++it;
   }
-  for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? c[i] / x[i] : 0.0;
+  for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? cs[i] / x[i] : 0.0;
   __syncthreads();
   double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
   for (int i = gwarp; i < K; i += nwarps) {
@@ -425,7 +437,7 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
     PMB_LAUNCH_CHECK();
     return PMB_OK;
   }
-  const size_t smem = (size_t)2 * K * sizeof(double);
+  const size_t smem = (size_t)3 * K * sizeof(double);
   PMB_REQUIRE(smem <= 200 * 1024, "pmb_mle_rev: K=%d too large", K);
   PMB_CUDA(cudaFuncSetAttribute(mle_grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PMB_CUDA(cudaFuncSetAttribute(mle_grid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

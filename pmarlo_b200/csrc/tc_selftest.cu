@@ -15,8 +15,10 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  unsigned char* sA = smem;                                   // 128 * Kdim * 4 bytes
-  unsigned char* sB = smem + (size_t)128 * Kdim * 4;          // N * Kdim * 4 bytes (1024-aligned: Kdim % 8 == 0)
+  // swizzle patterns are functions of the ABSOLUTE shared address: align the tile base by hand
+  // (static __shared__ variables precede the dynamic region, which is only 16 B aligned)
+  unsigned char* sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // 128 * Kdim * 4 bytes
+  unsigned char* sB = sA + (size_t)128 * Kdim * 4;            // N * Kdim * 4 bytes (1024-aligned: Kdim % 8 == 0)
   uint32_t cols = 32;
   while (cols < (uint32_t)N) cols <<= 1;
 

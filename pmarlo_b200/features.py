@@ -95,7 +95,12 @@ class FeaturePlan:
     periodic: np.ndarray = field(default_factory=lambda: np.zeros((0,), dtype=bool))
 
     def device_units(self, device) -> torch.Tensor:
-        return torch.from_numpy(np.ascontiguousarray(self.units, dtype=np.int32)).to(device)
+        """Unit list on the device (uploaded once per device and cached)."""
+        cache = self.__dict__.setdefault("_dev_units", {})
+        key = str(device)
+        if key not in cache:
+            cache[key] = torch.from_numpy(np.ascontiguousarray(self.units, dtype=np.int32)).to(device)
+        return cache[key]
 
 
 def _unit(kind, atoms, col_value=-1, col_cos=-1, col_sin=-1):

@@ -82,18 +82,30 @@ def seeded_initial_centers(Y: torch.Tensor, K: int, seed: int, comm: Comm) -> to
 def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | None, cfg: PipelineConfig,
                  comm: Comm | None = None, features: torch.Tensor | None = None,
                  initial_centers: torch.Tensor | None = None, timer: StageTimer | None = None,
-                 read_back: bool = True) -> PipelineResult:
+                 read_back: bool = True, buffers: dict | None = None) -> PipelineResult:
     """Run the whole path on this rank's shard.  Either ``xyz`` (+ ``plan``) or
     precomputed ``features`` (N,d) float32 must be given; with ``cfg.tica_dim <= 0``
-    the features are clustered directly (config C2: 2-D Mueller-Brown data)."""
+    the features are clustered directly (config C2: 2-D Mueller-Brown data).
+    ``buffers``: a dict that keeps the large per-frame tensors (features, Y, labels) alive between
+    calls so that repeated runs on same-sized shards do not go through the allocator."""
     comm = comm if comm is not None else Comm()
     timer = timer if timer is not None else NULL_TIMER
     dev = (xyz if xyz is not None else features).device
     off = segs.device(dev)
 
+    def _buf(name, shape, dtype):
+        if buffers is None:
+            return None
+        t = buffers.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            buffers[name] = t
+        return t
+
     if features is None:
+        out = _buf("features", (int(xyz.shape[0]), plan.n_cols), torch.float32)
         with timer.stage("featurize"):
-            features = featurize_device(xyz, plan)
+            features = featurize_device(xyz, plan, out=out)
     X = features
 
     tica_model = None
@@ -102,14 +114,17 @@ def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | N
             est = TICA(cfg.tica_lag, cfg.tica_dim, preprocess=cfg.preprocess, comm=comm, gram_impl=cfg.gram_impl)
             tica_model = est.fit_device(X, segs, off, timer=timer)
         with timer.stage("project"):
-            Y = est.transform_device(tica_model, X, out_f64=False)
+            Y = est.transform_device(tica_model, X, out_f64=False,
+                                     out=_buf("Y", (int(X.shape[0]), tica_model.dim), torch.float32))
     else:
         Y = X
 
     with timer.stage("kmeans"):
         if initial_centers is None:
             initial_centers = seeded_initial_centers(Y, cfg.n_states, cfg.seed, comm)
-        labels = torch.empty((int(Y.shape[0]),), dtype=torch.int32, device=dev)
+        labels = _buf("labels", (int(Y.shape[0]),), torch.int32)
+        if labels is None:
+            labels = torch.empty((int(Y.shape[0]),), dtype=torch.int32, device=dev)
         res = lloyd_device(Y, initial_centers, cfg.kmeans_max_iter, cfg.kmeans_tolerance, comm, labels=labels,
                            timer=timer)
         # final labels against the final centres (model.transform, clustering.py:609)
@@ -137,7 +152,7 @@ def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | N
 
 
 def estimate_msm_from_host(xyz_host, lengths, plan: FeaturePlan, cfg: PipelineConfig, comm: Comm | None = None,
-                           device=None) -> dict:
+                           device=None, buffers: dict | None = None) -> dict:
     """The call a user of the host-buffer API makes: coordinates of this rank's
     trajectories in (pinned) host memory -> timescales, eigenvalues, stationary
     vector and MLE diagnostics as numpy arrays.  The host->device copy of the
@@ -145,11 +160,18 @@ def estimate_msm_from_host(xyz_host, lengths, plan: FeaturePlan, cfg: PipelineCo
     device = device if device is not None else kernels.require_cuda()
     if isinstance(xyz_host, np.ndarray):
         xyz_host = torch.from_numpy(np.ascontiguousarray(xyz_host, dtype=np.float32))
-    xyz = xyz_host.to(device, non_blocking=True)
+    if buffers is not None:
+        xyz = buffers.get("xyz")
+        if xyz is None or tuple(xyz.shape) != tuple(xyz_host.shape) or xyz.device != device:
+            xyz = torch.empty(tuple(xyz_host.shape), dtype=torch.float32, device=device)
+            buffers["xyz"] = xyz
+        xyz.copy_(xyz_host, non_blocking=True)
+    else:
+        xyz = xyz_host.to(device, non_blocking=True)
     segs = Segments.from_lengths(lengths)
     if segs.n_frames != int(xyz.shape[0]):
         raise ValueError("lengths do not add up to the number of frames")
-    res = run_pipeline(xyz, segs, plan, cfg, comm, read_back=False)
+    res = run_pipeline(xyz, segs, plan, cfg, comm, read_back=False, buffers=buffers)
     ev = res.eigenvalues.cpu().numpy()
     pi = res.pi.cpu().numpy()
     info = res.mle_info.cpu().numpy()
