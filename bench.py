@@ -346,6 +346,7 @@ def gpu_arm(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "stages_ms": stages, "kmeans_iters_run": int(res.kmeans_iters),
         "tica_rank_sweeps": [int(v) for v in res.tica.rank_dev.tolist()],
+        "mle_phase_cycles": debug_counters(),
         "mle_iters": int(res.mle_info[0].item()), "timescales": [None if not np.isfinite(t) else float(t)
                                                                 for t in (res.timescales if res.timescales is not None else [])],
     }
@@ -353,6 +354,16 @@ def gpu_arm(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def debug_counters():
+    import ctypes
+
+    from pmarlo_b200 import _lib
+
+    buf = (ctypes.c_int64 * 8)()
+    _lib.check(_lib.lib().pmb_debug_counters(ctypes.cast(buf, ctypes.c_void_p)), "pmb_debug_counters")
+    return list(buf)
 
 
 def roofline(stages, counts, frames, cfg, peaks, args):

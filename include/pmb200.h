@@ -190,7 +190,7 @@ PMB_API int pmb_counts_active(const int64_t* C, int K, double eps, double* Cf, u
 /* Self-test of the tcgen05 plumbing (descriptor encodings, TMEM round trip): one
  * 128 x N x Kdim TF32 tile product.  mode 0: A (128 x Kdim), B (N x Kdim) row-major
  * (K-major, no swizzle: the k-means score layout); mode 1: A (Kdim x 128),
- * B (Kdim x N) row-major (MN-major, 128 B swizzle: the Gram layout).  D: 128 x N fp32. */
+ * B (Kdim x N) row-major (MN-major, 128 B swizzle with 32 B base: the Gram layout).  D: 128 x N fp32. */
 PMB_API int pmb_tc_selftest(const float* A, const float* B, int N, int Kdim, int mode, float* D,
                             pmb_stream_t stream);
 
@@ -211,6 +211,11 @@ PMB_API size_t pmb_mle_rev_ws_bytes(int K, int batch);
 PMB_API int pmb_mle_rev(const double* C, const uint8_t* active, int K, int batch, double alpha,
                 double maxerr, int64_t maxiter, double* T, double* pi, int64_t* info,
                 void* ws, size_t ws_bytes, pmb_stream_t stream);
+
+/* Diagnostics: cycle counters of the last cooperative MLE run, HOST pointer to 8 int64:
+ * {iterations, q phase, row phase, exchange, norm/err phase, CTAs, register path, 0}.
+ * Synchronises the device. */
+PMB_API int pmb_debug_counters(int64_t* out8_host);
 
 /* ---- K9 leading eigenvalues of a reversible T ----------------------------------------
  * Replaces deeptime.markov.tools.analysis.eigenvalues(T, k, reversible=True, mu)

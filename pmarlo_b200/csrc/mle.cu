@@ -269,6 +269,8 @@ __device__ __forceinline__ void gather_sync(unsigned long long* flags, unsigned 
   __syncthreads();
 }
 
+__device__ long long g_dbg[8];  // phase cycle counters of the last grid-kernel run (CTA 0, thread 0)
+
 // REG: one row per warp with K <= 1024: the warp keeps its row of S in registers (32 doubles per
 // lane) for the whole iteration, so an iteration touches no memory but the K-vector exchange.
 template <bool REG>
@@ -341,17 +343,22 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
 
   long long it = 0;
   double err = 1.7976931348623157e308;
+  long long cyc[4] = {0, 0, 0, 0};
   while (it < p.maxiter && err > p.maxerr) {
+    const long long t0 = clock64();
     for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? cs[i] * fast_rcp(x[i]) : 0.0;
     __syncthreads();
+    const long long t1 = clock64();
     double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
     for (int i = gwarp; i < K; i += nwarps) {
       double r = 0.0;
       if (x[i] > 0.0) r = apply_row(i, q, q[i]);
       if (lane == 0) ub[i] = r;
     }
+    const long long t2 = clock64();
     ++gen;
     gather_sync(p.flags, gen);
+    const long long t3 = clock64();
     ucur = ub;
     part = 0.0;
     for (int i = tid; i < K; i += blockDim.x) part += __ldcg(ucur + i);
@@ -364,6 +371,12 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     }
     err = cta_max(e, s_red);
     ++it;
+    const long long t4 = clock64();
+    cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    g_dbg[0] = it; g_dbg[1] = cyc[0]; g_dbg[2] = cyc[1]; g_dbg[3] = cyc[2]; g_dbg[4] = cyc[3];
+    g_dbg[5] = gridDim.x; g_dbg[6] = REG ? 1 : 0;
   }
   for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? cs[i] / x[i] : 0.0;
   __syncthreads();
@@ -468,5 +481,14 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
                                          smem, st));
     count_launch();
   }
+  return PMB_OK;
+}
+
+extern "C" int pmb_debug_counters(int64_t* out8) {
+  using namespace pmb;
+  PMB_REQUIRE(out8 != nullptr, "pmb_debug_counters: null pointer");
+  long long h[8];
+  PMB_CUDA(cudaMemcpyFromSymbol(h, g_dbg, sizeof(h)));
+  for (int i = 0; i < 8; ++i) out8[i] = h[i];
   return PMB_OK;
 }

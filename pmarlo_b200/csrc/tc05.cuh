@@ -17,7 +17,7 @@ namespace tc {
 //   [0,14)  start address >> 4        [16,30) leading-dimension byte offset >> 4
 //   [32,46) stride-dimension byte offset >> 4     [46,48) version = 1 (sm_100)
 //   [49,52) base offset (0: atoms are 1024 B aligned)   [61,64) layout type
-enum : uint64_t { kLayoutNone = 0, kLayoutSw128 = 2, kLayoutSw64 = 4, kLayoutSw32 = 6 };
+enum : uint64_t { kLayoutNone = 0, kLayoutSw128Base32 = 1, kLayoutSw128 = 2, kLayoutSw64 = 4, kLayoutSw32 = 6 };
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                               uint64_t layout) {
@@ -94,11 +94,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ uint32_t off_kmajor(int row, int k /*fp32 index*/, uint32_t lbo, uint32_t sbo) {
   return (uint32_t)(row >> 3) * sbo + (uint32_t)(k >> 2) * lbo + (uint32_t)(row & 7) * 16u + (uint32_t)(k & 3) * 4u;
 }
-// MN-major, 128-byte swizzle: an atom is 8 k-rows of 128 B (32 fp32 along M/N), 16-byte chunks XOR-ed
-// with the k-row index; atoms adjacent in M/N are `lbo` apart, adjacent in K (8 rows) `sbo` apart.
-__device__ __forceinline__ uint32_t off_mnmajor_sw128(int mn, int k, uint32_t lbo, uint32_t sbo) {
-  const uint32_t k8 = (uint32_t)k & 7u, chunk = ((uint32_t)mn & 31u) >> 2;
-  return ((uint32_t)mn >> 5) * lbo + ((uint32_t)k >> 3) * sbo + k8 * 128u + ((chunk ^ k8) << 4) + ((uint32_t)mn & 3u) * 4u;
+// MN-major fp32/tf32 operands: the only layout the tensor core accepts is the 128-byte swizzle with
+// a 32-byte base (layout type 1): an atom is 4 k-rows of 128 B (32 fp32 along M/N); the 32-byte chunk
+// index (address bits 5-6) is XOR-ed with the k-row index (address bits 7-8).  Atoms adjacent in M/N
+// are `lbo` apart, adjacent in K (4 rows) `sbo` apart; one K = 8 instruction spans two atoms in K.
+__device__ __forceinline__ uint32_t off_mnmajor_sw128b32(int mn, int k, uint32_t lbo, uint32_t sbo) {
+  const uint32_t k4 = (uint32_t)k & 3u, chunk = ((uint32_t)mn & 31u) >> 3;
+  return ((uint32_t)mn >> 5) * lbo + ((uint32_t)k >> 2) * sbo + k4 * 128u + ((chunk ^ k4) << 5) + ((uint32_t)mn & 7u) * 4u;
 }
 
 }  // namespace tc

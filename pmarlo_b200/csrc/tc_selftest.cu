@@ -3,7 +3,7 @@
 // descriptor encodings are validated in isolation (tests/test_gpu_tc.py) before a
 // kernel that depends on them is trusted:
 //   mode 0: A (128 x Kdim), B (N x Kdim) row-major  -> K-major, no swizzle   (k-means scores)
-//   mode 1: A (Kdim x 128), B (Kdim x N) row-major  -> MN-major, 128B swizzle (Gram X^T X)
+//   mode 1: A (Kdim x 128), B (Kdim x N) row-major  -> MN-major, 128B swizzle with 32B base (Gram X^T X)
 // D (128 x N) fp32 = A B^T resp. A^T B with fp32 accumulation in TMEM.
 #include "tc05.cuh"
 
@@ -42,14 +42,14 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
     }
   } else {
     lbo = (uint32_t)Kdim * 128u;
-    sbo = 1024u;
+    sbo = 512u;
     for (int i = tid; i < Kdim * 128; i += 128) {
       const int k = i / 128, m = i - k * 128;
-      *reinterpret_cast<float*>(sA + tc::off_mnmajor_sw128(m, k, lbo, sbo)) = A[i];
+      *reinterpret_cast<float*>(sA + tc::off_mnmajor_sw128b32(m, k, lbo, sbo)) = A[i];
     }
     for (int i = tid; i < Kdim * N; i += 128) {
       const int k = i / N, n = i - k * N;
-      *reinterpret_cast<float*>(sB + tc::off_mnmajor_sw128(n, k, lbo, sbo)) = B[i];
+      *reinterpret_cast<float*>(sB + tc::off_mnmajor_sw128b32(n, k, lbo, sbo)) = B[i];
     }
   }
   fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor (async) proxy
@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
 
   if (tid == 0) {
     const uint32_t idesc = tc::idesc_tf32(128, N, mode, mode);
-    const uint64_t layout = mode == 0 ? tc::kLayoutNone : tc::kLayoutSw128;
+    const uint64_t layout = mode == 0 ? tc::kLayoutNone : tc::kLayoutSw128Base32;
     for (int s = 0; s < Kdim / 8; ++s) {
-      const uint32_t step = mode == 0 ? (uint32_t)s * 2u * lbo : (uint32_t)s * sbo;
+      const uint32_t step = mode == 0 ? (uint32_t)s * 2u * lbo : (uint32_t)s * 2u * sbo;
       const uint64_t da = tc::smem_desc(smem_u32(sA) + step, lbo, sbo, layout);
       const uint64_t db = tc::smem_desc(smem_u32(sB) + step, lbo, sbo, layout);
       tc::mma_tf32(tmem, da, db, idesc, s > 0 ? 1u : 0u);
