@@ -56,7 +56,6 @@ struct MleParams {
   unsigned long long* flags;  // gridDim.x generation counters, 16 words apart (grid kernel only)
 };
 
-constexpr int kFlagStride = 16;  // 128 B between the flag words of different CTAs
 
 // 1/d for d > 0: fp32 seed + two Newton steps in fp64 (falls back to the IEEE
 // quotient outside the fp32 exponent range).
@@ -233,46 +232,50 @@ __global__ void __launch_bounds__(kMleThreads) mle_cta_kernel(MleParams p) {
 }
 
 // ---------------------------------------------------------------- cooperative grid, one problem
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+// Exchange of the K-vector u between CTAs without fences (NCCL "LL" style): every double is
+// published as two 8-byte words, each carrying 32 data bits and a 32-bit generation tag; an aligned
+// 8-byte store is single-copy atomic, so a consumer that sees the expected tag in both words has the
+// whole value.  Consumers spin on the data itself: one L2 round trip after the producer's store.
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned int tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)tag << 32);
+  const unsigned long long w1 = (bits >> 32) | ((unsigned long long)tag << 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ double ll_load(const unsigned long long* slot, unsigned int tag) {
+  unsigned long long w0, w1;
+  unsigned int spins = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    if ((unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag) break;
+    if (++spins > (1u << 24)) __trap();  // a lost producer must not hang the GPU
+  }
+  return __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
 }
 
-// publish generation g of this CTA's rows, then wait until every CTA has published it.
-// Only warp 0 polls (relaxed loads; one fence after the loop): polling with acquire loads from
-// every thread costs a memory barrier per poll and floods L2.
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+// reciprocal of d > 0 from an fp32 seed r0 ~ 1/d (rel. error <= 2^-21): ONE Newton step in fp64
+// (rel. error <= 2^-42); the seed is widened to fp64 with integer ops, not an fp64-pipe convert.
+__device__ __forceinline__ double widen_pos(float f) {
+  const unsigned int fb = __float_as_uint(f);
+  return __hiloint2double((int)((fb >> 3) + 0x38000000u), (int)(fb << 29));
 }
-__device__ __forceinline__ void gather_sync(unsigned long long* flags, unsigned long long gen) {
-  __syncthreads();  // all row results of this CTA are written
-  if (threadIdx.x < 32) {
-    if (threadIdx.x == 0) {
-      __threadfence();
-      st_release_u64(flags + (size_t)blockIdx.x * kFlagStride, gen);
-    }
-    for (int c = threadIdx.x; c < (int)gridDim.x; c += 32) {
-      const unsigned long long* f = flags + (size_t)c * kFlagStride;
-      unsigned int spins = 0;
-      while (ld_relaxed_u64(f) < gen) {
-        if (++spins > (1u << 24)) __trap();  // a lost CTA must not hang the GPU
-      }
-    }
-    __threadfence();  // acquire side: order the u reads below after the flag observations
-  }
-  __syncthreads();
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ double rcp_newton1(double d, float df) {
+  const double r0 = widen_pos(rcp_approx(df));
+  const double e = fma(-d, r0, 1.0);
+  return fma(r0, e, r0);
 }
 
 __device__ long long g_dbg[8];  // phase cycle counters of the last grid-kernel run (CTA 0, thread 0)
 
 // REG: one row per warp with K <= 1024: the warp keeps its row of S in registers (32 doubles per
 // lane) for the whole iteration, so an iteration touches no memory but the K-vector exchange.
+// SIMT fp64 runs at ~1/16 of the fp32 rate on B200, so the kernel is built to minimise fp64
+// instructions: 4 per matrix element (add, 2 Newton FMAs, accumulate FMA).
 template <bool REG>
 __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) {
   extern __shared__ __align__(16) double sm[];
@@ -281,9 +284,13 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
   double* x = sm;
   double* q = sm + K;
   double* cs = sm + 2 * K;   // row sums of the (regularised) counts, staged once
+  double* us = sm + 3 * K;   // gathered u of the current generation
+  float* qf = reinterpret_cast<float*>(sm + 4 * K);   // fp32 image of q (reciprocal seeds)
   const int tid = threadIdx.x, lane = tid & 31;
   const int gwarp = (blockIdx.x * blockDim.x + tid) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint8_t* act = p.active;
+  unsigned long long* xb = reinterpret_cast<unsigned long long*>(p.ubuf);   // 2 generations x K x 2 words
   for (int i = tid; i < K; i += blockDim.x) cs[i] = p.cvec[i];
   double sreg[32];
   if constexpr (REG) {
@@ -293,44 +300,56 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
       sreg[t] = (gwarp < K && j < K) ? p.S[(size_t)gwarp * K + j] : 0.0;
     }
   }
-  auto apply_row = [&](int i, const double* qv, double qi) -> double {
+  // sum_j S_ij / (q_i + q_j) for row i (warp-wide)
+  auto apply_row = [&](int i, double qi, float qfi) -> double {
+    double a0 = 0.0, a1 = 0.0;
     if constexpr (REG) {
-      double a0 = 0.0, a1 = 0.0;
 #pragma unroll
       for (int t = 0; t < 32; t += 2) {
         const int j0 = lane + 32 * t, j1 = j0 + 32;
-        if (j0 < K) a0 = fma(sreg[t], fast_rcp(qi + qv[j0]), a0);
-        if (j1 < K) a1 = fma(sreg[t + 1], fast_rcp(qi + qv[j1]), a1);
+        if (j0 < K) a0 = fma(sreg[t], rcp_newton1(qi + q[j0], qfi + qf[j0]), a0);
+        if (j1 < K) a1 = fma(sreg[t + 1], rcp_newton1(qi + q[j1], qfi + qf[j1]), a1);
       }
-      return warp_sum(a0 + a1);
     } else {
-      return row_apply(p.S + (size_t)i * K, qv, qi, K, lane);
+      const double* __restrict__ Srow = p.S + (size_t)i * K;
+      int j = lane;
+      for (; j + 32 < K; j += 64) {
+        const double s0 = Srow[j], s1 = Srow[j + 32];
+        a0 = fma(s0, rcp_newton1(qi + q[j], qfi + qf[j]), a0);
+        a1 = fma(s1, rcp_newton1(qi + q[j + 32], qfi + qf[j + 32]), a1);
+      }
+      if (j < K) a0 = fma(Srow[j], rcp_newton1(qi + q[j], qfi + qf[j]), a0);
     }
+    return warp_sum(a0 + a1);
   };
-  const double* __restrict__ S = p.S;
-  const double* __restrict__ c = p.cvec;
-  const uint8_t* act = p.active;
-  unsigned long long gen = 0;
+  // publish row results of generation `gen`, gather the whole vector into us[]
+  auto exchange_store = [&](unsigned int gen, int i, double v) {
+    ll_store(xb + ((size_t)(gen & 1u) * K + i) * 2, v, gen);
+  };
+  auto exchange_gather = [&](unsigned int gen) {
+    for (int i = tid; i < K; i += blockDim.x) us[i] = ll_load(xb + ((size_t)(gen & 1u) * K + i) * 2, gen);
+  };
 
-  // generation 1: row sums of S
-  {
-    double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
-    for (int i = gwarp; i < K; i += nwarps) {
-      double acc = 0.0;
-      for (int j = lane; j < K; j += 32) acc += S[(size_t)i * K + j];
-      acc = warp_sum(acc);
-      if (lane == 0) ub[i] = acc;
+  unsigned int gen = 1;
+  // generation 1: row sums of S -> x0
+  for (int i = gwarp; i < K; i += nwarps) {
+    double acc = 0.0;
+    if constexpr (REG) {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) acc += sreg[t];
+    } else {
+      for (int j = lane; j < K; j += 32) acc += p.S[(size_t)i * K + j];
     }
-    ++gen;
-    gather_sync(p.flags, gen);
+    acc = warp_sum(acc);
+    if (lane == 0) exchange_store(gen, i, acc);
   }
-  const double* ucur = p.ubuf + (size_t)(gen & 1) * K;
+  exchange_gather(gen);
   double part = 0.0;
   int bad = 0;
   for (int i = tid; i < K; i += blockDim.x) {
-    part += __ldcg(ucur + i);
+    part += us[i];
     const bool on = !act || act[i];
-    if (on && !(c[i] > 0.0)) bad = 1;
+    if (on && !(cs[i] > 0.0)) bad = 1;
   }
   const double tot = cta_sum(part, s_red);
   bad = __syncthreads_or(bad);
@@ -338,82 +357,86 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     if (blockIdx.x == 0 && tid == 0) { p.info[0] = 0; p.info[1] = -1; }
     return;
   }
-  for (int i = tid; i < K; i += blockDim.x) x[i] = __ldcg(ucur + i) / tot;
+  for (int i = tid; i < K; i += blockDim.x) {
+    const double xn = us[i] / tot;
+    x[i] = xn;
+    const double qn = (xn > 0.0) ? cs[i] / xn : 0.0;
+    q[i] = qn;
+    qf[i] = (float)qn;
+  }
   __syncthreads();
 
   long long it = 0;
-  double err = 1.7976931348623157e308;
+  int notconv = 1;
   long long cyc[4] = {0, 0, 0, 0};
-  while (it < p.maxiter && err > p.maxerr) {
+  while (it < p.maxiter && notconv) {
     const long long t0 = clock64();
-    for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? cs[i] * fast_rcp(x[i]) : 0.0;
-    __syncthreads();
-    const long long t1 = clock64();
-    double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
+    ++gen;
     for (int i = gwarp; i < K; i += nwarps) {
       double r = 0.0;
-      if (x[i] > 0.0) r = apply_row(i, q, q[i]);
-      if (lane == 0) ub[i] = r;
+      if (x[i] > 0.0) r = apply_row(i, q[i], qf[i]);
+      if (lane == 0) exchange_store(gen, i, r);
     }
+    const long long t1 = clock64();
+    exchange_gather(gen);
     const long long t2 = clock64();
-    ++gen;
-    gather_sync(p.flags, gen);
-    const long long t3 = clock64();
-    ucur = ub;
     part = 0.0;
-    for (int i = tid; i < K; i += blockDim.x) part += __ldcg(ucur + i);
-    const double rnorm = 1.0 / cta_sum(part, s_red);
-    double e = 0.0;
+    for (int i = tid; i < K; i += blockDim.x) part += us[i];
+    const double norm = cta_sum(part, s_red);      // includes the barrier that orders us[] writes
+    const double rnorm = 1.0 / norm;
+    __syncthreads();                               // every warp has finished reading q of this iteration
+    int flag = 0;
     for (int i = tid; i < K; i += blockDim.x) {
-      const double xo = x[i], xn = __ldcg(ucur + i) * rnorm;
-      if (xo > 0.0 || xn > 0.0) e = fmax(e, fabs(xo - xn) * fast_rcp(0.5 * (xo + xn)));
+      const double xo = x[i], xn = us[i] * rnorm;
+      // |xo - xn| / (0.5 (xo + xn)) > maxerr  without the division
+      if (fabs(xo - xn) > p.maxerr * 0.5 * (xo + xn)) flag = 1;
       x[i] = xn;
+      double qn = 0.0;
+      if (xn > 0.0) qn = cs[i] * rcp_newton1(xn, (float)xn);
+      q[i] = qn;
+      qf[i] = (float)qn;
     }
-    err = cta_max(e, s_red);
+    notconv = __syncthreads_or(flag);
     ++it;
-    const long long t4 = clock64();
-    cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
+    const long long t3 = clock64();
+    cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2;
   }
   if (blockIdx.x == 0 && tid == 0) {
-    g_dbg[0] = it; g_dbg[1] = cyc[0]; g_dbg[2] = cyc[1]; g_dbg[3] = cyc[2]; g_dbg[4] = cyc[3];
-    g_dbg[5] = gridDim.x; g_dbg[6] = REG ? 1 : 0;
+    g_dbg[0] = it; g_dbg[1] = cyc[0]; g_dbg[2] = cyc[1]; g_dbg[3] = cyc[2]; g_dbg[4] = 0;
+    g_dbg[5] = gridDim.x; g_dbg[6] = REG ? 1 : 0; g_dbg[7] = 0;
   }
-  for (int i = tid; i < K; i += blockDim.x) q[i] = (x[i] > 0.0) ? cs[i] / x[i] : 0.0;
-  __syncthreads();
-  double* ub = p.ubuf + (size_t)((gen + 1) & 1) * K;
+  // final application with the last x: T rows and pi
+  ++gen;
   for (int i = gwarp; i < K; i += nwarps) {
     const bool on = x[i] > 0.0;
     double rs = 0.0;
-    if (on) rs = apply_row(i, q, q[i]);
-    if (lane == 0) ub[i] = rs;
+    if (on) rs = apply_row(i, q[i], qf[i]);
+    if (lane == 0) exchange_store(gen, i, rs);
     const double qi = q[i];
     for (int j = lane; j < K; j += 32) {
       double t;
       if (on && rs > 0.0) {
-        const double s = S[(size_t)i * K + j];
-        t = (s != 0.0) ? (s * fast_rcp(qi + q[j])) / rs : 0.0;
+        const double s = p.S[(size_t)i * K + j];
+        t = (s != 0.0) ? (s / (qi + q[j])) / rs : 0.0;
       } else {
         t = (i == j) ? 1.0 : 0.0;
       }
       p.T[(size_t)i * K + j] = t;
     }
   }
-  ++gen;
-  gather_sync(p.flags, gen);
+  exchange_gather(gen);
   part = 0.0;
-  for (int i = tid; i < K; i += blockDim.x) part += __ldcg(ub + i);
+  for (int i = tid; i < K; i += blockDim.x) part += us[i];
   const double rtot = cta_sum(part, s_red);
-  for (int i = blockIdx.x * blockDim.x + tid; i < K; i += gridDim.x * blockDim.x)
-    p.pi[i] = __ldcg(ub + i) / rtot;
-  if (blockIdx.x == 0 && tid == 0) { p.info[0] = it; p.info[1] = (err <= p.maxerr) ? 1 : 0; }
+  for (int i = blockIdx.x * blockDim.x + tid; i < K; i += gridDim.x * blockDim.x) p.pi[i] = us[i] / rtot;
+  if (blockIdx.x == 0 && tid == 0) { p.info[0] = it; p.info[1] = notconv ? 0 : 1; }
 }
 
 }  // namespace pmb
 
 extern "C" size_t pmb_mle_rev_ws_bytes(int K, int batch) {
   if (K <= 0 || batch <= 0) return 0;
-  return ((size_t)batch * K * K + (size_t)batch * K + 2 * (size_t)K) * sizeof(double) + 64 +
-         (size_t)256 * pmb::kFlagStride * sizeof(unsigned long long);
+  return ((size_t)batch * K * K + (size_t)batch * K + 4 * (size_t)K + 8) * sizeof(double) + 64;
 }
 
 extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int batch, double alpha, double maxerr,
@@ -432,8 +455,13 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
   p.T = T; p.pi = pi; p.info = reinterpret_cast<long long*>(info);
   p.S = static_cast<double*>(ws);
   p.cvec = p.S + (size_t)batch * K * K;
-  p.ubuf = p.cvec + (size_t)batch * K;
-  p.flags = reinterpret_cast<unsigned long long*>(p.ubuf + 2 * (size_t)K);
+  {
+    // exchange buffer: 2 generations x K x 2 words, 16-byte aligned
+    uintptr_t a = reinterpret_cast<uintptr_t>(p.cvec + (size_t)batch * K);
+    a = (a + 15) & ~(uintptr_t)15;
+    p.ubuf = reinterpret_cast<double*>(a);
+    p.flags = nullptr;
+  }
   {
     dim3 g((K + 31) / 32, (K + 31) / 32, batch), b(32, 8);
     mle_prepare_kernel<<<g, b, 0, st>>>(p);
@@ -450,7 +478,7 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
     PMB_LAUNCH_CHECK();
     return PMB_OK;
   }
-  const size_t smem = (size_t)3 * K * sizeof(double);
+  const size_t smem = (size_t)4 * K * sizeof(double) + (size_t)K * sizeof(float);
   PMB_REQUIRE(smem <= 200 * 1024, "pmb_mle_rev: K=%d too large", K);
   PMB_CUDA(cudaFuncSetAttribute(mle_grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PMB_CUDA(cudaFuncSetAttribute(mle_grid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -464,7 +492,6 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
   int grid = (K + warps_per_cta - 1) / warps_per_cta;
   if (grid > sms * per_sm) grid = sms * per_sm;
   if (grid > sms) grid = sms;  // one CTA per SM
-  if (grid > 256) grid = 256;  // flag words reserved in the workspace
   for (int b = 0; b < batch; ++b) {
     MleParams pb = p;
     pb.active = active ? active + (size_t)b * K : nullptr;
@@ -473,7 +500,7 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
     pb.info = p.info + 2 * b;
     pb.S = p.S + (size_t)b * K * K;
     pb.cvec = p.cvec + (size_t)b * K;
-    PMB_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)256 * kFlagStride * sizeof(unsigned long long), st));
+    PMB_CUDA(cudaMemsetAsync(p.ubuf, 0, (size_t)4 * K * sizeof(double), st));   // tags start at 1
     void* args[] = {&pb};
     const bool reg = (K <= 1024) && ((long long)grid * warps_per_cta >= K);
     PMB_CUDA(cudaLaunchCooperativeKernel(reg ? (void*)mle_grid_kernel<true> : (void*)mle_grid_kernel<false>,

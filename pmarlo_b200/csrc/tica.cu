@@ -366,6 +366,9 @@ __global__ void tica_finalize_kernel(const double* __restrict__ evals, const dou
   }
 }
 
+int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double eps, double* evals, double* evecs,
+                           int32_t* rank, void* ws, cudaStream_t st);  // tica_grid.cu
+
 int sym_eigvals_launch(double* A, int n, int batch, double* evals, double* scratch, int* order,
                        cudaStream_t st) {
   sym_eigvals_kernel<<<batch, kJacThreads, 0, st>>>(A, n, evals, scratch, order);
@@ -396,6 +399,7 @@ extern "C" int pmb_tica_solve(const double* C00, const double* C0t, int d, doubl
   w.W = base; w.V = base + dd; w.L = base + 2 * dd; w.TMP = base + 3 * dd; w.M = base + 4 * dd;
   w.s = base + 5 * dd;
   w.order = reinterpret_cast<int*>(base + 5 * dd + d);
+  if (d >= 48) return tica_solve_grid_launch(C00, C0t, d, eps, evals, evecs, rank, ws, as_stream(stream));
   tica_solve_kernel<<<1, kJacThreads, 0, as_stream(stream)>>>(C00, C0t, d, eps, evals, evecs, rank, w);
   PMB_LAUNCH_CHECK();
   return PMB_OK;
