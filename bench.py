@@ -41,6 +41,10 @@ N_DIST = 128
 FRAMES_PER_TRAJ = 125_000
 TICA_LAG, TICA_DIM, N_STATES, KMEANS_ITERS, MSM_LAG, N_TIMESCALES = 20, 10, 1000, 20, 20, 5
 METRIC = "frames/sec end-to-end MSM pipeline"
+# CPU arm: the reversible-MLE fixed point costs ~3 ms per iteration on the host (K^2 = 10^6 cells) whatever the
+# number of frames, and a small sample's sparse count matrix needs > 50 000 iterations.  The full C4 count
+# matrix (10 M frames) converges in ~10^3 iterations (bench.py prints mle_iters), so the CPU sample is capped there.
+CPU_MLE_ITER_CAP = 1000
 UNIT = "frames/s"
 
 
@@ -176,7 +180,8 @@ def run_cpu_pipeline(trajs, n_states=N_STATES, kmeans_iters=KMEANS_ITERS):
     psi = ofeat.dihedral_quads(top.names, top.resid, top.chainid, "psi")
     pairs = ofeat.ca_pairs_all(ofeat.ca_indices(top.names))[:N_DIST]
     return opipe.run(trajs, phi, psi, pairs, tica_lag=TICA_LAG, tica_dim=TICA_DIM, n_states=n_states,
-                     kmeans_iters=kmeans_iters, msm_lag=MSM_LAG, n_timescales=N_TIMESCALES, seed=4)
+                     kmeans_iters=kmeans_iters, msm_lag=MSM_LAG, n_timescales=N_TIMESCALES, seed=4,
+                     mle_maxiter=CPU_MLE_ITER_CAP)
 
 
 def cpu_threads() -> int:
@@ -212,7 +217,8 @@ def reference_arm(args):
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     value = res.n_frames / dt
     sample = (f"{n_traj} trajectories x {n_frames} frames of the C4 workload per step (same shapes, K={N_STATES}, "
-              f"{KMEANS_ITERS} Lloyd iterations), numpy/scipy BLAS + sklearn Lloyd on {cores} threads")
+              f"{KMEANS_ITERS} Lloyd iterations, reversible MLE capped at {CPU_MLE_ITER_CAP} iterations = what the full "
+              f"10 M-frame count matrix needs), numpy/scipy BLAS + sklearn Lloyd on {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -279,12 +285,16 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStart()   # ncu --profile-from-start off: only the timed steps
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         res = run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, timer=timer, read_back=True, buffers=bufs)
     ev1.record()
     sync()
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
@@ -332,8 +342,9 @@ def gpu_arm(args):
         v, secs, cres = time_cpu(2, args.cpu_sample_frames // 2)
         cpu = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
                "sample": f"2 trajectories x {args.cpu_sample_frames // 2} frames of the same workload "
-                         f"(K={N_STATES}, {KMEANS_ITERS} Lloyd iterations), {secs:.1f} s of oracle work; the "
-                         "K^2-sized MLE/eigen stages do not shrink with the sample",
+                         f"(K={N_STATES}, {KMEANS_ITERS} Lloyd iterations, reversible MLE capped at {CPU_MLE_ITER_CAP} "
+                         f"iterations), {secs:.1f} s of oracle work on {cpu_threads()} threads; the K^2-sized "
+                         "MLE/eigen stages do not shrink with the sample",
                "stages_s": {k: round(v2, 3) for k, v2 in cres.stage_seconds.items()}}
 
     line = {
@@ -416,9 +427,11 @@ def main():
                     help="frames of this rank's shard (default: the whole of C4, 10 M frames = 80 trajectories "
                          "x 125 000, on every GPU; weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample-frames", type=int, default=20_000)
+    ap.add_argument("--cpu-sample-frames", type=int, default=40_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gram-impl", type=int, default=0)
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("note: fewer than 3 warm-up steps", file=sys.stderr)

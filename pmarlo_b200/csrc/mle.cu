@@ -242,15 +242,32 @@ __device__ __forceinline__ void ll_store(unsigned long long* slot, double v, uns
   const unsigned long long w1 = (bits >> 32) | ((unsigned long long)tag << 32);
   asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ double ll_load(const unsigned long long* slot, unsigned int tag) {
+__device__ __forceinline__ bool ll_try_load(const unsigned long long* slot, unsigned int tag, double& out) {
   unsigned long long w0, w1;
-  unsigned int spins = 0;
-  while (true) {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
-    if ((unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag) break;
-    if (++spins > (1u << 24)) __trap();  // a lost producer must not hang the GPU
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  out = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+  return (unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag;
+}
+// gather entries i = tid, tid + nthreads, ... of generation `tag` into dst[]: four independent
+// polls in flight per thread (a dependent chain of L2 round trips would cost ~1000 cycles each)
+__device__ __forceinline__ void ll_gather(const unsigned long long* base, unsigned int tag, double* dst, int K) {
+  const int nt = blockDim.x;
+  for (int i0 = threadIdx.x; i0 < K; i0 += 4 * nt) {
+    double v[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ok[u] = (i0 + u * nt >= K);
+    unsigned int spins = 0;
+    while (!(ok[0] && ok[1] && ok[2] && ok[3])) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (!ok[u]) ok[u] = ll_try_load(base + (size_t)(i0 + u * nt) * 2, tag, v[u]);
+      if (++spins > (1u << 24)) __trap();  // a lost producer must not hang the GPU
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * nt < K) dst[i0 + u * nt] = v[u];
   }
-  return __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
 }
 
 // reciprocal of d > 0 from an fp32 seed r0 ~ 1/d (rel. error <= 2^-21): ONE Newton step in fp64
@@ -327,7 +344,7 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     ll_store(xb + ((size_t)(gen & 1u) * K + i) * 2, v, gen);
   };
   auto exchange_gather = [&](unsigned int gen) {
-    for (int i = tid; i < K; i += blockDim.x) us[i] = ll_load(xb + ((size_t)(gen & 1u) * K + i) * 2, gen);
+    ll_gather(xb + (size_t)(gen & 1u) * K * 2, gen, us, K);
   };
 
   unsigned int gen = 1;
@@ -383,8 +400,8 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     part = 0.0;
     for (int i = tid; i < K; i += blockDim.x) part += us[i];
     const double norm = cta_sum(part, s_red);      // includes the barrier that orders us[] writes
-    const double rnorm = 1.0 / norm;
-    __syncthreads();                               // every warp has finished reading q of this iteration
+    double rnorm = rcp_newton1(norm, (float)norm);  // two Newton steps: full fp64 accuracy
+    rnorm = fma(rnorm, fma(-norm, rnorm, 1.0), rnorm);
     int flag = 0;
     for (int i = tid; i < K; i += blockDim.x) {
       const double xo = x[i], xn = us[i] * rnorm;
