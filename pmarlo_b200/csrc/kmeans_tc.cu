@@ -1,0 +1,434 @@
+// kmeans_tc.cu -- K6 (tensor-core path): nearest-centre assignment as a tcgen05 TF32 GEMM with the
+// argmin fused into the TMEM epilogue, labels bit-exact against the fp64 oracle.
+//
+//   score(t,k) = |y_t|^2 + |c_k|^2 - 2 y_t.c_k            (one 128 x 256 x KS MMA tile per chunk)
+//
+// The product is made fp32-accurate on TF32 tensor cores by splitting along the MMA K dimension
+// ("3xTF32 in K"): every coordinate d contributes three K slots
+//      A (frame side):  y_hi  y_lo  y_hi        B (centre side):  c'_hi  c'_hi  c'_lo     (c' = -2 c)
+// and the norms ride in spare slots (|c|^2 as three TF32 pieces against 1.0, |y|^2 as two pieces),
+// so the accumulator that leaves TMEM already is the squared distance.  KS = 3 D + 5 rounded up to 8.
+//
+// Pipeline (one persistent CTA per SM, 21 warps, warp-specialised, mbarrier hand-offs):
+//   warps 17-20  producers : build the A tile (128 frames x KS slots, K-major core-matrix layout)
+//                            of tile i, then FINALISE tile i-1 (merge, certainty test, labels,
+//                            fused Lloyd accumulation)
+//   warp  16     MMA issuer: per 256-centre chunk KS/8 tcgen05.mma into one of two TMEM buffers
+//   warps 0-15   epilogue  : tcgen05.ld 64 columns per warp and chunk, running (best, second) as
+//                            packed integer keys (score bits with the column in the low 5 bits)
+// The centre operand B (Kpad x KS) is staged once per CTA and stays resident in shared memory.
+//
+// Exactness: a frame whose best and second-best scores are closer than a bound on the arithmetic
+// error (operand rounding, dropped lo.lo terms, tensor-core accumulation, key truncation) is NOT
+// labelled here: it goes to a list, and kmeans_recheck_kernel re-evaluates it against all centres
+// in fp64 with the oracle's operation order (oracle/kmeans.py::sqdist_direct), one warp per frame.
+#include "tc05.cuh"
+
+namespace pmb {
+
+constexpr int kTcTile = 128;     // frames per tile  (MMA M)
+constexpr int kTcChunk = 256;    // centres per MMA  (MMA N)
+constexpr int kTcEpiWarps = 16;
+constexpr int kTcProdWarps = 4;
+constexpr int kTcMmaWarp = kTcEpiWarps;
+constexpr int kTcThreads = (kTcEpiWarps + 1 + kTcProdWarps) * 32;   // 672
+constexpr int kTcColsPerWarp = kTcChunk / (kTcEpiWarps / 4);        // 64
+constexpr float kTcErrScale = 1.9073486e-6f;   // 2^-19: envelope of the score error in units of (|y| + |c|max)^2
+constexpr float kTcKeyTrunc = 1.0f + 7.6293945e-6f;  // 1 + 2^-17 (5 key bits of a 23-bit mantissa dropped)
+
+struct KmTcParams {
+  const float* Y;
+  int64_t n;
+  int D;
+  int64_t ld;
+  const double* centers;
+  int K;
+  int Kpad;   // K rounded up to a multiple of 256 (dummy centres score 2^126)
+  int KS;     // K slots per row, multiple of 8
+  int32_t* labels;
+  double* sums;
+  int64_t* counts;
+  double* inertia;
+  int64_t* n_rechecked;
+  int* recheck_list;    // n entries
+  int* recheck_count;   // zeroed by the host wrapper
+  float* dbg_scores;    // n x Kpad (tests only) or nullptr
+};
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct TcSmem {
+  uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], r_full[2], r_empty[2];
+  uint32_t tmem_slot;
+  float cmax;
+  float red[32];
+  int res_best[2][4][kTcTile];
+  int res_second[2][4][kTcTile];
+  int res_chunk[2][4][kTcTile];
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KS = p.KS, D = p.D, K = p.K, Kpad = p.Kpad;
+  const uint32_t lbo = 128u, sbo = (uint32_t)(KS / 4) * 128u;
+  unsigned char* sB = smem_raw;                                   // Kpad x KS floats
+  unsigned char* sA = sB + (size_t)Kpad * KS * 4;                 // 2 x 128 x KS floats
+  TcSmem* S = reinterpret_cast<TcSmem*>(sA + (size_t)2 * kTcTile * KS * 4);
+  const int n_chunks = Kpad / kTcChunk;
+  const int64_t n_tiles = (p.n + kTcTile - 1) / kTcTile;
+
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S->a_full[b], kTcProdWarps * 32);
+      mbar_init(&S->a_empty[b], 1);
+      mbar_init(&S->t_full[b], 1);
+      mbar_init(&S->t_empty[b], kTcEpiWarps);
+      mbar_init(&S->r_full[b], kTcEpiWarps * 32);
+      mbar_init(&S->r_empty[b], kTcProdWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kTcMmaWarp) tc::tmem_alloc(&S->tmem_slot, 512);
+
+  // ---- stage the centre operand: row k = [c'_hi c'_hi c'_lo]_d | n2 pieces (3) | 1 1 | 0...
+  float cmax2 = 0.f;
+  for (int k = tid; k < Kpad; k += kTcThreads) {
+    auto put = [&](int slot, float v) {
+      *reinterpret_cast<float*>(sB + tc::off_kmajor(k, slot, lbo, sbo)) = v;
+    };
+    for (int s = 0; s < KS; ++s) put(s, 0.f);
+    if (k < K) {
+      double n2 = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const float c32 = (float)p.centers[(size_t)k * D + d];
+        n2 = fma((double)c32, (double)c32, n2);
+        const float cm = -2.0f * c32;
+        const float hi = tf32_rna(cm);
+        const float lo = tf32_rna(cm - hi);
+        put(3 * d + 0, hi);
+        put(3 * d + 1, hi);
+        put(3 * d + 2, lo);
+      }
+      const float p1 = tf32_rna((float)n2);
+      const float p2 = tf32_rna((float)(n2 - (double)p1));
+      const float p3 = tf32_rna((float)(n2 - (double)p1 - (double)p2));
+      put(3 * D + 0, p1);
+      put(3 * D + 1, p2);
+      put(3 * D + 2, p3);
+      put(3 * D + 3, 1.0f);
+      put(3 * D + 4, 1.0f);
+      cmax2 = fmaxf(cmax2, (float)n2 * 1.0001f);
+    } else {
+      put(3 * D + 0, 8.507059e37f);   // 2^126: a dummy centre never wins
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cmax2 = fmaxf(cmax2, __shfl_xor_sync(0xffffffffu, cmax2, o));
+  if (lane == 0) S->red[warp] = cmax2;
+  fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (tid == 0) {
+    float m = 0.f;
+    for (int w = 0; w < kTcThreads / 32; ++w) m = fmaxf(m, S->red[w]);
+    S->cmax = sqrtf(m) * 1.0001f;
+  }
+  __syncthreads();
+  const uint32_t tmem = S->tmem_slot;
+  const float cmax = S->cmax;
+
+  if (warp < kTcEpiWarps) {
+    // =========================================================== epilogue warps
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int row = quarter * 32 + lane;
+    uint32_t j = 0;   // chunk counter across tiles
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      int best = 0x7fffffff, second = 0x7fffffff, bchunk = 0;
+      for (int c = 0; c < n_chunks; ++c, ++j) {
+        const uint32_t tb = j & 1u;
+        mbar_wait(&S->t_full[tb], (j >> 1) & 1u);
+        tc::fence_after_sync();
+        const int before = best;
+#pragma unroll
+        for (int h = 0; h < kTcColsPerWarp / 32; ++h) {
+          const int col0 = grp * kTcColsPerWarp + h * 32;
+          float v[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTcChunk + (uint32_t)col0, v);
+          if (p.dbg_scores != nullptr) {
+            const int64_t grow = tile * kTcTile + row;
+            if (grow < p.n)
+              for (int q = 0; q < 32; ++q) p.dbg_scores[grow * Kpad + c * kTcChunk + col0 + q] = v[q];
+          }
+          // packed keys: score bits with the position inside this 32-column block in the low 5 bits;
+          // h (which block of the warp's 64 columns) goes to bit 5 via the block id below
+          const int blk_before = best;
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            const int k0 = (int)((__float_as_uint(v[q]) & 0xFFFFFFE0u) | (uint32_t)q);
+            const int k1 = (int)((__float_as_uint(v[q + 1]) & 0xFFFFFFE0u) | (uint32_t)(q + 1));
+            const int lo = min(k0, k1), hi = max(k0, k1);
+            const int t = max(best, lo);
+            second = min(min(second, hi), t);
+            best = min(best, lo);
+          }
+          if (best != blk_before) bchunk = (c << 1) | h;   // low 5 key bits refer to this block
+        }
+        (void)before;
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&S->t_empty[tb]);
+      }
+      const uint32_t rb = it & 1u;
+      mbar_wait(&S->r_empty[rb], ((it >> 1) & 1u) ^ 1u);
+      S->res_best[rb][grp][row] = best;
+      S->res_second[rb][grp][row] = second;
+      S->res_chunk[rb][grp][row] = bchunk;
+      tc::mbar_arrive(&S->r_full[rb]);
+    }
+  } else if (warp == kTcMmaWarp) {
+    // =========================================================== MMA issuer (lane 0 issues, the warp stays converged)
+    const uint32_t idesc = tc::idesc_tf32(kTcTile, kTcChunk, 0, 0);
+    const uint32_t aB = smem_u32(sB), aA = smem_u32(sA);
+    uint32_t j = 0, it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ab = it & 1u;
+      mbar_wait(&S->a_full[ab], (it >> 1) & 1u);
+      tc::fence_after_sync();
+      const uint32_t a_base = aA + ab * (uint32_t)(kTcTile * KS * 4);
+      for (int c = 0; c < n_chunks; ++c, ++j) {
+        const uint32_t tb = j & 1u;
+        mbar_wait(&S->t_empty[tb], ((j >> 1) & 1u) ^ 1u);
+        tc::fence_after_sync();
+        if (lane == 0) {
+          const uint32_t b_base = aB + (uint32_t)c * (kTcChunk / 8) * sbo;
+          for (int s = 0; s < KS / 8; ++s) {
+            const uint64_t da = tc::smem_desc(a_base + (uint32_t)s * 2u * lbo, lbo, sbo, tc::kLayoutNone);
+            const uint64_t db = tc::smem_desc(b_base + (uint32_t)s * 2u * lbo, lbo, sbo, tc::kLayoutNone);
+            tc::mma_tf32(tmem + tb * kTcChunk, da, db, idesc, s > 0 ? 1u : 0u);
+          }
+          tc::mma_commit(&S->t_full[tb]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) tc::mma_commit(&S->a_empty[ab]);
+      __syncwarp();
+    }
+  } else {
+    // =========================================================== producers / finalisers
+    const int pt = tid - (kTcMmaWarp + 1) * 32;   // 0..127: row of the tile
+    double inertia_acc = 0.0;
+    int recheck_acc = 0;
+    const float eps_trunc = kTcKeyTrunc;
+
+    auto finalize = [&](uint32_t itf, int64_t tilef) {
+      const uint32_t rb = itf & 1u;
+      mbar_wait(&S->r_full[rb], (itf >> 1) & 1u);
+      int b = 0x7fffffff, s2 = 0x7fffffff, bc = 0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int gb = S->res_best[rb][g][pt], gs = S->res_second[rb][g][pt], gc = S->res_chunk[rb][g][pt];
+        // merge (b, s2) with (gb, gs): new second = min(s2, gs, max(b, gb))
+        const int t = max(b, gb);
+        s2 = min(min(s2, gs), t);
+        if (gb < b) { b = gb; bc = (gc << 2) | g; }
+      }
+      tc::mbar_arrive(&S->r_empty[rb]);
+      const int64_t row = tilef * kTcTile + pt;
+      const bool valid = row < p.n;
+      int lab = -1;
+      if (valid) {
+        // column = chunk * 256 + group * 64 + h * 32 + (key & 31);  bc = ((chunk << 1 | h) << 2) | group
+        const int g = bc & 3, h = (bc >> 2) & 1, ch = bc >> 3;
+        int k = ch * kTcChunk + g * kTcColsPerWarp + h * 32 + (b & 31);
+        if (k >= K) k = K - 1;   // cannot happen for finite data (dummy centres score 2^126)
+        const float s1f = __uint_as_float((uint32_t)b & 0xFFFFFFE0u);
+        const float s2f = __uint_as_float((uint32_t)s2 & 0xFFFFFFE0u);
+        float xn2 = 0.f;
+        for (int d = 0; d < D; ++d) {
+          const float y = p.Y[row * p.ld + d];
+          xn2 = fmaf(y, y, xn2);
+        }
+        const float rr = sqrtf(xn2) * 1.0001f + cmax;
+        const float E = kTcErrScale * rr * rr;
+        const bool certain = (b >= 0) && (K == 1 || (s1f * eps_trunc + E < s2f - E));
+        p.labels[row] = k;
+        if (certain) {
+          lab = k;
+          if (p.inertia != nullptr) {
+            double acc = 0.0;
+            const double* c = p.centers + (size_t)k * D;
+            for (int d = 0; d < D; ++d) {
+              const double t = __dsub_rn((double)p.Y[row * p.ld + d], c[d]);
+              acc = __dadd_rn(acc, __dmul_rn(t, t));
+            }
+            inertia_acc += acc;
+          }
+        } else {
+          ++recheck_acc;
+          const int pos = atomicAdd(p.recheck_count, 1);
+          p.recheck_list[pos] = (int)row;
+        }
+      }
+      // fused Lloyd accumulation, segmented by runs of equal labels inside the warp
+      if (p.sums != nullptr) {
+        const int prev = __shfl_up_sync(0xffffffffu, lab, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || lab != prev);
+        const int my_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        bool take[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+          const int oh = __shfl_down_sync(0xffffffffu, my_head, 1 << s);
+          take[s] = (lane + (1 << s) < 32) && (oh == my_head);
+        }
+        const bool is_head = (lane == my_head) && lab >= 0;
+        for (int d = 0; d < D; ++d) {
+          double v = (lab >= 0) ? (double)p.Y[row * p.ld + d] : 0.0;
+#pragma unroll
+          for (int s = 0; s < 5; ++s) {
+            const double o = __shfl_down_sync(0xffffffffu, v, 1 << s);
+            if (take[s]) v += o;
+          }
+          if (is_head) atomicAdd(p.sums + (size_t)lab * D + d, v);
+        }
+        if (is_head && p.counts != nullptr) {
+          const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+          const int next = above ? (__ffs(above) - 1) : 32;
+          atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + lab), (unsigned long long)(next - lane));
+        }
+      }
+    };
+
+    uint32_t it = 0;
+    int64_t prev_tile = -1;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ab = it & 1u;
+      mbar_wait(&S->a_empty[ab], ((it >> 1) & 1u) ^ 1u);
+      unsigned char* A = sA + (size_t)ab * kTcTile * KS * 4;
+      const int64_t row = tile * kTcTile + pt;
+      auto put = [&](int slot, float v) {
+        *reinterpret_cast<float*>(A + tc::off_kmajor(pt, slot, lbo, sbo)) = v;
+      };
+      float xn2 = 0.f;
+      for (int d = 0; d < D; ++d) {
+        const float y = (row < p.n) ? p.Y[row * p.ld + d] : 0.f;
+        xn2 = fmaf(y, y, xn2);
+        const float hi = tf32_rna(y);
+        const float lo = tf32_rna(y - hi);
+        put(3 * d + 0, hi);
+        put(3 * d + 1, lo);
+        put(3 * d + 2, hi);
+      }
+      const float one = (row < p.n) ? 1.0f : 0.0f;
+      put(3 * D + 0, one);
+      put(3 * D + 1, one);
+      put(3 * D + 2, one);
+      const float x1 = tf32_rna(xn2);
+      put(3 * D + 3, x1);
+      put(3 * D + 4, tf32_rna(xn2 - x1));
+      for (int s = 3 * D + 5; s < KS; ++s) put(s, 0.f);
+      fence_proxy_async_smem();
+      tc::mbar_arrive(&S->a_full[ab]);
+      if (prev_tile >= 0) finalize(it - 1, prev_tile);
+      prev_tile = tile;
+    }
+    if (prev_tile >= 0) finalize(it - 1, prev_tile);
+
+    if (p.inertia != nullptr || p.n_rechecked != nullptr) {
+      const double v = warp_sum(inertia_acc);
+      int r = recheck_acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+      if (lane == 0) {
+        if (p.inertia != nullptr && v != 0.0) atomicAdd(p.inertia, v);
+        if (p.n_rechecked != nullptr && r)
+          atomicAdd(reinterpret_cast<unsigned long long*>(p.n_rechecked), (unsigned long long)r);
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == kTcMmaWarp) tc::tmem_dealloc(tmem, 512);
+}
+
+// One warp per listed frame: fp64 direct-difference distances in the oracle's operation order,
+// first minimum wins; the frame then joins the Lloyd accumulation.
+__global__ void __launch_bounds__(256) kmeans_recheck_kernel(KmTcParams p) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int count = *p.recheck_count;
+  const int D = p.D, K = p.K;
+  double inertia_acc = 0.0;
+  for (int e = gw; e < count; e += nw) {
+    const int64_t row = p.recheck_list[e];
+    double bd = 1.7976931348623157e308;
+    int bk = 0x7fffffff;
+    for (int k = lane; k < K; k += 32) {
+      double acc = 0.0;
+      const double* c = p.centers + (size_t)k * D;
+      for (int d = 0; d < D; ++d) {
+        const double t = __dsub_rn((double)p.Y[row * p.ld + d], c[d]);
+        acc = __dadd_rn(acc, __dmul_rn(t, t));
+      }
+      if (acc < bd) { bd = acc; bk = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+    }
+    if (lane == 0) {
+      p.labels[row] = bk;
+      inertia_acc += bd;
+      if (p.counts != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + bk), 1ull);
+    }
+    if (p.sums != nullptr)
+      for (int d = lane; d < D; d += 32) atomicAdd(p.sums + (size_t)bk * D + d, (double)p.Y[row * p.ld + d]);
+  }
+  if (lane == 0 && p.inertia != nullptr && inertia_acc != 0.0) atomicAdd(p.inertia, inertia_acc);
+}
+
+static inline int tc_slots(int D) { return ((3 * D + 5) + 7) / 8 * 8; }
+static inline int tc_kpad(int K) { return (K + kTcChunk - 1) / kTcChunk * kTcChunk; }
+static inline size_t tc_smem_bytes(int D, int K) {
+  return (size_t)tc_kpad(K) * tc_slots(D) * 4 + (size_t)2 * kTcTile * tc_slots(D) * 4 + sizeof(TcSmem) + 16;
+}
+
+bool kmeans_tc_supported(int D, int K) {
+  return D >= 1 && K >= 1 && tc_smem_bytes(D, K) <= 227 * 1024 && tc_kpad(K) / kTcChunk <= (1 << 20);
+}
+
+size_t kmeans_tc_ws_bytes(int64_t n) { return (size_t)n * sizeof(int) + 64; }
+
+int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double* centers, int K, int32_t* labels,
+                     double* sums, int64_t* counts, double* inertia, int64_t* n_rechecked, void* ws,
+                     float* dbg_scores, cudaStream_t st) {
+  KmTcParams p;
+  p.Y = Y; p.n = n; p.D = D; p.ld = ld; p.centers = centers; p.K = K;
+  p.Kpad = tc_kpad(K); p.KS = tc_slots(D);
+  p.labels = labels; p.sums = sums; p.counts = counts; p.inertia = inertia; p.n_rechecked = n_rechecked;
+  p.recheck_count = static_cast<int*>(ws);
+  p.recheck_list = static_cast<int*>(ws) + 16;
+  p.dbg_scores = dbg_scores;
+  PMB_REQUIRE(n < (int64_t)0x7fffffff, "pmb_kmeans_assign: tensor path needs n < 2^31");
+  const size_t smem = tc_smem_bytes(D, K);
+  PMB_CUDA(cudaMemsetAsync(p.recheck_count, 0, 64, st));
+  PMB_CUDA(cudaFuncSetAttribute(kmeans_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_tiles = (n + kTcTile - 1) / kTcTile;
+  const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  kmeans_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
+  PMB_LAUNCH_CHECK();
+  kmeans_recheck_kernel<<<2 * kNumSMs, 256, 0, st>>>(p);
+  PMB_LAUNCH_CHECK();
+  return PMB_OK;
+}
+
+}  // namespace pmb

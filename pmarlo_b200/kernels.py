@@ -15,7 +15,7 @@ from ._lib import check, ptr, stream_handle
 
 __all__ = [
     "require_cuda", "featurize", "pair_mask", "col_moments", "scaler_from_moments", "gram",
-    "tica_covariances", "tica_solve", "tica_finalize", "sym_eigvals_batched", "project", "kmeans_assign",
+    "tica_covariances", "tica_solve", "tica_finalize", "sym_eigvals_batched", "project", "kmeans_assign", "kmeans_tc_scores",
     "kmeans_update", "count_lagged", "count_lagged_weighted", "counts_active", "trig_expand", "mle_rev", "eig_rev_topk",
 ]
 
@@ -196,8 +196,10 @@ def project(X: torch.Tensor, a: torch.Tensor, nanfill: torch.Tensor, W: torch.Te
 
 def kmeans_assign(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor | None = None,
                   sums: torch.Tensor | None = None, counts: torch.Tensor | None = None,
-                  inertia: torch.Tensor | None = None, n_rechecked: torch.Tensor | None = None):
-    """K6.  labels int32 (n,), optional accumulation into sums/counts/inertia."""
+                  inertia: torch.Tensor | None = None, n_rechecked: torch.Tensor | None = None,
+                  impl: int = 0):
+    """K6.  labels int32 (n,), optional accumulation into sums/counts/inertia.
+    impl: 0 auto, 1 SIMT kernel, 2 tcgen05 score GEMM with fused argmin."""
     if Y.dtype not in (torch.float32, torch.float64) or not Y.is_cuda:
         raise TypeError("Y must be a float32/float64 CUDA tensor")
     _dev(centers, torch.float64, "centers")
@@ -209,11 +211,32 @@ def kmeans_assign(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor |
         raise ValueError("centers and Y disagree on the feature dimension")
     if labels is None:
         labels = torch.empty((n,), dtype=torch.int32, device=Y.device)
-    check(_lib.lib().pmb_kmeans_assign(ptr(Y), 1 if Y.dtype == torch.float64 else 0, n, D, ld,
-                                       ptr(centers), K, ptr(labels), ptr(sums), ptr(counts),
-                                       ptr(inertia), ptr(n_rechecked), stream_handle(Y.device)),
+    L = _lib.lib()
+    ws = _ws(L.pmb_kmeans_assign_ws_bytes(n, D, K), Y.device) if Y.dtype == torch.float32 else None
+    check(L.pmb_kmeans_assign(ptr(Y), 1 if Y.dtype == torch.float64 else 0, n, D, ld,
+                              ptr(centers), K, ptr(labels), ptr(sums), ptr(counts),
+                              ptr(inertia), ptr(n_rechecked), ptr(ws), ws.numel() if ws is not None else 0,
+                              int(impl), stream_handle(Y.device)),
           "pmb_kmeans_assign")
     return labels
+
+
+def kmeans_tc_scores(Y: torch.Tensor, centers: torch.Tensor):
+    """Test hook: (labels, scores (n, Kpad) float32) of the tcgen05 assignment path."""
+    _dev(Y, torch.float32, "Y")
+    _dev(centers, torch.float64, "centers")
+    ld = _rowmajor(Y, "Y")
+    n, D = int(Y.shape[0]), int(Y.shape[1])
+    centers = centers.contiguous()
+    K = int(centers.shape[0])
+    kpad = (K + 255) // 256 * 256
+    labels = torch.empty((n,), dtype=torch.int32, device=Y.device)
+    scores = torch.empty((n, kpad), dtype=torch.float32, device=Y.device)
+    L = _lib.lib()
+    ws = _ws(L.pmb_kmeans_assign_ws_bytes(n, D, K), Y.device)
+    check(L.pmb_kmeans_tc_scores(ptr(Y), n, D, ld, ptr(centers), K, ptr(labels), ptr(scores), ptr(ws),
+                                 ws.numel(), stream_handle(Y.device)), "pmb_kmeans_tc_scores")
+    return labels, scores
 
 
 def kmeans_update(centers: torch.Tensor, sums: torch.Tensor, counts: torch.Tensor,

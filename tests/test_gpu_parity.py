@@ -161,6 +161,77 @@ def test_kmeans_vs_oracle(D, K, n):
     parity.check_kmeans(Y, K, 3, seed=K)
 
 
+@pytest.mark.parametrize("D,K,n", [(10, 1000, 40000), (3, 17, 5000), (10, 500, 1000), (2, 200, 70000),
+                                   (16, 400, 20011), (1, 5, 300)])
+def test_kmeans_tensor_path_labels_and_accumulation(D, K, n):
+    """tcgen05 score GEMM + fused argmin (impl=2): labels bit-exact against the fp64 argmin, the fused
+    sums / counts / inertia equal to the oracle's, re-check fraction small."""
+    from pmarlo_b200 import kernels
+
+    feats = synth.ar1_features(1, n, D, seed=D * 11 + K)[0]
+    Y = torch.from_numpy(feats).to(dev())
+    Yh = feats.astype(np.float64)
+    rng = np.random.default_rng(K)
+    c0 = Yh[np.sort(rng.choice(n, size=K, replace=False))] + 1e-3 * rng.normal(size=(K, D))
+    cd = torch.from_numpy(c0).to(dev())
+    sums = torch.zeros((K, D), dtype=torch.float64, device=dev())
+    counts = torch.zeros((K,), dtype=torch.int64, device=dev())
+    inertia = torch.zeros((1,), dtype=torch.float64, device=dev())
+    nre = torch.zeros((1,), dtype=torch.int64, device=dev())
+    lab = kernels.kmeans_assign(Y, cd, sums=sums, counts=counts, inertia=inertia, n_rechecked=nre, impl=2)
+    lab_o, dmin_o = oracle.kmeans.assign(Yh, c0)
+    np.testing.assert_array_equal(lab.cpu().numpy().astype(np.int64), lab_o)
+    so = np.zeros((K, D))
+    np.add.at(so, lab_o, Yh)
+    np.testing.assert_array_equal(counts.cpu().numpy(), np.bincount(lab_o, minlength=K))
+    assert parity.rel_err(sums.cpu().numpy(), so) < 1e-12
+    assert abs(float(inertia.item()) - float(dmin_o.sum())) <= 1e-12 * float(dmin_o.sum())
+    frac = float(nre.item()) / n
+    print(f"tensor path D={D} K={K}: re-checked fraction {frac:.2e}")
+    assert frac < 0.05
+    # the SIMT path gives the same labels
+    np.testing.assert_array_equal(kernels.kmeans_assign(Y, cd, impl=1).cpu().numpy(), lab.cpu().numpy())
+
+
+def test_kmeans_tensor_path_ties_and_duplicates():
+    from pmarlo_b200 import kernels
+
+    rng = np.random.default_rng(0)
+    c = rng.normal(size=(300, 6))
+    c[5] = c[2]
+    c[299] = c[0]
+    Y = np.concatenate([c, 0.5 * (c[0] + c[1])[None], 0.5 * (c[10] + c[200])[None],
+                        rng.normal(size=(3000, 6))]).astype(np.float32)
+    cd = torch.from_numpy(c.astype(np.float32).astype(np.float64)).to(dev())
+    lab = kernels.kmeans_assign(torch.from_numpy(Y).to(dev()), cd, impl=2).cpu().numpy()
+    ref, _ = oracle.kmeans.assign(Y.astype(np.float64), c.astype(np.float32).astype(np.float64))
+    np.testing.assert_array_equal(lab, ref)
+    assert lab[5] == 2 and lab[299] == 0
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1e-3, 0.0), (50.0, 0.0), (1.0, 30.0)])
+def test_kmeans_tensor_score_error_envelope(scale, offset):
+    """The certainty test of kmeans_tc.cu assumes |score - exact d^2| <= 2^-19 (|y| + max|c|)^2.
+    Measure the scores as they leave TMEM against fp64 (tolerance written here: a quarter of the envelope)."""
+    from pmarlo_b200 import kernels
+
+    rng = np.random.default_rng(7)
+    n, D, K = 4096, 10, 1000
+    Y = (scale * rng.normal(size=(n, D)) + offset).astype(np.float32)
+    c = scale * rng.normal(size=(K, D)) + offset
+    lab, sc = kernels.kmeans_tc_scores(torch.from_numpy(Y).to(dev()), torch.from_numpy(c).to(dev()))
+    sc = sc.cpu().numpy().astype(np.float64)[:, :K]
+    exact = oracle.kmeans.sqdist_direct(Y.astype(np.float64), c)
+    yn = np.linalg.norm(Y.astype(np.float64), axis=1)[:, None]
+    cmax = np.linalg.norm(c, axis=1).max()
+    ratio = np.abs(sc - exact) / (2.0 ** -19 * (yn + cmax) ** 2)
+    print(f"score error / envelope: max {ratio.max():.3f}, mean {ratio.mean():.4f}; "
+          f"signed mean error / envelope {((sc - exact) / (2.0 ** -19 * (yn + cmax) ** 2)).mean():+.4f}")
+    assert ratio.max() <= 0.25
+    ref, _ = oracle.kmeans.assign(Y.astype(np.float64), c)
+    np.testing.assert_array_equal(lab.cpu().numpy(), ref)
+
+
 def test_assign_ties_duplicates_and_float64():
     """Duplicate centres and exact ties: the FIRST minimum wins, as np.argmin does."""
     from pmarlo_b200 import kernels
