@@ -222,12 +222,16 @@ int gram_tcgen05(const float* X, int64_t n, int d, int64_t ld, const uint8_t* ma
                  int mode, const float* shift, const float* scale, double* G, void* ws,
                  size_t ws_bytes, cudaStream_t stream);  // gram_tc.cu
 bool gram_tcgen05_supported(int d, int64_t ld, const float* X);
+size_t gram_tcgen05_ws_bytes(int d);
+constexpr int64_t kGramTcMinFrames = 65536;   // auto dispatch: below this the SIMT kernel is as fast
 
 }  // namespace pmb
 
 extern "C" size_t pmb_gram_ws_bytes(int d) {
   if (d <= 0) return 0;
-  return (size_t)pmb::gram_tiles(d) * pmb::gram_chunks(d) * pmb::kGT * pmb::kGT * sizeof(double);
+  const size_t simt = (size_t)pmb::gram_tiles(d) * pmb::gram_chunks(d) * pmb::kGT * pmb::kGT * sizeof(double);
+  const size_t tc = pmb::gram_tcgen05_ws_bytes(d);
+  return simt > tc ? simt : tc;
 }
 
 extern "C" int pmb_gram(const float* X, int64_t n, int d, int64_t ld, const uint8_t* mask, int lag,
@@ -241,9 +245,9 @@ extern "C" int pmb_gram(const float* X, int64_t n, int d, int64_t ld, const uint
     set_error("pmb_gram: workspace too small (%zu < %zu)", ws_bytes, pmb_gram_ws_bytes(d));
     return PMB_EWORKSPACE;
   }
-  if (impl == 2 || (impl == 0 && gram_tcgen05_supported(d, ld, X))) {
+  if (impl == 2 || (impl == 0 && n >= kGramTcMinFrames && gram_tcgen05_supported(d, ld, X))) {
     if (!gram_tcgen05_supported(d, ld, X)) {
-      set_error("pmb_gram: tcgen05 path needs d %% 64 == 0, d <= 256, 16B-aligned rows");
+      set_error("pmb_gram: tcgen05 path needs d %% 32 == 0, 32 <= d <= 256, 16B-aligned rows");
       return PMB_EUNSUPPORTED;
     }
     return gram_tcgen05(X, n, d, ld, mask, lag, mode, shift, scale, G, ws, ws_bytes, as_stream(stream));

@@ -1,10 +1,339 @@
-// gram_tc.cu -- K3 (tensor-core path): placeholder until the tcgen05 kernel lands.
-#include "common.cuh"
+// gram_tc.cu -- K3 (tensor-core path): the TICA Gram matrices as tcgen05 TF32 products with fp64-grade
+// accuracy, accumulators in TMEM.
+//
+//   mode 0: G = sum_g w_g z_g z_g^T,  w_g = popcount(mask_g & 3)      (X0^T X0 + Xt^T Xt)
+//   mode 1: G = sum_g (mask_g & 1) v_g v_g^T,  v_g = z_g - z_{g+lag}  (-> X0^T Xt + Xt^T X0)
+//   z = NaN ? 0 : (x - shift) * scale                                  (same conditioning as gram.cu)
+//
+// Split ("3xTF32 with an exactly accumulating leading term").  Tensor-core fp32 accumulation of the
+// monotone diagonal sums over millions of frames is the accuracy limit of a plain 3xTF32 scheme, so
+// each conditioned value is split into THREE TF32-representable parts
+//      z = a + r_hi + r_lo,   a = round(8 z) / 8 clamped to [-8, 8],  r = z - a (exact),
+//      r_hi = tf32(r),  r_lo = tf32(r - r_hi)
+// and
+//      w z z^T ~= (w a) a^T + [(w a) r^T + r (w a)^T] + (w r_hi) r_hi^T
+//   P  += (2 w a)^T a                         every product is a multiple of 2^-5: the fp32 sums in TMEM are
+//                                             EXACT while a window's partial sums stay below 2^19
+//   Q  += (2 w a)^T r_hi + (2 w a)^T r_lo + (w r_hi)^T r_hi      (|terms| <= 2^-4 |z|: their fp32
+//                                             accumulation error is ~1e-9 of G)
+//      G = P / 2 + (Q + Q^T) / 2
+// Dropped: r_hi r_lo^T + r_lo r_hi^T + r_lo r_lo^T, zero-mean, ~2^-21 |z|^2 per frame.
+// Every kWindow frames the two 128 x d accumulators are drained into a per-CTA fp64 workspace.
+//
+// One CTA per (128-row block of G, frame chunk); 148 CTAs = 2 row blocks x 74 chunks for d = 256.
+//   warps 0-7  producers: coalesced float4 loads (next stage prefetched in registers), conditioning,
+//              split, 16-byte stores into the MN-major 128B-swizzled operand tiles; drain TMEM at the
+//              end of a window
+//   warp  8    MMA issuer: 8 tcgen05.mma (M = 128, N = d, K = 8) per 16-frame stage
+// 3-stage shared-memory ring, mbarrier full/empty hand-off, tcgen05.commit frees a stage.
+#include "tc05.cuh"
+
 namespace pmb {
-bool gram_tcgen05_supported(int, int64_t, const float*) { return false; }
-int gram_tcgen05(const float*, int64_t, int, int64_t, const uint8_t*, int, int, const float*,
-                 const float*, double*, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 Gram path not built");
-  return PMB_EUNSUPPORTED;
+
+constexpr int kGtBK = 16;            // frames per stage
+constexpr int kGtStages = 3;
+constexpr int kGtProdWarps = 8;
+constexpr int kGtThreads = (kGtProdWarps + 1) * 32;   // 288
+constexpr int kGtWindow = 4096;      // frames per TMEM accumulation window (multiple of kGtBK)
+constexpr uint32_t kGtTileB = 256 * kGtBK * 4;        // bytes of one N-side tile (256 features x 16 frames)
+constexpr uint32_t kGtTileA = 128 * kGtBK * 4;
+constexpr uint32_t kGtStageBytes = 3 * kGtTileB + 2 * kGtTileA;   // a, r_hi, r_lo | 2wa, w r_hi  = 64 KB
+
+struct GramTcParams {
+  const float* X;
+  int64_t n;
+  int d;
+  int64_t ld;
+  const uint8_t* mask;
+  int lag;
+  int mode;
+  const float* shift;
+  const float* scale;
+  double* ws;        // [n_rb * n_chunks][2][d][128]
+  int n_chunks;
+  int64_t chunk;     // frames per chunk, multiple of kGtBK
+};
+
+__device__ __forceinline__ float gt_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
+__device__ __forceinline__ float gt_cond(float x, float sh, float sc) { return (x == x) ? (x - sh) * sc : 0.0f; }
+
+struct GtBars {
+  uint64_t full[kGtStages], empty[kGtStages], wdone, drained;
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  GtBars* B = reinterpret_cast<GtBars*>(tiles + (size_t)kGtStages * kGtStageBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = p.d;
+  const int rb = blockIdx.x / p.n_chunks, ck = blockIdx.x - rb * p.n_chunks;
+  const int64_t g_begin = (int64_t)ck * p.chunk;
+  int64_t g_end = g_begin + p.chunk;
+  if (g_end > p.n) g_end = p.n;
+  const int n_stages = g_begin < g_end ? (int)((g_end - g_begin + kGtBK - 1) / kGtBK) : 0;
+  const int stages_per_window = kGtWindow / kGtBK;
+  const uint32_t lbo = kGtBK * 128u, sbo = 512u;
+
+  // zero every tile once (features >= d and the unused half of narrow row blocks stay zero)
+  for (uint32_t i = tid; i < kGtStages * kGtStageBytes / 16; i += kGtThreads)
+    reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    for (int s = 0; s < kGtStages; ++s) {
+      mbar_init(&B->full[s], kGtProdWarps * 32);
+      mbar_init(&B->empty[s], 1);
+    }
+    mbar_init(&B->wdone, 1);
+    mbar_init(&B->drained, kGtProdWarps);
+    fence_barrier_init();
+  }
+  if (warp == kGtProdWarps) tc::tmem_alloc(&B->tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = B->tmem_slot;
+  double* ws = p.ws + (size_t)blockIdx.x * 2 * d * 128;
+
+  if (warp < kGtProdWarps) {
+    // ============================================================ producers
+    const int fr = tid >> 4;          // frame within the stage
+    const int g4 = tid & 15;          // float4 group: handles float4 indices g4 + 16 j
+    const int nf4 = d >> 2;
+    float4 sh[4], sc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (g4 + 16 * j) * 4;
+      if (c < d) {
+        sh[j] = *reinterpret_cast<const float4*>(p.shift + c);
+        sc[j] = *reinterpret_cast<const float4*>(p.scale + c);
+      } else {
+        sh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sc[j] = sh[j];
+      }
+    }
+    float4 xa[4], xb[4];
+    int mk = 0;
+    auto prefetch = [&](int s) {
+      const int64_t g = g_begin + (int64_t)s * kGtBK + fr;
+      mk = 0;
+      if (g < g_end) mk = p.mask[g];
+      const int w = (p.mode == 0) ? __popc(mk & 3) : (mk & 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[j] = xa[j];
+        const int idx = g4 + 16 * j;
+        if (w && idx < nf4) {
+          xa[j] = ldg_stream_f4(reinterpret_cast<const float4*>(p.X + g * p.ld) + idx);
+          if (p.mode == 1) xb[j] = ldg_stream_f4(reinterpret_cast<const float4*>(p.X + (g + p.lag) * p.ld) + idx);
+        }
+      }
+      mk = w;
+    };
+    // element offset of (feature mn, frame k) inside an MN-major swizzled tile
+    auto toff = [&](int mn, int k) -> uint32_t {
+      return tc::off_mnmajor_sw128b32(mn, k, lbo, sbo);
+    };
+    auto drain = [&](bool first) {
+      // warp w: lane quarter w % 4, accumulator (w / 4): 0 = P (columns 0..d), 1 = Q (columns 256..256+d)
+      const int quarter = warp & 3, which = warp >> 2;
+      double* dst = ws + (size_t)which * d * 128 + quarter * 32 + lane;
+      for (int c0 = 0; c0 < d; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(which * 256 + c0), v);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          double* e = dst + (size_t)(c0 + q) * 128;
+          *e = first ? (double)v[q] : (*e + (double)v[q]);
+        }
+      }
+    };
+
+    if (n_stages > 0) prefetch(0);
+    int n_windows_done = 0;
+    for (int s = 0; s < n_stages; ++s) {
+      const int slot = s % kGtStages;
+      const uint32_t use = (uint32_t)(s / kGtStages);
+      // current stage data -> registers, then prefetch the next stage
+      float4 ca[4], cb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ca[j] = xa[j]; cb[j] = xb[j]; }
+      const int w = mk;
+      if (s + 1 < n_stages) prefetch(s + 1);
+      mbar_wait(&B->empty[slot], (use & 1u) ^ 1u);
+      unsigned char* T = tiles + (size_t)slot * kGtStageBytes;
+      unsigned char* Ta = T, *Th = T + kGtTileB, *Tl = T + 2 * kGtTileB;
+      unsigned char* T2a = T + 3 * kGtTileB, *Twh = T2a + kGtTileA;
+      const float wf = (float)w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = g4 + 16 * j;
+        if (idx >= nf4) continue;
+        float z[4];
+        z[0] = gt_cond(ca[j].x, sh[j].x, sc[j].x);
+        z[1] = gt_cond(ca[j].y, sh[j].y, sc[j].y);
+        z[2] = gt_cond(ca[j].z, sh[j].z, sc[j].z);
+        z[3] = gt_cond(ca[j].w, sh[j].w, sc[j].w);
+        if (p.mode == 1) {
+          z[0] -= gt_cond(cb[j].x, sh[j].x, sc[j].x);
+          z[1] -= gt_cond(cb[j].y, sh[j].y, sc[j].y);
+          z[2] -= gt_cond(cb[j].z, sh[j].z, sc[j].z);
+          z[3] -= gt_cond(cb[j].w, sh[j].w, sc[j].w);
+        }
+        float a[4], rh[4], rl[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float zz = w ? z[q] : 0.f;
+          a[q] = fminf(fmaxf(rintf(zz * 8.0f), -64.0f), 64.0f) * 0.125f;
+          const float r = zz - a[q];
+          rh[q] = gt_tf32(r);
+          rl[q] = gt_tf32(r - rh[q]);
+        }
+        const int mn = idx * 4;
+        const uint32_t o = toff(mn, fr);
+        *reinterpret_cast<float4*>(Ta + o) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(Th + o) = make_float4(rh[0], rh[1], rh[2], rh[3]);
+        *reinterpret_cast<float4*>(Tl + o) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+        const int mloc = mn - rb * 128;
+        if (mloc >= 0 && mloc < 128) {
+          const uint32_t oa = toff(mloc, fr);
+          const float w2 = 2.0f * wf;
+          *reinterpret_cast<float4*>(T2a + oa) = make_float4(w2 * a[0], w2 * a[1], w2 * a[2], w2 * a[3]);
+          *reinterpret_cast<float4*>(Twh + oa) = make_float4(wf * rh[0], wf * rh[1], wf * rh[2], wf * rh[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc::mbar_arrive(&B->full[slot]);
+
+      const bool window_end = ((s + 1) % stages_per_window == 0) || (s + 1 == n_stages);
+      if (window_end) {
+        mbar_wait(&B->wdone, (uint32_t)(n_windows_done & 1));
+        tc::fence_after_sync();
+        drain(n_windows_done == 0);
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&B->drained);
+        ++n_windows_done;
+      }
+    }
+    if (n_stages == 0) {
+      // empty chunk: the reduce kernel still reads this CTA's slice
+      for (int i = tid; i < 2 * d * 128; i += kGtProdWarps * 32) ws[i] = 0.0;
+    }
+  } else {
+    // ============================================================ MMA issuer
+    const uint32_t idesc = tc::idesc_tf32(128, d, 1, 1);
+    const uint32_t base = smem_u32(tiles);
+    int n_windows_done = 0;
+    for (int s = 0; s < n_stages; ++s) {
+      const int slot = s % kGtStages;
+      const uint32_t use = (uint32_t)(s / kGtStages);
+      const bool window_start = (s % stages_per_window) == 0;
+      if (window_start && n_windows_done > 0) {
+        mbar_wait(&B->drained, (uint32_t)((n_windows_done - 1) & 1));
+        tc::fence_after_sync();
+      }
+      mbar_wait(&B->full[slot], use & 1u);
+      tc::fence_after_sync();
+      if (lane == 0) {
+        const uint32_t T = base + (uint32_t)slot * kGtStageBytes;
+        const uint32_t Ta = T, Th = T + kGtTileB, Tl = T + 2 * kGtTileB, T2a = T + 3 * kGtTileB, Twh = T2a + kGtTileA;
+#pragma unroll
+        for (int ks = 0; ks < kGtBK / 8; ++ks) {
+          const uint32_t off = (uint32_t)ks * 2u * sbo;
+          const uint64_t dA2a = tc::smem_desc(T2a + off, lbo, sbo, tc::kLayoutSw128Base32);
+          const uint64_t dAwh = tc::smem_desc(Twh + off, lbo, sbo, tc::kLayoutSw128Base32);
+          const uint64_t dBa = tc::smem_desc(Ta + off, lbo, sbo, tc::kLayoutSw128Base32);
+          const uint64_t dBh = tc::smem_desc(Th + off, lbo, sbo, tc::kLayoutSw128Base32);
+          const uint64_t dBl = tc::smem_desc(Tl + off, lbo, sbo, tc::kLayoutSw128Base32);
+          const uint32_t acc = (window_start && ks == 0) ? 0u : 1u;
+          tc::mma_tf32(tmem, dA2a, dBa, idesc, acc);
+          tc::mma_tf32(tmem + 256u, dA2a, dBh, idesc, acc);
+          tc::mma_tf32(tmem + 256u, dA2a, dBl, idesc, 1u);
+          tc::mma_tf32(tmem + 256u, dAwh, dBh, idesc, 1u);
+        }
+        tc::mma_commit(&B->empty[slot]);
+        const bool window_end = ((s + 1) % stages_per_window == 0) || (s + 1 == n_stages);
+        if (window_end) tc::mma_commit(&B->wdone);
+      }
+      __syncwarp();
+      if (((s + 1) % stages_per_window == 0) || (s + 1 == n_stages)) ++n_windows_done;
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == kGtProdWarps) tc::tmem_dealloc(tmem, 512);
+}
+
+// Pf[i][j], Qf[i][j] = sum over frame chunks (fixed order) of the per-CTA fp64 partials
+__global__ void gram_tc_reduce_kernel(const double* __restrict__ ws, int n_chunks, int d, double* __restrict__ PQ) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // i fastest
+  if (e >= d * d) return;
+  const int i = e % d, j = e / d;
+  const int rb = i >> 7, il = i & 127;
+  double accP = 0.0, accQ = 0.0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const double* w = ws + (size_t)(rb * n_chunks + c) * 2 * d * 128;
+    accP += w[(size_t)j * 128 + il];
+    accQ += w[(size_t)d * 128 + (size_t)j * 128 + il];
+  }
+  PQ[(size_t)i * d + j] = accP;
+  PQ[(size_t)d * d + (size_t)i * d + j] = accQ;
+}
+__global__ void gram_tc_combine_kernel(const double* __restrict__ PQ, int d, double* __restrict__ G) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d * d) return;
+  const int i = e / d, j = e - i * d;
+  const double* P = PQ;
+  const double* Q = PQ + (size_t)d * d;
+  // P is symmetric by construction (exact integer-valued sums); use the (min, max) entry so that G is
+  // bit-symmetric as well
+  const int a = i < j ? i : j, b = i < j ? j : i;
+  G[e] = 0.5 * P[(size_t)a * d + b] + 0.5 * (Q[(size_t)a * d + b] + Q[(size_t)b * d + a]);
+}
+
+static inline int gt_row_blocks(int d) { return (d + 127) / 128; }
+static inline int gt_chunks(int d) { return kNumSMs / gt_row_blocks(d); }
+
+bool gram_tcgen05_supported(int d, int64_t ld, const float* X) {
+  return d >= 32 && d <= 256 && d % 32 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+}
+size_t gram_tcgen05_ws_bytes(int d) {
+  if (d < 32 || d > 256 || d % 32 != 0) return 0;
+  return ((size_t)gt_row_blocks(d) * gt_chunks(d) * 2 * d * 128 + (size_t)2 * d * d) * sizeof(double);
+}
+
+int gram_tcgen05(const float* X, int64_t n, int d, int64_t ld, const uint8_t* mask, int lag, int mode,
+                 const float* shift, const float* scale, double* G, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PMB_REQUIRE(ws_bytes >= gram_tcgen05_ws_bytes(d), "pmb_gram: workspace too small for the tcgen05 path");
+  PMB_REQUIRE((reinterpret_cast<uintptr_t>(shift) & 15) == 0 && (reinterpret_cast<uintptr_t>(scale) & 15) == 0,
+              "pmb_gram: shift/scale must be 16-byte aligned for the tcgen05 path");
+  GramTcParams p;
+  p.X = X; p.n = n; p.d = d; p.ld = ld; p.mask = mask; p.lag = lag; p.mode = mode; p.shift = shift; p.scale = scale;
+  p.ws = static_cast<double*>(ws);
+  const int nrb = gt_row_blocks(d);
+  int nc = gt_chunks(d);
+  int64_t chunk = (n + nc - 1) / nc;
+  chunk = ((chunk + kGtBK - 1) / kGtBK) * kGtBK;
+  p.n_chunks = nc;
+  p.chunk = chunk;
+  const size_t smem = (size_t)kGtStages * kGtStageBytes + sizeof(GtBars) + 1024;
+  PMB_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_tc_kernel<<<nrb * nc, kGtThreads, smem, st>>>(p);
+  PMB_LAUNCH_CHECK();
+  double* PQ = p.ws + (size_t)nrb * nc * 2 * d * 128;
+  gram_tc_reduce_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(p.ws, nc, d, PQ);
+  PMB_LAUNCH_CHECK();
+  gram_tc_combine_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(PQ, d, G);
+  PMB_LAUNCH_CHECK();
+  return PMB_OK;
+}
+
 }  // namespace pmb

@@ -106,6 +106,44 @@ def test_tica_vs_oracle(d, lag, dim, pre):
     parity.check_tica(feats, lag, dim, pre)
 
 
+@pytest.mark.parametrize("d,n_frames,lag", [(256, 9000, 20), (64, 5000, 3), (96, 4100, 7), (160, 6000, 11)])
+def test_gram_tensor_path_matches_fp64(d, n_frames, lag):
+    """tcgen05 Gram (impl=2: exact leading term + TF32 remainders, fp64 window drain) against an fp64
+    evaluation of the same conditioned fp32 data, and against the SIMT kernel.  Tolerance 1e-7 of the
+    matrix scale (north star: covariances within 1e-6)."""
+    from pmarlo_b200 import kernels
+    from pmarlo_b200.shards import Segments
+
+    feats = synth.ar1_features(3, n_frames, d, seed=d + 1, offset=2.0)
+    feats[1] = feats[1][: n_frames - 777]
+    feats.append(feats[0][: lag])                      # contributes no pair
+    feats[0][5, 3] = np.nan
+    X = np.concatenate(feats).astype(np.float32)
+    segs = Segments.from_lengths([f.shape[0] for f in feats])
+    Xd = torch.from_numpy(X).to(dev())
+    mask = kernels.pair_mask(segs.device(dev()), X.shape[0], lag)
+    shift = np.nanmean(X, axis=0).astype(np.float32)
+    scale = (1.0 / np.nanstd(X, axis=0)).astype(np.float32)
+    cond = torch.from_numpy(np.stack([shift, scale])).to(dev())
+    m = mask.cpu().numpy()
+    z = np.where(np.isnan(X), np.float32(0), (X - shift[None]) * scale[None]).astype(np.float32)
+    w0 = ((m & 1) + ((m >> 1) & 1)).astype(np.float64)
+    G0 = (z.astype(np.float64) * w0[:, None]).T @ z.astype(np.float64)
+    idx = np.flatnonzero(m & 1)
+    v = (z[idx] - z[idx + lag]).astype(np.float32).astype(np.float64)
+    G1 = v.T @ v
+    for mode, ref in ((0, G0), (1, G1)):
+        tc = kernels.gram(Xd, mask, lag, mode, cond, impl=2).cpu().numpy()
+        simt = kernels.gram(Xd, mask, lag, mode, cond, impl=1).cpu().numpy()
+        scale_ref = np.max(np.abs(ref))
+        e_tc = np.max(np.abs(tc - ref)) / scale_ref
+        e_simt = np.max(np.abs(simt - ref)) / scale_ref
+        e_diag = np.max(np.abs(np.diag(tc) - np.diag(ref)) / np.abs(np.diag(ref)))
+        print(f"gram d={d} mode={mode}: tcgen05 err {e_tc:.2e} (diag rel {e_diag:.2e}), SIMT err {e_simt:.2e}")
+        assert e_tc <= 1e-7 and e_diag <= 1e-7
+        np.testing.assert_array_equal(tc, tc.T)
+
+
 def test_tica_nan_imputation_and_constant_column(golden):
     from pmarlo_b200.reduction import preprocess, tica_reduce
 
