@@ -160,13 +160,16 @@ PMB_API int pmb_project(const float* X, int64_t n, int d, int64_t ld, const doub
  * pass NULL for sums/counts/inertia to only assign.  y_f64: Y element type.
  * impl: 0 = auto, 1 = SIMT register-tiled kernel (kmeans.cu), 2 = tcgen05 TF32 score GEMM with the
  * argmin fused into the TMEM epilogue (kmeans_tc.cu; float32 Y, needs the workspace).  Both paths
- * return the same labels: near ties are re-evaluated in fp64. */
+ * return the same labels: near ties are re-evaluated in fp64.
+ * hints (n, may be NULL, may alias labels): labels of a previous assignment, e.g. the last Lloyd
+ * iteration.  They never change the result; the tcgen05 epilogue uses the distance to the hinted centre
+ * to skip 32-centre blocks that cannot contain the winner. */
 PMB_API size_t pmb_kmeans_assign_ws_bytes(int64_t n, int D, int K);
 PMB_API int pmb_kmeans_assign(const void* Y, int y_f64, int64_t n, int D, int64_t ld,
                       const double* centers, int K, int32_t* labels,
                       double* sums, int64_t* counts, double* inertia,
-                      int64_t* n_rechecked, void* ws, size_t ws_bytes, int impl,
-                      pmb_stream_t stream);
+                      int64_t* n_rechecked, const int32_t* hints, void* ws, size_t ws_bytes,
+                      int impl, pmb_stream_t stream);
 /* Test hook of the tcgen05 path: also writes the (n x Kpad, Kpad = K rounded up to 256) fp32 score
  * matrix |y|^2 + |c_k|^2 - 2 y.c_k as it leaves TMEM, so that the error envelope the certainty test
  * relies on can be measured (tests/test_gpu_parity.py). */

@@ -40,7 +40,7 @@ PROTOTYPES = {
     "pmb_sym_eigvals_batched": (_i32, [_p, _i32, _i32, _p, _p, _sz, _p]),
     "pmb_project": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _i32, _p, _i64, _i32, _p]),
     "pmb_kmeans_assign_ws_bytes": (_sz, [_i64, _i32, _i32]),
-    "pmb_kmeans_assign": (_i32, [_p, _i32, _i64, _i32, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _sz, _i32, _p]),
+    "pmb_kmeans_assign": (_i32, [_p, _i32, _i64, _i32, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _i32, _p]),
     "pmb_kmeans_tc_scores": (_i32, [_p, _i64, _i32, _i64, _p, _i32, _p, _p, _p, _sz, _p]),
     "pmb_kmeans_update": (_i32, [_p, _p, _p, _i32, _i32, _p, _p]),
     "pmb_count_lagged": (_i32, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p]),

@@ -97,11 +97,13 @@ def lloyd_device(Y: torch.Tensor, initial_centers: torch.Tensor, max_iter: int =
         labels = torch.empty((int(Y.shape[0]),), dtype=torch.int32, device=Y.device)
     prev_cost, cost, it, converged = 0.0, None, 0, False
     pending = False  # an update whose cost has not been measured yet
+    hints = None   # the first iteration starts cold; later ones pass the previous labels as hints
     while True:
         acc.zero_()
         with timer.stage("kmeans_assign"):
             kernels.kmeans_assign(Y, centers, labels=labels, sums=acc.sums, counts=acc.counts,
-                                  inertia=acc.inertia)
+                                  inertia=acc.inertia, hints=hints)
+        hints = labels
         comm.allreduce_sum(acc.f, acc.counts)
         if pending and tolerance is not None:
             cost = float(acc.inertia.item())   # cost of the centres produced by iteration `it`

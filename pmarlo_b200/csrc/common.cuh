@@ -82,6 +82,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a lost transaction traps (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // rolled loop on purpose: an unrolled spin multiplies the code size of warp-specialised kernels,
+  // whose roles already compete for the instruction cache
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 26); ++spin)
     if (mbar_try_wait(bar, parity)) return;
   __trap();

@@ -281,9 +281,9 @@ __global__ void kmeans_update_kernel(double* __restrict__ centers, const double*
 
 // kmeans_tc.cu
 bool kmeans_tc_supported(int D, int K);
-size_t kmeans_tc_ws_bytes(int64_t n);
+size_t kmeans_tc_ws_bytes(int64_t n, int D, int K);
 int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double* centers, int K, int32_t* labels,
-                     double* sums, int64_t* counts, double* inertia, int64_t* n_rechecked, void* ws,
+                     const int32_t* hints, double* sums, int64_t* counts, double* inertia, int64_t* n_rechecked, void* ws,
                      float* dbg_scores, cudaStream_t st);
 
 constexpr int64_t kKmTcMinFrames = 16384;   // below this the launch is latency-bound either way
@@ -292,7 +292,7 @@ constexpr int64_t kKmTcMinFrames = 16384;   // below this the launch is latency-
 
 extern "C" size_t pmb_kmeans_assign_ws_bytes(int64_t n, int D, int K) {
   if (n <= 0 || !pmb::kmeans_tc_supported(D, K)) return 0;
-  return pmb::kmeans_tc_ws_bytes(n);
+  return pmb::kmeans_tc_ws_bytes(n, D, K);
 }
 
 extern "C" int pmb_kmeans_tc_scores(const float* Y, int64_t n, int D, int64_t ld, const double* centers, int K,
@@ -302,15 +302,16 @@ extern "C" int pmb_kmeans_tc_scores(const float* Y, int64_t n, int D, int64_t ld
   PMB_REQUIRE(n > 0 && D > 0 && K > 0 && ld >= D, "pmb_kmeans_tc_scores: bad sizes");
   PMB_REQUIRE(Y && centers && labels && scores && ws, "pmb_kmeans_tc_scores: null pointer");
   PMB_REQUIRE(kmeans_tc_supported(D, K), "pmb_kmeans_tc_scores: D=%d K=%d does not fit the tensor path", D, K);
-  PMB_REQUIRE(ws_bytes >= kmeans_tc_ws_bytes(n), "pmb_kmeans_tc_scores: workspace too small");
-  return kmeans_tc_assign(Y, n, D, ld, centers, K, labels, nullptr, nullptr, nullptr, nullptr, ws, scores,
+  PMB_REQUIRE(ws_bytes >= kmeans_tc_ws_bytes(n, D, K), "pmb_kmeans_tc_scores: workspace too small");
+  return kmeans_tc_assign(Y, n, D, ld, centers, K, labels, nullptr, nullptr, nullptr, nullptr, nullptr, ws, scores,
                           as_stream(stream));
 }
 
 extern "C" int pmb_kmeans_assign(const void* Y, int y_f64, int64_t n, int D, int64_t ld,
                                  const double* centers, int K, int32_t* labels, double* sums,
-                                 int64_t* counts, double* inertia, int64_t* n_rechecked, void* ws,
-                                 size_t ws_bytes, int impl, pmb_stream_t stream) {
+                                 int64_t* counts, double* inertia, int64_t* n_rechecked,
+                                 const int32_t* hints, void* ws, size_t ws_bytes, int impl,
+                                 pmb_stream_t stream) {
   using namespace pmb;
   PMB_REQUIRE(n >= 0 && D > 0 && K > 0 && ld >= D, "pmb_kmeans_assign: bad sizes");
   PMB_REQUIRE(impl >= 0 && impl <= 2, "pmb_kmeans_assign: impl must be 0 (auto), 1 (SIMT) or 2 (tcgen05)");
@@ -318,14 +319,14 @@ extern "C" int pmb_kmeans_assign(const void* Y, int y_f64, int64_t n, int D, int
   PMB_REQUIRE(Y && centers && labels, "pmb_kmeans_assign: null pointer");
   PMB_REQUIRE((sums == nullptr) == (counts == nullptr), "pmb_kmeans_assign: sums and counts go together");
   {
-    const bool tc_ok = !y_f64 && kmeans_tc_supported(D, K) && ws != nullptr && ws_bytes >= kmeans_tc_ws_bytes(n);
+    const bool tc_ok = !y_f64 && kmeans_tc_supported(D, K) && ws != nullptr && ws_bytes >= kmeans_tc_ws_bytes(n, D, K);
     if (impl == 2 && !tc_ok) {
       set_error("pmb_kmeans_assign: tcgen05 path needs float32 Y, a workspace of pmb_kmeans_assign_ws_bytes "
                 "and centres that fit shared memory (D=%d, K=%d)", D, K);
       return PMB_EUNSUPPORTED;
     }
     if (impl == 2 || (impl == 0 && tc_ok && n >= kKmTcMinFrames && (int64_t)D * K >= 2048))
-      return kmeans_tc_assign(static_cast<const float*>(Y), n, D, ld, centers, K, labels, sums, counts, inertia,
+      return kmeans_tc_assign(static_cast<const float*>(Y), n, D, ld, centers, K, labels, hints, sums, counts, inertia,
                               n_rechecked, ws, nullptr, as_stream(stream));
   }
   if (y_f64) {

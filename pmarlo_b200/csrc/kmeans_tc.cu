@@ -9,10 +9,10 @@
 // and the norms ride in spare slots (|c|^2 as three TF32 pieces against 1.0, |y|^2 as two pieces),
 // so the accumulator that leaves TMEM already is the squared distance.  KS = 3 D + 5 rounded up to 8.
 //
-// Pipeline (one persistent CTA per SM, 21 warps, warp-specialised, mbarrier hand-offs):
-//   warps 17-20  producers : build the A tile (128 frames x KS slots, K-major core-matrix layout)
-//                            of tile i, then FINALISE tile i-1 (merge, certainty test, labels,
-//                            fused Lloyd accumulation)
+// Pipeline (one persistent CTA per SM, 25 warps, warp-specialised, mbarrier hand-offs):
+//   warps 17-20  producers : build the A tile (128 frames x KS slots, K-major core-matrix layout) and
+//                            the per-row screening threshold from the hinted centre (rows prefetched)
+//   warps 21-24  finalisers: merge the column groups, certainty test, labels, fused Lloyd accumulation
 //   warp  16     MMA issuer: per 256-centre chunk KS/8 tcgen05.mma into one of two TMEM buffers
 //   warps 0-15   epilogue  : tcgen05.ld 64 columns per warp and chunk, running (best, second) as
 //                            packed integer keys (score bits with the column in the low 5 bits)
@@ -30,8 +30,10 @@ constexpr int kTcTile = 128;     // frames per tile  (MMA M)
 constexpr int kTcChunk = 256;    // centres per MMA  (MMA N)
 constexpr int kTcEpiWarps = 16;
 constexpr int kTcProdWarps = 4;
+constexpr int kTcFinWarps = 4;
 constexpr int kTcMmaWarp = kTcEpiWarps;
-constexpr int kTcThreads = (kTcEpiWarps + 1 + kTcProdWarps) * 32;   // 672
+constexpr int kTcThreads = (kTcEpiWarps + 1 + kTcProdWarps + kTcFinWarps) * 32;   // 800
+constexpr int kTcDReg = 16;      // coordinates of a frame held in registers (larger D: re-read from L1/L2)
 constexpr int kTcColsPerWarp = kTcChunk / (kTcEpiWarps / 4);        // 64
 constexpr float kTcErrScale = 1.9073486e-6f;   // 2^-19: envelope of the score error in units of (|y| + |c|max)^2
 constexpr float kTcKeyTrunc = 1.0f + 7.6293945e-6f;  // 1 + 2^-17 (5 key bits of a 23-bit mantissa dropped)
@@ -46,12 +48,17 @@ struct KmTcParams {
   int Kpad;   // K rounded up to a multiple of 256 (dummy centres score 2^126)
   int KS;     // K slots per row, multiple of 8
   int32_t* labels;
+  const int32_t* hints;   // previous labels (may alias labels) or nullptr: only used to skip work
   double* sums;
   int64_t* counts;
   double* inertia;
   int64_t* n_rechecked;
   int* recheck_list;    // n entries
   int* recheck_count;   // zeroed by the host wrapper
+  double* ysq;          // sum over frames of |y|^2 (zeroed by the host wrapper)
+  double* lsums;        // K x D, this call's sums (zeroed by the host wrapper)
+  unsigned long long* lcounts;   // K
+  int accumulate;       // sums / counts / inertia requested
   float* dbg_scores;    // n x Kpad (tests only) or nullptr
 };
 
@@ -62,15 +69,19 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 struct TcSmem {
-  uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], r_full[2], r_empty[2];
+  uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], r_full[2], r_empty[2], thr_ready[4];
   uint32_t tmem_slot;
   float cmax;
   float red[32];
+  float thr[4][kTcTile];   // per-row screening threshold of tile it (slot it & 3)
   int res_best[2][4][kTcTile];
   int res_second[2][4][kTcTile];
   int res_chunk[2][4][kTcTile];
+  float res_thr[2][kTcTile];
 };
 
+// DBG: also write the raw scores (tests).  INREG: D <= kTcDReg, a frame's coordinates live in registers.
+template <bool DBG, bool INREG>
 __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -89,8 +100,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       mbar_init(&S->t_full[b], 1);
       mbar_init(&S->t_empty[b], kTcEpiWarps);
       mbar_init(&S->r_full[b], kTcEpiWarps * 32);
-      mbar_init(&S->r_empty[b], kTcProdWarps * 32);
+      mbar_init(&S->r_empty[b], kTcFinWarps * 32);
     }
+    for (int b = 0; b < 4; ++b) mbar_init(&S->thr_ready[b], 1);
     fence_barrier_init();
   }
   if (warp == kTcMmaWarp) tc::tmem_alloc(&S->tmem_slot, 512);
@@ -151,23 +163,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       int best = 0x7fffffff, second = 0x7fffffff, bchunk = 0;
+      // screening threshold of this row (written by the producers, handed over by the MMA warp)
+      mbar_wait(&S->thr_ready[it & 3u], (it >> 2) & 1u);
+      const float thr = S->thr[it & 3u][row];
       for (int c = 0; c < n_chunks; ++c, ++j) {
         const uint32_t tb = j & 1u;
         mbar_wait(&S->t_full[tb], (j >> 1) & 1u);
         tc::fence_after_sync();
-        const int before = best;
 #pragma unroll
         for (int h = 0; h < kTcColsPerWarp / 32; ++h) {
           const int col0 = grp * kTcColsPerWarp + h * 32;
           float v[32];
           tc::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTcChunk + (uint32_t)col0, v);
-          if (p.dbg_scores != nullptr) {
+          if constexpr (DBG) {
             const int64_t grow = tile * kTcTile + row;
             if (grow < p.n)
               for (int q = 0; q < 32; ++q) p.dbg_scores[grow * Kpad + c * kTcChunk + col0 + q] = v[q];
           }
-          // packed keys: score bits with the position inside this 32-column block in the low 5 bits;
-          // h (which block of the warp's 64 columns) goes to bit 5 via the block id below
+          // screen: a block whose minimum is above the row's threshold cannot hold the best centre nor
+          // one within the certainty margin of it (the finaliser caps `second` at the threshold)
+          float m8[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) m8[q] = fminf(fminf(v[4 * q], v[4 * q + 1]), fminf(v[4 * q + 2], v[4 * q + 3]));
+          const float bmin = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])),
+                                   fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
+          if (!__any_sync(0xffffffffu, bmin <= thr)) continue;
+          // packed keys: score bits with the position inside this 32-column block in the low 5 bits
           const int blk_before = best;
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
@@ -180,7 +201,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
           }
           if (best != blk_before) bchunk = (c << 1) | h;   // low 5 key bits refer to this block
         }
-        (void)before;
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S->t_empty[tb]);
@@ -190,6 +210,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       S->res_best[rb][grp][row] = best;
       S->res_second[rb][grp][row] = second;
       S->res_chunk[rb][grp][row] = bchunk;
+      if (grp == 0) S->res_thr[rb][row] = thr;
       tc::mbar_arrive(&S->r_full[rb]);
     }
   } else if (warp == kTcMmaWarp) {
@@ -201,6 +222,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       const uint32_t ab = it & 1u;
       mbar_wait(&S->a_full[ab], (it >> 1) & 1u);
       tc::fence_after_sync();
+      if (lane == 0) tc::mbar_arrive(&S->thr_ready[it & 3u]);   // producers' thr[] -> epilogue warps
       const uint32_t a_base = aA + ab * (uint32_t)(kTcTile * KS * 4);
       for (int c = 0; c < n_chunks; ++c, ++j) {
         const uint32_t tb = j & 1u;
@@ -220,27 +242,142 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       if (lane == 0) tc::mma_commit(&S->a_empty[ab]);
       __syncwarp();
     }
-  } else {
-    // =========================================================== producers / finalisers
+  } else if (warp < kTcMmaWarp + 1 + kTcProdWarps) {
+    // =========================================================== producers: A tile + screening threshold
     const int pt = tid - (kTcMmaWarp + 1) * 32;   // 0..127: row of the tile
-    double inertia_acc = 0.0;
+    constexpr bool in_regs = INREG;
+    float yn[kTcDReg];   // coordinates of this thread's row of the NEXT tile (prefetched)
+    int hint_n = -1;
+    auto prefetch = [&](int64_t tile) {
+      const int64_t row = tile * kTcTile + pt;
+      hint_n = -1;
+      if (row < p.n) {
+        if (p.hints != nullptr) hint_n = p.hints[row];
+        if constexpr (in_regs) {
+#pragma unroll
+          for (int d = 0; d < kTcDReg; ++d) yn[d] = (d < D) ? p.Y[row * p.ld + d] : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < kTcDReg; ++d) yn[d] = 0.f;
+      }
+    };
+    uint32_t it = 0;
+    double ysq_acc = 0.0;
+    if ((int64_t)blockIdx.x < n_tiles) prefetch(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ab = it & 1u;
+      const int64_t row = tile * kTcTile + pt;
+      const bool valid = row < p.n;
+      float y[kTcDReg];
+#pragma unroll
+      for (int d = 0; d < kTcDReg; ++d) y[d] = yn[d];
+      const int hint = hint_n;
+      // distance to the hinted centre: its loads are issued before the (possibly long) wait below
+      float u = __int_as_float(0x7f800000);
+      if (valid && hint >= 0 && hint < K) {
+        const double* c = p.centers + (size_t)hint * D;
+        u = 0.f;
+        if constexpr (in_regs) {
+          double cc[kTcDReg];
+#pragma unroll
+          for (int d = 0; d < kTcDReg; ++d) cc[d] = (d < D) ? c[d] : 0.0;
+#pragma unroll
+          for (int d = 0; d < kTcDReg; ++d) {
+            const float t = y[d] - (float)cc[d];
+            u = fmaf(t, t, u);
+          }
+        } else {
+#pragma unroll 4
+          for (int d = 0; d < D; ++d) {
+            const float t = p.Y[row * p.ld + d] - (float)c[d];
+            u = fmaf(t, t, u);
+          }
+        }
+      }
+      if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+      mbar_wait(&S->a_empty[ab], ((it >> 1) & 1u) ^ 1u);
+      unsigned char* A = sA + (size_t)ab * kTcTile * KS * 4;
+      auto put = [&](int slot, float v) {
+        *reinterpret_cast<float*>(A + tc::off_kmajor(pt, slot, lbo, sbo)) = v;
+      };
+      float xn2 = 0.f;
+      if constexpr (in_regs) {
+#pragma unroll
+        for (int d = 0; d < kTcDReg; ++d) {
+          if (d < D) {
+            const float v = y[d];
+            xn2 = fmaf(v, v, xn2);
+            ysq_acc = fma((double)v, (double)v, ysq_acc);
+            const float hi = tf32_rna(v);
+            put(3 * d + 0, hi);
+            put(3 * d + 1, tf32_rna(v - hi));
+            put(3 * d + 2, hi);
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int d = 0; d < D; ++d) {
+          const float v = valid ? p.Y[row * p.ld + d] : 0.f;
+          xn2 = fmaf(v, v, xn2);
+          ysq_acc = fma((double)v, (double)v, ysq_acc);
+          const float hi = tf32_rna(v);
+          put(3 * d + 0, hi);
+          put(3 * d + 1, tf32_rna(v - hi));
+          put(3 * d + 2, hi);
+        }
+      }
+      const float one = valid ? 1.0f : 0.0f;
+      put(3 * D + 0, one);
+      put(3 * D + 1, one);
+      put(3 * D + 2, one);
+      const float x1 = tf32_rna(xn2);
+      put(3 * D + 3, x1);
+      put(3 * D + 4, tf32_rna(xn2 - x1));
+      for (int s = 3 * D + 5; s < KS; ++s) put(s, 0.f);
+      // screening threshold: the fp32 distance to the hinted centre bounds the best score from above
+      // (up to the envelope E); the margin keeps the certainty test decidable
+      const float rr = sqrtf(xn2) * 1.0001f + cmax;
+      S->thr[it & 3u][pt] = u * (1.0f + 1.5258789e-5f) + 4.0f * kTcErrScale * rr * rr;
+      fence_proxy_async_smem();
+      tc::mbar_arrive(&S->a_full[ab]);
+    }
+    if (p.accumulate) {
+      ysq_acc = warp_sum(ysq_acc);
+      if (lane == 0 && ysq_acc != 0.0) atomicAdd(p.ysq, ysq_acc);
+    }
+  } else {
+    // =========================================================== finalisers: merge, certainty test, labels,
+    // fused Lloyd accumulation
+    const int pt = tid - (kTcMmaWarp + 1 + kTcProdWarps) * 32;
+    constexpr bool in_regs = INREG;
     int recheck_acc = 0;
-    const float eps_trunc = kTcKeyTrunc;
-
-    auto finalize = [&](uint32_t itf, int64_t tilef) {
-      const uint32_t rb = itf & 1u;
-      mbar_wait(&S->r_full[rb], (itf >> 1) & 1u);
+    float yn[kTcDReg];
+    auto prefetch = [&](int64_t tile) {
+      const int64_t row = tile * kTcTile + pt;
+#pragma unroll
+      for (int d = 0; d < kTcDReg; ++d) yn[d] = (in_regs && d < D && row < p.n) ? p.Y[row * p.ld + d] : 0.f;
+    };
+    uint32_t it = 0;
+    if ((int64_t)blockIdx.x < n_tiles) prefetch(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      float y[kTcDReg];
+#pragma unroll
+      for (int d = 0; d < kTcDReg; ++d) y[d] = yn[d];
+      if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+      const uint32_t rb = it & 1u;
+      mbar_wait(&S->r_full[rb], (it >> 1) & 1u);
       int b = 0x7fffffff, s2 = 0x7fffffff, bc = 0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int gb = S->res_best[rb][g][pt], gs = S->res_second[rb][g][pt], gc = S->res_chunk[rb][g][pt];
-        // merge (b, s2) with (gb, gs): new second = min(s2, gs, max(b, gb))
-        const int t = max(b, gb);
+        const int t = max(b, gb);           // merge: new second = min(s2, gs, max(b, gb))
         s2 = min(min(s2, gs), t);
         if (gb < b) { b = gb; bc = (gc << 2) | g; }
       }
+      const float thr = S->res_thr[rb][pt];
       tc::mbar_arrive(&S->r_empty[rb]);
-      const int64_t row = tilef * kTcTile + pt;
+      const int64_t row = tile * kTcTile + pt;
       const bool valid = row < p.n;
       int lab = -1;
       if (valid) {
@@ -249,107 +386,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
         int k = ch * kTcChunk + g * kTcColsPerWarp + h * 32 + (b & 31);
         if (k >= K) k = K - 1;   // cannot happen for finite data (dummy centres score 2^126)
         const float s1f = __uint_as_float((uint32_t)b & 0xFFFFFFE0u);
-        const float s2f = __uint_as_float((uint32_t)s2 & 0xFFFFFFE0u);
+        const float s2f = fminf(__uint_as_float((uint32_t)s2 & 0xFFFFFFE0u), thr);
         float xn2 = 0.f;
-        for (int d = 0; d < D; ++d) {
-          const float y = p.Y[row * p.ld + d];
-          xn2 = fmaf(y, y, xn2);
+        if constexpr (in_regs) {
+#pragma unroll
+          for (int d = 0; d < kTcDReg; ++d) xn2 = fmaf(y[d], y[d], xn2);
+        } else {
+#pragma unroll 4
+          for (int d = 0; d < D; ++d) {
+            const float v = p.Y[row * p.ld + d];
+            xn2 = fmaf(v, v, xn2);
+          }
         }
         const float rr = sqrtf(xn2) * 1.0001f + cmax;
         const float E = kTcErrScale * rr * rr;
-        const bool certain = (b >= 0) && (K == 1 || (s1f * eps_trunc + E < s2f - E));
+        const bool certain = (b >= 0) && (b != 0x7fffffff) && (K == 1 || (s1f * kTcKeyTrunc + E < s2f - E));
         p.labels[row] = k;
         if (certain) {
           lab = k;
-          if (p.inertia != nullptr) {
-            double acc = 0.0;
-            const double* c = p.centers + (size_t)k * D;
-            for (int d = 0; d < D; ++d) {
-              const double t = __dsub_rn((double)p.Y[row * p.ld + d], c[d]);
-              acc = __dadd_rn(acc, __dmul_rn(t, t));
-            }
-            inertia_acc += acc;
-          }
         } else {
           ++recheck_acc;
           const int pos = atomicAdd(p.recheck_count, 1);
           p.recheck_list[pos] = (int)row;
         }
       }
-      // fused Lloyd accumulation, segmented by runs of equal labels inside the warp
-      if (p.sums != nullptr) {
-        const int prev = __shfl_up_sync(0xffffffffu, lab, 1);
-        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || lab != prev);
-        const int my_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-        bool take[5];
+      // fused Lloyd accumulation into this call's private sums / counts.  32 consecutive frames of a
+      // trajectory mostly share their label: one warp reduction and D atomics; otherwise one atomic per
+      // frame and coordinate.
+      if (p.accumulate) {
+        const int lab0 = __shfl_sync(0xffffffffu, lab, 0);
+        if (__all_sync(0xffffffffu, lab == lab0)) {
+          if (lab0 >= 0) {
+            if constexpr (in_regs) {
 #pragma unroll
-        for (int s = 0; s < 5; ++s) {
-          const int oh = __shfl_down_sync(0xffffffffu, my_head, 1 << s);
-          take[s] = (lane + (1 << s) < 32) && (oh == my_head);
-        }
-        const bool is_head = (lane == my_head) && lab >= 0;
-        for (int d = 0; d < D; ++d) {
-          double v = (lab >= 0) ? (double)p.Y[row * p.ld + d] : 0.0;
-#pragma unroll
-          for (int s = 0; s < 5; ++s) {
-            const double o = __shfl_down_sync(0xffffffffu, v, 1 << s);
-            if (take[s]) v += o;
+              for (int d = 0; d < kTcDReg; ++d) {
+                if (d < D) {
+                  const double v = warp_sum((double)y[d]);
+                  if (lane == 0) atomicAdd(p.lsums + (size_t)lab0 * D + d, v);
+                }
+              }
+            } else {
+              for (int d = 0; d < D; ++d) {
+                const double v = warp_sum((double)p.Y[row * p.ld + d]);
+                if (lane == 0) atomicAdd(p.lsums + (size_t)lab0 * D + d, v);
+              }
+            }
+            if (lane == 0) atomicAdd(p.lcounts + lab0, 32ull);
           }
-          if (is_head) atomicAdd(p.sums + (size_t)lab * D + d, v);
-        }
-        if (is_head && p.counts != nullptr) {
-          const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
-          const int next = above ? (__ffs(above) - 1) : 32;
-          atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + lab), (unsigned long long)(next - lane));
+        } else if (lab >= 0) {
+          if constexpr (in_regs) {
+#pragma unroll
+            for (int d = 0; d < kTcDReg; ++d)
+              if (d < D) atomicAdd(p.lsums + (size_t)lab * D + d, (double)y[d]);
+          } else {
+            for (int d = 0; d < D; ++d) atomicAdd(p.lsums + (size_t)lab * D + d, (double)p.Y[row * p.ld + d]);
+          }
+          atomicAdd(p.lcounts + lab, 1ull);
         }
       }
-    };
-
-    uint32_t it = 0;
-    int64_t prev_tile = -1;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t ab = it & 1u;
-      mbar_wait(&S->a_empty[ab], ((it >> 1) & 1u) ^ 1u);
-      unsigned char* A = sA + (size_t)ab * kTcTile * KS * 4;
-      const int64_t row = tile * kTcTile + pt;
-      auto put = [&](int slot, float v) {
-        *reinterpret_cast<float*>(A + tc::off_kmajor(pt, slot, lbo, sbo)) = v;
-      };
-      float xn2 = 0.f;
-      for (int d = 0; d < D; ++d) {
-        const float y = (row < p.n) ? p.Y[row * p.ld + d] : 0.f;
-        xn2 = fmaf(y, y, xn2);
-        const float hi = tf32_rna(y);
-        const float lo = tf32_rna(y - hi);
-        put(3 * d + 0, hi);
-        put(3 * d + 1, lo);
-        put(3 * d + 2, hi);
-      }
-      const float one = (row < p.n) ? 1.0f : 0.0f;
-      put(3 * D + 0, one);
-      put(3 * D + 1, one);
-      put(3 * D + 2, one);
-      const float x1 = tf32_rna(xn2);
-      put(3 * D + 3, x1);
-      put(3 * D + 4, tf32_rna(xn2 - x1));
-      for (int s = 3 * D + 5; s < KS; ++s) put(s, 0.f);
-      fence_proxy_async_smem();
-      tc::mbar_arrive(&S->a_full[ab]);
-      if (prev_tile >= 0) finalize(it - 1, prev_tile);
-      prev_tile = tile;
     }
-    if (prev_tile >= 0) finalize(it - 1, prev_tile);
-
-    if (p.inertia != nullptr || p.n_rechecked != nullptr) {
-      const double v = warp_sum(inertia_acc);
+    if (p.n_rechecked != nullptr) {
       int r = recheck_acc;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-      if (lane == 0) {
-        if (p.inertia != nullptr && v != 0.0) atomicAdd(p.inertia, v);
-        if (p.n_rechecked != nullptr && r)
-          atomicAdd(reinterpret_cast<unsigned long long*>(p.n_rechecked), (unsigned long long)r);
-      }
+      if (lane == 0 && r) atomicAdd(reinterpret_cast<unsigned long long*>(p.n_rechecked), (unsigned long long)r);
     }
   }
 
@@ -365,7 +465,6 @@ __global__ void __launch_bounds__(256) kmeans_recheck_kernel(KmTcParams p) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int count = *p.recheck_count;
   const int D = p.D, K = p.K;
-  double inertia_acc = 0.0;
   for (int e = gw; e < count; e += nw) {
     const int64_t row = p.recheck_list[e];
     double bd = 1.7976931348623157e308;
@@ -387,13 +486,43 @@ __global__ void __launch_bounds__(256) kmeans_recheck_kernel(KmTcParams p) {
     }
     if (lane == 0) {
       p.labels[row] = bk;
-      inertia_acc += bd;
-      if (p.counts != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + bk), 1ull);
+      if (p.accumulate) atomicAdd(p.lcounts + bk, 1ull);
     }
-    if (p.sums != nullptr)
-      for (int d = lane; d < D; d += 32) atomicAdd(p.sums + (size_t)bk * D + d, (double)p.Y[row * p.ld + d]);
+    if (p.accumulate)
+      for (int d = lane; d < D; d += 32) atomicAdd(p.lsums + (size_t)bk * D + d, (double)p.Y[row * p.ld + d]);
   }
-  if (lane == 0 && p.inertia != nullptr && inertia_acc != 0.0) atomicAdd(p.inertia, inertia_acc);
+}
+
+// Hand this call's sums / counts to the caller and form the inertia from them:
+//   sum_t |y_t - c_l(t)|^2 = sum_t |y_t|^2 + sum_k (n_k |c_k|^2 - 2 c_k . S_k)       (all in fp64)
+__global__ void __launch_bounds__(256) kmeans_tc_commit_kernel(KmTcParams p) {
+  __shared__ double s_red[8];
+  const int D = p.D, K = p.K;
+  double part = 0.0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+    const unsigned long long nk = p.lcounts[k];
+    if (nk == 0) continue;
+    double n2 = 0.0, cs = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double c = p.centers[(size_t)k * D + d], sv = p.lsums[(size_t)k * D + d];
+      n2 = fma(c, c, n2);
+      cs = fma(c, sv, cs);
+      if (p.sums != nullptr) p.sums[(size_t)k * D + d] += sv;
+    }
+    if (p.counts != nullptr) p.counts[k] += (int64_t)nk;
+    part += (double)nk * n2 - 2.0 * cs;
+  }
+  if (p.inertia != nullptr) {
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += s_red[w];
+      if (blockIdx.x == 0) t += *p.ysq;
+      atomicAdd(p.inertia, t);
+    }
+  }
 }
 
 static inline int tc_slots(int D) { return ((3 * D + 5) + 7) / 8 * 8; }
@@ -406,28 +535,47 @@ bool kmeans_tc_supported(int D, int K) {
   return D >= 1 && K >= 1 && tc_smem_bytes(D, K) <= 227 * 1024 && tc_kpad(K) / kTcChunk <= (1 << 20);
 }
 
-size_t kmeans_tc_ws_bytes(int64_t n) { return (size_t)n * sizeof(int) + 64; }
+size_t kmeans_tc_ws_bytes(int64_t n, int D, int K) {
+  // [count | ysq | pad to 64 B][local sums K x D][local counts K][re-check list n]
+  return 64 + ((size_t)K * D + K) * sizeof(double) + (size_t)n * sizeof(int) + 64;
+}
 
 int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double* centers, int K, int32_t* labels,
-                     double* sums, int64_t* counts, double* inertia, int64_t* n_rechecked, void* ws,
+                     const int32_t* hints, double* sums, int64_t* counts, double* inertia, int64_t* n_rechecked, void* ws,
                      float* dbg_scores, cudaStream_t st) {
   KmTcParams p;
   p.Y = Y; p.n = n; p.D = D; p.ld = ld; p.centers = centers; p.K = K;
   p.Kpad = tc_kpad(K); p.KS = tc_slots(D);
-  p.labels = labels; p.sums = sums; p.counts = counts; p.inertia = inertia; p.n_rechecked = n_rechecked;
-  p.recheck_count = static_cast<int*>(ws);
-  p.recheck_list = static_cast<int*>(ws) + 16;
+  p.labels = labels; p.hints = hints; p.sums = sums; p.counts = counts; p.inertia = inertia; p.n_rechecked = n_rechecked;
+  unsigned char* w8 = static_cast<unsigned char*>(ws);
+  p.recheck_count = reinterpret_cast<int*>(w8);
+  p.ysq = reinterpret_cast<double*>(w8 + 16);
+  p.lsums = reinterpret_cast<double*>(w8 + 64);
+  p.lcounts = reinterpret_cast<unsigned long long*>(p.lsums + (size_t)K * D);
+  p.recheck_list = reinterpret_cast<int*>(p.lcounts + K);
+  p.accumulate = (sums != nullptr || inertia != nullptr) ? 1 : 0;
   p.dbg_scores = dbg_scores;
   PMB_REQUIRE(n < (int64_t)0x7fffffff, "pmb_kmeans_assign: tensor path needs n < 2^31");
   const size_t smem = tc_smem_bytes(D, K);
-  PMB_CUDA(cudaMemsetAsync(p.recheck_count, 0, 64, st));
-  PMB_CUDA(cudaFuncSetAttribute(kmeans_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PMB_CUDA(cudaMemsetAsync(ws, 0, 64 + (p.accumulate ? ((size_t)K * D + K) * sizeof(double) : 0), st));
   const int64_t n_tiles = (n + kTcTile - 1) / kTcTile;
   const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-  kmeans_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
-  PMB_LAUNCH_CHECK();
+  auto launch = [&](auto kern) -> int {
+    PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kTcThreads, smem, st>>>(p);
+    PMB_LAUNCH_CHECK();
+    return PMB_OK;
+  };
+  int rc;
+  if (dbg_scores != nullptr) rc = (D <= kTcDReg) ? launch(kmeans_tc_kernel<true, true>) : launch(kmeans_tc_kernel<true, false>);
+  else rc = (D <= kTcDReg) ? launch(kmeans_tc_kernel<false, true>) : launch(kmeans_tc_kernel<false, false>);
+  if (rc != PMB_OK) return rc;
   kmeans_recheck_kernel<<<2 * kNumSMs, 256, 0, st>>>(p);
   PMB_LAUNCH_CHECK();
+  if (p.accumulate) {
+    kmeans_tc_commit_kernel<<<(K + 255) / 256 < 64 ? (K + 255) / 256 : 64, 256, 0, st>>>(p);
+    PMB_LAUNCH_CHECK();
+  }
   return PMB_OK;
 }
 

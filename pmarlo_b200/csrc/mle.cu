@@ -291,8 +291,9 @@ __device__ long long g_dbg[8];  // phase cycle counters of the last grid-kernel 
 
 // REG: one row per warp with K <= 1024: the warp keeps its row of S in registers (32 doubles per
 // lane) for the whole iteration, so an iteration touches no memory but the K-vector exchange.
-// SIMT fp64 runs at ~1/16 of the fp32 rate on B200, so the kernel is built to minimise fp64
-// instructions: 4 per matrix element (add, 2 Newton FMAs, accumulate FMA).
+// The kernel keeps the fp64 work per matrix element at 4 instructions (add, 2 Newton FMAs, accumulate
+// FMA; B200 issues 57 fp64 FMA/clk/SM, profiles/r01a_ubench.log); an iteration is bound by the
+// latency of the K-vector exchange between the CTAs.
 template <bool REG>
 __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) {
   extern __shared__ __align__(16) double sm[];

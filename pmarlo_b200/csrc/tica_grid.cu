@@ -1,9 +1,10 @@
-// tica_grid.cu -- K4 on many SMs: the same algorithm as tica_solve_kernel (tica.cu) as ONE
-// cooperative kernel.  SIMT fp64 on B200 runs at ~1/16 of the fp32 rate, so a d = 256 Jacobi
-// eigen-solve (3e9 fp64 operations over ~30 sweeps) is throughput-bound on a single SM
-// (measured 171 ms); here every round of the round-robin ordering gives one column pair to each
-// warp of the grid and the rounds are separated by grid barriers.  Data that other CTAs wrote is
-// always read with ld.global.cg (L2), never through L1.
+// tica_grid.cu -- K4 on several SMs: the same algorithm as tica_solve_kernel (tica.cu) as ONE
+// cooperative kernel.  A d = 256 Jacobi eigen-solve is latency-bound (about 3e9 fp64 operations, but
+// thousands of dependent rounds): the single-CTA kernel needs 171 ms, a grid-wide cyclic ordering
+// with one grid barrier per round 56 ms (measured on B200).  Here the rows are processed as BLOCK
+// pairs: a CTA orthogonalises the 2 x 16 rows of its block pair completely in shared memory before
+// the next grid barrier, so a sweep has 15 grid barriers instead of 255.  Data that other CTAs wrote
+// is always read with ld.global.cg (L2), never through L1.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -12,7 +13,7 @@ namespace cg = cooperative_groups;
 
 namespace pmb {
 
-constexpr int kTgThreads = 128;
+constexpr int kTgThreads = 512;   // 16 warps: one local row pair each
 constexpr int kTgMaxSweeps = 40;
 constexpr double kTgTol = 4.5e-16;  // x sqrt(n), as in tica.cu
 
@@ -24,56 +25,135 @@ struct TicaGridWs {
 
 __device__ __forceinline__ double ldg_cg(const double* p) { return __ldcg(p); }
 
-// one-sided cyclic Jacobi on the rows of W (n x n, symmetric input), rotations accumulated in V
-__device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, int* flags) {
-  const int lane = threadIdx.x & 31;
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int np = (n + 1) & ~1, half = np >> 1;
-  const double tol = kTgTol * sqrt((double)n);
+// 1/sqrt(x) and 1/x for x in [2^-8, 2^8]: fp32 seed (MUFU) + two fp64 Newton steps.  The IEEE fp64
+// divide / sqrt sequences cost ~300 dependent cycles each, and the rotation angle sits on the critical
+// path of every Jacobi round; these are ~100 cycles and accurate to a few ulp.
+__device__ __forceinline__ double tg_rsqrt(double x) {
+  double y = (double)rsqrtf((float)x);
+  double e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-x * y, y, 1.0);
+  return fma(0.5 * y, e, y);
+}
+__device__ __forceinline__ double tg_rcp(double x) {
+  double y = (double)__frcp_rn((float)x);
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+// Rotation (c, s) that orthogonalises two rows with squared norms a, b and inner product g != 0:
+// t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2 g), written without a division:
+// t = sign(alpha) g / (|alpha| + sqrt(alpha^2 + g^2)), alpha = (b - a) / 2, after scaling alpha and g
+// by a power of two so that the fp32 seeds cannot under- or overflow.
+__device__ __forceinline__ void tg_rotation(double a, double b, double g, double& c, double& s) {
+  const double alpha = 0.5 * (b - a);
+  const double mx = fmax(fabs(alpha), fabs(g));
+  const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
+  if (ex < 64 || ex > 1980) {   // denormal-range or huge operands: IEEE sequence
+    const double zeta = (b - a) / (2.0 * g);
+    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    c = 1.0 / sqrt(1.0 + t * t);
+    s = c * t;
+    return;
+  }
+  const double sc = __hiloint2double((2046 - ex) << 20, 0);   // 2^(1023 - ex): mx * sc in [1, 2)
+  const double as = alpha * sc, gs = g * sc;
+  const double q = fma(as, as, gs * gs);                      // [1, 8)
+  const double r = q * tg_rsqrt(q);
+  const double inv = tg_rcp(fabs(as) + r);
+  const double t = ((__double2hiint(alpha) < 0) ? -gs : gs) * inv;
+  c = tg_rsqrt(fma(t, t, 1.0));
+  s = c * t;
+}
+
+// One-sided BLOCK Jacobi on the rows of W (n x n, symmetric input), rotations accumulated in V.
+// The rows are cut into blocks of `b`; a CTA takes one block PAIR per block round (round-robin
+// tournament over the blocks), loads its 2b rows of W and V into shared memory, runs one complete
+// cyclic sweep over those 2b rows there (2b - 1 local rounds separated by __syncthreads, one warp
+// per row pair) and writes them back.  A sweep therefore costs nb - 1 grid barriers instead of
+// n - 1, and every rotation works on shared memory instead of L2.
+__device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, int b, int* flags, double* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  int nb = (n + b - 1) / b;
+  if (nb & 1) ++nb;
+  if (nb < 2) nb = 2;
+  const int npairs = nb >> 1, rows = 2 * b;
+  double* sW = sm;
+  double* sV = sm + (size_t)rows * n;
+  const double tol2 = kTgTol * kTgTol * (double)n;
   if (blockIdx.x == 0 && threadIdx.x == 0) { flags[0] = 0; flags[1] = 0; }
   grid.sync();
   int sweep = 0;
   for (; sweep < kTgMaxSweeps; ++sweep) {
     int rotated = 0;
-    for (int r = 0; r < np - 1; ++r) {
-      for (int k = gwarp; k < half; k += nwarps) {
-        int p, q;
-        if (k == 0) { p = np - 1; q = r; }
-        else { p = (r + k) % (np - 1); q = (r - k + (np - 1)) % (np - 1); }
-        if (p >= n || q >= n) continue;
-        if (p > q) { const int t = p; p = q; q = t; }
-        double* wp = W + (size_t)p * n;
-        double* wq = W + (size_t)q * n;
-        double a = 0.0, b = 0.0, g = 0.0;
-        for (int e = lane; e < n; e += 32) {
-          const double x = ldg_cg(wp + e), y = ldg_cg(wq + e);
-          a = fma(x, x, a);
-          b = fma(y, y, b);
-          g = fma(x, y, g);
+    for (int r = 0; r < nb - 1; ++r) {
+      for (int k = blockIdx.x; k < npairs; k += gridDim.x) {
+        int bi, bj;
+        if (k == 0) { bi = nb - 1; bj = r; }
+        else { bi = (r + k) % (nb - 1); bj = (r - k + (nb - 1)) % (nb - 1); }
+        if (bi > bj) { const int t = bi; bi = bj; bj = t; }
+        auto grow = [&](int li) { return li < b ? bi * b + li : bj * b + (li - b); };
+        for (int li = warp; li < rows; li += nwarps) {
+          const int gr = grow(li);
+          if (gr < n)
+            for (int e = lane; e < n; e += 32) {
+              sW[(size_t)li * n + e] = ldg_cg(W + (size_t)gr * n + e);
+              if (V != nullptr) sV[(size_t)li * n + e] = ldg_cg(V + (size_t)gr * n + e);
+            }
         }
-        a = warp_sum(a);
-        b = warp_sum(b);
-        g = warp_sum(g);
-        if (fabs(g) <= tol * sqrt(a * b) || g == 0.0) continue;
-        rotated = 1;
-        const double zeta = (b - a) / (2.0 * g);
-        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-        for (int e = lane; e < n; e += 32) {
-          const double x = ldg_cg(wp + e), y = ldg_cg(wq + e);
-          __stcg(wp + e, c * x - s * y);
-          __stcg(wq + e, s * x + c * y);
-        }
-        if (V != nullptr) {
-          double* vp = V + (size_t)p * n;
-          double* vq = V + (size_t)q * n;
-          for (int e = lane; e < n; e += 32) {
-            const double x = ldg_cg(vp + e), y = ldg_cg(vq + e);
-            __stcg(vp + e, c * x - s * y);
-            __stcg(vq + e, s * x + c * y);
+        __syncthreads();
+        const int lm = rows - 1;   // local tournament over `rows` players (rows is even)
+        for (int lr = 0; lr < lm; ++lr) {
+          for (int kk = warp; kk < b; kk += nwarps) {
+            int lp, lq;
+            if (kk == 0) { lp = lm; lq = lr; }
+            else { lp = (lr + kk) % lm; lq = (lr - kk + lm) % lm; }
+            int gp = grow(lp), gq = grow(lq);
+            if (gp >= n || gq >= n) continue;
+            if (gp > gq) { const int t = lp; lp = lq; lq = t; }
+            double* wp = sW + (size_t)lp * n;
+            double* wq = sW + (size_t)lq * n;
+            double a = 0.0, bb = 0.0, g = 0.0;
+            for (int e = lane; e < n; e += 32) {
+              const double x = wp[e], y = wq[e];
+              a = fma(x, x, a);
+              bb = fma(y, y, bb);
+              g = fma(x, y, g);
+            }
+            a = warp_sum(a);
+            bb = warp_sum(bb);
+            g = warp_sum(g);
+            if (g * g <= tol2 * (a * bb) || g == 0.0) continue;
+            rotated = 1;
+            double c, s;
+            tg_rotation(a, bb, g, c, s);
+            for (int e = lane; e < n; e += 32) {
+              const double x = wp[e], y = wq[e];
+              wp[e] = c * x - s * y;
+              wq[e] = s * x + c * y;
+            }
+            if (V != nullptr) {
+              double* vp = sV + (size_t)lp * n;
+              double* vq = sV + (size_t)lq * n;
+              for (int e = lane; e < n; e += 32) {
+                const double x = vp[e], y = vq[e];
+                vp[e] = c * x - s * y;
+                vq[e] = s * x + c * y;
+              }
+            }
           }
+          __syncthreads();
         }
+        for (int li = warp; li < rows; li += nwarps) {
+          const int gr = grow(li);
+          if (gr < n)
+            for (int e = lane; e < n; e += 32) {
+              __stcg(W + (size_t)gr * n + e, sW[(size_t)li * n + e]);
+              if (V != nullptr) __stcg(V + (size_t)gr * n + e, sV[(size_t)li * n + e]);
+            }
+        }
+        __syncthreads();
       }
       grid.sync();
     }
@@ -105,7 +185,9 @@ __device__ void rank_grid(cg::grid_group& grid, const double* vals, int n, int* 
 
 __global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
     const double* __restrict__ C00, const double* __restrict__ C0t, int d, double eps,
-    double* __restrict__ evals, double* __restrict__ evecs, int32_t* __restrict__ rank_out, TicaGridWs ws) {
+    double* __restrict__ evals, double* __restrict__ evecs, int32_t* __restrict__ rank_out, TicaGridWs ws,
+    int blk) {
+  extern __shared__ __align__(16) double tg_sm[];
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gnt = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31, gwarp = gtid >> 5, nwarps = gnt >> 5;
@@ -118,7 +200,7 @@ __global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
     ws.V[i] = (r == c) ? 1.0 : 0.0;
   }
   grid.sync();
-  const int sweeps1 = jacobi_grid(grid, ws.W, ws.V, d, ws.ctrl + 1);
+  const int sweeps1 = jacobi_grid(grid, ws.W, ws.V, d, blk, ws.ctrl + 1, tg_sm);
   for (int j = gwarp; j < d; j += nwarps) {   // Rayleigh quotients v_j . w_j
     double acc = 0.0;
     for (int e = lane; e < d; e += 32) acc = fma(ldg_cg(ws.V + (size_t)j * d + e), ldg_cg(ws.W + (size_t)j * d + e), acc);
@@ -206,7 +288,7 @@ __global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
     ws.V[i] = (r == c) ? 1.0 : 0.0;
   }
   grid.sync();
-  const int sweeps2 = jacobi_grid(grid, ws.W, ws.V, m, ws.ctrl + 1);
+  const int sweeps2 = jacobi_grid(grid, ws.W, ws.V, m, blk, ws.ctrl + 1, tg_sm);
   for (int j = gwarp; j < m; j += nwarps) {
     double acc = 0.0;
     for (int e = lane; e < m; e += 32) acc = fma(ldg_cg(ws.V + (size_t)j * m + e), ldg_cg(ws.W + (size_t)j * m + e), acc);
@@ -259,14 +341,22 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   int dev = 0, sms = 0, per_sm = 0;
   PMB_CUDA(cudaGetDevice(&dev));
   PMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tica_solve_grid_kernel, kTgThreads, 0));
+  // rows per block: the 2 b rows of W and of V (n doubles each) must fit in shared memory
+  int blk = 16;
+  while (blk > 1 && (size_t)4 * blk * d * sizeof(double) > (size_t)200 * 1024) blk >>= 1;
+  const size_t smem = (size_t)4 * blk * d * sizeof(double);
+  PMB_REQUIRE(smem <= (size_t)227 * 1024, "pmb_tica_solve: d=%d too large for the block-Jacobi kernel", d);
+  PMB_CUDA(cudaFuncSetAttribute(tica_solve_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tica_solve_grid_kernel, kTgThreads, smem));
   PMB_REQUIRE(per_sm >= 1, "pmb_tica_solve: kernel does not fit on an SM");
-  const int half = ((d + 1) & ~1) / 2, wpc = kTgThreads / 32;
-  int grid = (half + wpc - 1) / wpc;
+  int nb = (d + blk - 1) / blk;
+  if (nb & 1) ++nb;
+  int grid = nb / 2;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  void* args[] = {(void*)&C00, (void*)&C0t, (void*)&d, (void*)&eps, (void*)&evals, (void*)&evecs, (void*)&rank, (void*)&w};
-  PMB_CUDA(cudaLaunchCooperativeKernel((void*)tica_solve_grid_kernel, dim3(grid), dim3(kTgThreads), args, 0, st));
+  void* args[] = {(void*)&C00, (void*)&C0t, (void*)&d, (void*)&eps, (void*)&evals, (void*)&evecs, (void*)&rank, (void*)&w,
+                  (void*)&blk};
+  PMB_CUDA(cudaLaunchCooperativeKernel((void*)tica_solve_grid_kernel, dim3(grid), dim3(kTgThreads), args, smem, st));
   count_launch();
   return PMB_OK;
 }

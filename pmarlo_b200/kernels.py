@@ -197,9 +197,10 @@ def project(X: torch.Tensor, a: torch.Tensor, nanfill: torch.Tensor, W: torch.Te
 def kmeans_assign(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor | None = None,
                   sums: torch.Tensor | None = None, counts: torch.Tensor | None = None,
                   inertia: torch.Tensor | None = None, n_rechecked: torch.Tensor | None = None,
-                  impl: int = 0):
+                  impl: int = 0, hints: torch.Tensor | None = None):
     """K6.  labels int32 (n,), optional accumulation into sums/counts/inertia.
-    impl: 0 auto, 1 SIMT kernel, 2 tcgen05 score GEMM with fused argmin."""
+    impl: 0 auto, 1 SIMT kernel, 2 tcgen05 score GEMM with fused argmin.
+    hints: int32 labels of a previous assignment (may be ``labels`` itself); results never depend on them."""
     if Y.dtype not in (torch.float32, torch.float64) or not Y.is_cuda:
         raise TypeError("Y must be a float32/float64 CUDA tensor")
     _dev(centers, torch.float64, "centers")
@@ -211,11 +212,16 @@ def kmeans_assign(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor |
         raise ValueError("centers and Y disagree on the feature dimension")
     if labels is None:
         labels = torch.empty((n,), dtype=torch.int32, device=Y.device)
+    if hints is not None:
+        _dev(hints, torch.int32, "hints")
+        if hints.numel() != n or not hints.is_contiguous():
+            raise ValueError("hints must be a contiguous int32 tensor with one entry per frame")
     L = _lib.lib()
     ws = _ws(L.pmb_kmeans_assign_ws_bytes(n, D, K), Y.device) if Y.dtype == torch.float32 else None
     check(L.pmb_kmeans_assign(ptr(Y), 1 if Y.dtype == torch.float64 else 0, n, D, ld,
                               ptr(centers), K, ptr(labels), ptr(sums), ptr(counts),
-                              ptr(inertia), ptr(n_rechecked), ptr(ws), ws.numel() if ws is not None else 0,
+                              ptr(inertia), ptr(n_rechecked), ptr(hints), ptr(ws),
+                              ws.numel() if ws is not None else 0,
                               int(impl), stream_handle(Y.device)),
           "pmb_kmeans_assign")
     return labels

@@ -71,9 +71,9 @@ def seeded_initial_centers(Y: torch.Tensor, K: int, seed: int, comm: Comm) -> to
         n = int(Y.shape[0])
         if n < K:
             raise ValueError(f"rank 0 holds {n} frames, fewer than n_states={K}")
-        g = torch.Generator(device="cpu")
-        g.manual_seed(int(seed))
-        idx = torch.randperm(n, generator=g)[:K].sort().values.to(Y.device)
+        # O(K) draw (numpy's Generator.choice without replacement does not permute all n frames)
+        pick = np.sort(np.random.default_rng(int(seed)).choice(n, size=K, replace=False))
+        idx = torch.from_numpy(pick).to(Y.device)
         centers.copy_(Y.index_select(0, idx).to(torch.float64))
     comm.broadcast(centers, src=0)
     return centers
@@ -129,7 +129,7 @@ def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | N
                            timer=timer)
         # final labels against the final centres (model.transform, clustering.py:609)
         with timer.stage("kmeans_assign"):
-            kernels.kmeans_assign(Y, res.centers, labels=labels)
+            kernels.kmeans_assign(Y, res.centers, labels=labels, hints=labels)
 
     with timer.stage("count"):
         C = torch.zeros((cfg.n_states, cfg.n_states), dtype=torch.int64, device=dev)

@@ -123,7 +123,7 @@ def project(X, a, nanfill, W, out_f64=False, out=None):
     return torch.from_numpy(y if out_f64 else y.astype(np.float32))
 
 
-def kmeans_assign(Y, centers, labels=None, sums=None, counts=None, inertia=None, n_rechecked=None, impl=0):
+def kmeans_assign(Y, centers, labels=None, sums=None, counts=None, inertia=None, n_rechecked=None, impl=0, hints=None):
     y = _np(Y).astype(np.float64)
     lab, dmin = oracle.kmeans.assign(y, _np(centers))
     if labels is None:

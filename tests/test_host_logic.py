@@ -143,7 +143,7 @@ def test_lloyd_host_loop_matches_oracle_semantics(monkeypatch):
     Y = np.concatenate([rng.normal(size=(200, 2)) + c for c in ([0, 0], [6, 0], [0, 6])])
     c0 = Y[[0, 250, 500]].copy()
 
-    def fake_assign(Yt, centers, labels=None, sums=None, counts=None, inertia=None, n_rechecked=None):
+    def fake_assign(Yt, centers, labels=None, sums=None, counts=None, inertia=None, n_rechecked=None, **_ignored):
         lab, dmin = oracle.kmeans.assign(Yt.numpy(), centers.numpy())
         labels.copy_(torch.from_numpy(lab.astype(np.int32)))
         if sums is not None:
