@@ -357,7 +357,7 @@ def gpu_arm(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "stages_ms": stages, "kmeans_iters_run": int(res.kmeans_iters),
         "tica_rank_sweeps": [int(v) for v in res.tica.rank_dev.tolist()],
-        "mle_phase_cycles": debug_counters(),
+        "mle_phase_cycles": debug_counters(), "kmeans_role_cycles": kmeans_debug_counters(), "tica_phase_cycles": tica_debug_counters(),
         "mle_iters": int(res.mle_info[0].item()), "timescales": [None if not np.isfinite(t) else float(t)
                                                                 for t in (res.timescales if res.timescales is not None else [])],
     }
@@ -374,6 +374,26 @@ def debug_counters():
 
     buf = (ctypes.c_int64 * 8)()
     _lib.check(_lib.lib().pmb_debug_counters(ctypes.cast(buf, ctypes.c_void_p)), "pmb_debug_counters")
+    return list(buf)
+
+
+def tica_debug_counters():
+    import ctypes
+
+    from pmarlo_b200 import _lib
+
+    buf = (ctypes.c_int64 * 8)()
+    _lib.check(_lib.lib().pmb_debug_counters_tica(ctypes.cast(buf, ctypes.c_void_p)), "pmb_debug_counters_tica")
+    return list(buf)
+
+
+def kmeans_debug_counters():
+    import ctypes
+
+    from pmarlo_b200 import _lib
+
+    buf = (ctypes.c_int64 * 16)()
+    _lib.check(_lib.lib().pmb_debug_counters_kmeans(ctypes.cast(buf, ctypes.c_void_p)), "pmb_debug_counters_kmeans")
     return list(buf)
 
 

@@ -173,6 +173,11 @@ PMB_API int pmb_kmeans_assign(const void* Y, int y_f64, int64_t n, int D, int64_
 /* Test hook of the tcgen05 path: also writes the (n x Kpad, Kpad = K rounded up to 256) fp32 score
  * matrix |y|^2 + |c_k|^2 - 2 y.c_k as it leaves TMEM, so that the error envelope the certainty test
  * relies on can be measured (tests/test_gpu_parity.py). */
+/* Debug: phase cycle counters of the last block-Jacobi solve (load, local sweeps, store, grid barrier,
+ * block rounds, total) as seen by CTA 0. */
+PMB_API int pmb_debug_counters_tica(int64_t* out8);
+/* Debug: role-timing counters of the last tcgen05 assignment (zeros unless built with -DPMB_KM_PROF). */
+PMB_API int pmb_debug_counters_kmeans(int64_t* out16);
 PMB_API int pmb_kmeans_tc_scores(const float* Y, int64_t n, int D, int64_t ld, const double* centers,
                       int K, int32_t* labels, float* scores, void* ws, size_t ws_bytes,
                       pmb_stream_t stream);

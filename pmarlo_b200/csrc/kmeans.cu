@@ -286,9 +286,16 @@ int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double*
                      const int32_t* hints, double* sums, int64_t* counts, double* inertia, int64_t* n_rechecked, void* ws,
                      float* dbg_scores, cudaStream_t st);
 
+int kmeans_tc_debug_counters(int64_t* out16);
 constexpr int64_t kKmTcMinFrames = 16384;   // below this the launch is latency-bound either way
 
 }  // namespace pmb
+
+extern "C" int pmb_debug_counters_kmeans(int64_t* out16) {
+  using namespace pmb;
+  PMB_REQUIRE(out16 != nullptr, "pmb_debug_counters_kmeans: null pointer");
+  return kmeans_tc_debug_counters(out16);
+}
 
 extern "C" size_t pmb_kmeans_assign_ws_bytes(int64_t n, int D, int K) {
   if (n <= 0 || !pmb::kmeans_tc_supported(D, K)) return 0;

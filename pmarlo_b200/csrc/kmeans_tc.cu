@@ -1,13 +1,14 @@
 // kmeans_tc.cu -- K6 (tensor-core path): nearest-centre assignment as a tcgen05 TF32 GEMM with the
 // argmin fused into the TMEM epilogue, labels bit-exact against the fp64 oracle.
 //
-//   score(t,k) = |y_t|^2 + |c_k|^2 - 2 y_t.c_k            (one 128 x 256 x KS MMA tile per chunk)
+//   score(t,k) - |y_t|^2 = |c_k|^2 - 2 y_t.c_k            (one 128 x 256 x KS MMA tile per chunk)
 //
 // The product is made fp32-accurate on TF32 tensor cores by splitting along the MMA K dimension
 // ("3xTF32 in K"): every coordinate d contributes three K slots
 //      A (frame side):  y_hi  y_lo  y_hi        B (centre side):  c'_hi  c'_hi  c'_lo     (c' = -2 c)
-// and the norms ride in spare slots (|c|^2 as three TF32 pieces against 1.0, |y|^2 as two pieces),
-// so the accumulator that leaves TMEM already is the squared distance.  KS = 3 D + 5 rounded up to 8.
+// and |c|^2 rides in two more slots (two TF32 pieces against 1.0), so the accumulator that leaves TMEM
+// is the squared distance minus |y|^2, which does not change the argmin.  Slot order: 0-1 |c|^2 pieces
+// (A side 1.0), then 2 + 3 d + {0,1,2}; KS = 3 D + 2 rounded up to 8 (D = 10: 32 slots, four MMAs).
 //
 // Pipeline (one persistent CTA per SM, 25 warps, warp-specialised, mbarrier hand-offs):
 //   warps 17-20  producers : build the A tile (128 frames x KS slots, K-major core-matrix layout) and
@@ -25,6 +26,21 @@
 #include "tc05.cuh"
 
 namespace pmb {
+
+// Role timing (build with -DPMB_KM_PROF): CTA 0 accumulates the cycles each warp role spends waiting on
+// its barriers and working; read back with pmb_debug_counters_kmeans.
+__device__ long long g_km_dbg[16];
+#ifdef PMB_KM_PROF
+#define KM_T(var) const long long var = clock64()
+#define KM_ACC(slot, a, b) km_prof[slot] += (b) - (a)
+#define KM_DECL long long km_prof[4] = {0, 0, 0, 0}
+#define KM_FLUSH(base, n) if (blockIdx.x == 0 && lane == 0) { for (int q_ = 0; q_ < (n); ++q_) g_km_dbg[(base) + q_] = km_prof[q_]; }
+#else
+#define KM_T(var)
+#define KM_ACC(slot, a, b)
+#define KM_DECL
+#define KM_FLUSH(base, n)
+#endif
 
 constexpr int kTcTile = 128;     // frames per tile  (MMA M)
 constexpr int kTcChunk = 256;    // centres per MMA  (MMA N)
@@ -73,11 +89,13 @@ struct TcSmem {
   uint32_t tmem_slot;
   float cmax;
   float red[32];
-  float thr[4][kTcTile];   // per-row screening threshold of tile it (slot it & 3)
+  float thr[4][kTcTile];   // per-row screening threshold of tile it (slot it & 3), minus |y|^2
+  float xn2[4][kTcTile];   // |y|^2 of the row
   int res_best[2][4][kTcTile];
   int res_second[2][4][kTcTile];
   int res_chunk[2][4][kTcTile];
   float res_thr[2][kTcTile];
+  float stage[kTcFinWarps][32][kTcDReg + 1];   // finalisers: transposed warp reduction of the coordinates
 };
 
 // DBG: also write the raw scores (tests).  INREG: D <= kTcDReg, a frame's coordinates live in registers.
@@ -107,7 +125,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
   }
   if (warp == kTcMmaWarp) tc::tmem_alloc(&S->tmem_slot, 512);
 
-  // ---- stage the centre operand: row k = [c'_hi c'_hi c'_lo]_d | n2 pieces (3) | 1 1 | 0...
+  // ---- stage the centre operand: row k = n2 pieces (2) | [c'_hi c'_hi c'_lo]_d | 0...
   float cmax2 = 0.f;
   for (int k = tid; k < Kpad; k += kTcThreads) {
     auto put = [&](int slot, float v) {
@@ -122,21 +140,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
         const float cm = -2.0f * c32;
         const float hi = tf32_rna(cm);
         const float lo = tf32_rna(cm - hi);
-        put(3 * d + 0, hi);
-        put(3 * d + 1, hi);
-        put(3 * d + 2, lo);
+        put(2 + 3 * d + 0, hi);
+        put(2 + 3 * d + 1, hi);
+        put(2 + 3 * d + 2, lo);
       }
       const float p1 = tf32_rna((float)n2);
-      const float p2 = tf32_rna((float)(n2 - (double)p1));
-      const float p3 = tf32_rna((float)(n2 - (double)p1 - (double)p2));
-      put(3 * D + 0, p1);
-      put(3 * D + 1, p2);
-      put(3 * D + 2, p3);
-      put(3 * D + 3, 1.0f);
-      put(3 * D + 4, 1.0f);
+      put(0, p1);
+      put(1, tf32_rna((float)(n2 - (double)p1)));
       cmax2 = fmaxf(cmax2, (float)n2 * 1.0001f);
     } else {
-      put(3 * D + 0, 8.507059e37f);   // 2^126: a dummy centre never wins
+      put(0, 8.507059e37f);   // 2^126: a dummy centre never wins
     }
   }
 #pragma unroll
@@ -161,14 +174,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     const int row = quarter * 32 + lane;
     uint32_t j = 0;   // chunk counter across tiles
     uint32_t it = 0;
+    KM_DECL;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       int best = 0x7fffffff, second = 0x7fffffff, bchunk = 0;
       // screening threshold of this row (written by the producers, handed over by the MMA warp)
+      KM_T(e0);
       mbar_wait(&S->thr_ready[it & 3u], (it >> 2) & 1u);
+      KM_T(e1);
+      KM_ACC(0, e0, e1);
       const float thr = S->thr[it & 3u][row];
+      const float xn2 = S->xn2[it & 3u][row];
       for (int c = 0; c < n_chunks; ++c, ++j) {
         const uint32_t tb = j & 1u;
+        KM_T(e2);
         mbar_wait(&S->t_full[tb], (j >> 1) & 1u);
+        KM_T(e3);
+        KM_ACC(1, e2, e3);
         tc::fence_after_sync();
 #pragma unroll
         for (int h = 0; h < kTcColsPerWarp / 32; ++h) {
@@ -178,22 +199,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
           if constexpr (DBG) {
             const int64_t grow = tile * kTcTile + row;
             if (grow < p.n)
-              for (int q = 0; q < 32; ++q) p.dbg_scores[grow * Kpad + c * kTcChunk + col0 + q] = v[q];
+              for (int q = 0; q < 32; ++q) p.dbg_scores[grow * Kpad + c * kTcChunk + col0 + q] = v[q] + xn2;
           }
           // screen: a block whose minimum is above the row's threshold cannot hold the best centre nor
           // one within the certainty margin of it (the finaliser caps `second` at the threshold)
-          float m8[8];
+          // 32 -> 1 with 3-input minima (FMNMX3): 10 + 4 + 1 + 1 instructions
+          float t12[12];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) m8[q] = fminf(fminf(v[4 * q], v[4 * q + 1]), fminf(v[4 * q + 2], v[4 * q + 3]));
-          const float bmin = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])),
-                                   fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
+          for (int q = 0; q < 10; ++q) t12[q] = fminf(fminf(v[3 * q], v[3 * q + 1]), v[3 * q + 2]);
+          t12[10] = v[30];
+          t12[11] = v[31];
+          float t4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) t4[q] = fminf(fminf(t12[3 * q], t12[3 * q + 1]), t12[3 * q + 2]);
+          const float bmin = fminf(fminf(fminf(t4[0], t4[1]), t4[2]), t4[3]);
           if (!__any_sync(0xffffffffu, bmin <= thr)) continue;
           // packed keys: score bits with the position inside this 32-column block in the low 5 bits
           const int blk_before = best;
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
-            const int k0 = (int)((__float_as_uint(v[q]) & 0xFFFFFFE0u) | (uint32_t)q);
-            const int k1 = (int)((__float_as_uint(v[q + 1]) & 0xFFFFFFE0u) | (uint32_t)(q + 1));
+            const int k0 = (int)((__float_as_uint(fmaxf(v[q] + xn2, 0.f)) & 0xFFFFFFE0u) | (uint32_t)q);
+            const int k1 = (int)((__float_as_uint(fmaxf(v[q + 1] + xn2, 0.f)) & 0xFFFFFFE0u) | (uint32_t)(q + 1));
             const int lo = min(k0, k1), hi = max(k0, k1);
             const int t = max(best, lo);
             second = min(min(second, hi), t);
@@ -204,44 +230,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S->t_empty[tb]);
+        KM_T(e4);
+        KM_ACC(2, e3, e4);
       }
       const uint32_t rb = it & 1u;
+      KM_T(e5);
       mbar_wait(&S->r_empty[rb], ((it >> 1) & 1u) ^ 1u);
+      KM_T(e6);
+      KM_ACC(3, e5, e6);
       S->res_best[rb][grp][row] = best;
       S->res_second[rb][grp][row] = second;
       S->res_chunk[rb][grp][row] = bchunk;
-      if (grp == 0) S->res_thr[rb][row] = thr;
+      if (grp == 0) S->res_thr[rb][row] = thr + xn2;   // back in score space, like the keys
       tc::mbar_arrive(&S->r_full[rb]);
     }
+    if (warp == 0) { KM_FLUSH(0, 4); }
   } else if (warp == kTcMmaWarp) {
     // =========================================================== MMA issuer (lane 0 issues, the warp stays converged)
     const uint32_t idesc = tc::idesc_tf32(kTcTile, kTcChunk, 0, 0);
     const uint32_t aB = smem_u32(sB), aA = smem_u32(sA);
     uint32_t j = 0, it = 0;
+    KM_DECL;
+    KM_T(m_begin);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ab = it & 1u;
+      KM_T(m0);
       mbar_wait(&S->a_full[ab], (it >> 1) & 1u);
+      KM_T(m1);
+      KM_ACC(0, m0, m1);
       tc::fence_after_sync();
       if (lane == 0) tc::mbar_arrive(&S->thr_ready[it & 3u]);   // producers' thr[] -> epilogue warps
       const uint32_t a_base = aA + ab * (uint32_t)(kTcTile * KS * 4);
       for (int c = 0; c < n_chunks; ++c, ++j) {
         const uint32_t tb = j & 1u;
+        KM_T(m2);
         mbar_wait(&S->t_empty[tb], ((j >> 1) & 1u) ^ 1u);
+        KM_T(m3);
+        KM_ACC(1, m2, m3);
         tc::fence_after_sync();
-        if (lane == 0) {
-          const uint32_t b_base = aB + (uint32_t)c * (kTcChunk / 8) * sbo;
-          for (int s = 0; s < KS / 8; ++s) {
-            const uint64_t da = tc::smem_desc(a_base + (uint32_t)s * 2u * lbo, lbo, sbo, tc::kLayoutNone);
-            const uint64_t db = tc::smem_desc(b_base + (uint32_t)s * 2u * lbo, lbo, sbo, tc::kLayoutNone);
-            tc::mma_tf32(tmem + tb * kTcChunk, da, db, idesc, s > 0 ? 1u : 0u);
+        {
+          // descriptor of k-step s = base descriptor + (s * 2 * lbo >> 4) in the 14-bit address field
+          const uint64_t da0 = tc::smem_desc(a_base, lbo, sbo, tc::kLayoutNone);
+          const uint64_t db0 = tc::smem_desc(aB + (uint32_t)c * (kTcChunk / 8) * sbo, lbo, sbo, tc::kLayoutNone);
+          const uint32_t d_tmem = tmem + tb * kTcChunk;
+          const int nks = KS / 8;
+#pragma unroll 1
+          for (int s = 0; s < nks; ++s) {
+            const uint64_t step = (uint64_t)((uint32_t)s * ((2u * lbo) >> 4));
+            tc::mma_tf32_elect(d_tmem, da0 + step, db0 + step, idesc, s > 0 ? 1u : 0u);
           }
-          tc::mma_commit(&S->t_full[tb]);
+          tc::mma_commit_elect(&S->t_full[tb]);
         }
-        __syncwarp();
       }
-      if (lane == 0) tc::mma_commit(&S->a_empty[ab]);
-      __syncwarp();
+      tc::mma_commit_elect(&S->a_empty[ab]);
     }
+    KM_T(m_end);
+    KM_ACC(2, m_begin, m_end);
+#ifdef PMB_KM_PROF
+    km_prof[3] = (long long)it;
+#endif
+    KM_FLUSH(4, 4);
   } else if (warp < kTcMmaWarp + 1 + kTcProdWarps) {
     // =========================================================== producers: A tile + screening threshold
     const int pt = tid - (kTcMmaWarp + 1) * 32;   // 0..127: row of the tile
@@ -264,6 +312,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     };
     uint32_t it = 0;
     double ysq_acc = 0.0;
+    KM_DECL;
     if ((int64_t)blockIdx.x < n_tiles) prefetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ab = it & 1u;
@@ -273,75 +322,93 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
 #pragma unroll
       for (int d = 0; d < kTcDReg; ++d) y[d] = yn[d];
       const int hint = hint_n;
-      // distance to the hinted centre: its loads are issued before the (possibly long) wait below
+      if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+      // distance to the hinted centre from the resident centre operand: c32 = -(c'_hi + c'_lo) / 2 exactly
       float u = __int_as_float(0x7f800000);
       if (valid && hint >= 0 && hint < K) {
-        const double* c = p.centers + (size_t)hint * D;
         u = 0.f;
+        auto cget = [&](int d) {
+          const float hi = *reinterpret_cast<const float*>(sB + tc::off_kmajor(hint, 2 + 3 * d, lbo, sbo));
+          const float lo = *reinterpret_cast<const float*>(sB + tc::off_kmajor(hint, 2 + 3 * d + 2, lbo, sbo));
+          return -0.5f * (hi + lo);
+        };
         if constexpr (in_regs) {
-          double cc[kTcDReg];
-#pragma unroll
-          for (int d = 0; d < kTcDReg; ++d) cc[d] = (d < D) ? c[d] : 0.0;
 #pragma unroll
           for (int d = 0; d < kTcDReg; ++d) {
-            const float t = y[d] - (float)cc[d];
-            u = fmaf(t, t, u);
+            if (d < D) {
+              const float t = y[d] - cget(d);
+              u = fmaf(t, t, u);
+            }
           }
         } else {
 #pragma unroll 4
           for (int d = 0; d < D; ++d) {
-            const float t = p.Y[row * p.ld + d] - (float)c[d];
+            const float t = p.Y[row * p.ld + d] - cget(d);
             u = fmaf(t, t, u);
           }
         }
       }
-      if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+      KM_T(p0);
       mbar_wait(&S->a_empty[ab], ((it >> 1) & 1u) ^ 1u);
+      KM_T(p1);
+      KM_ACC(0, p0, p1);
       unsigned char* A = sA + (size_t)ab * kTcTile * KS * 4;
-      auto put = [&](int slot, float v) {
-        *reinterpret_cast<float*>(A + tc::off_kmajor(pt, slot, lbo, sbo)) = v;
-      };
       float xn2 = 0.f;
       if constexpr (in_regs) {
 #pragma unroll
         for (int d = 0; d < kTcDReg; ++d) {
-          if (d < D) {
-            const float v = y[d];
-            xn2 = fmaf(v, v, xn2);
-            ysq_acc = fma((double)v, (double)v, ysq_acc);
-            const float hi = tf32_rna(v);
-            put(3 * d + 0, hi);
-            put(3 * d + 1, tf32_rna(v - hi));
-            put(3 * d + 2, hi);
-          }
+          const float v = y[d];          // zero beyond D and for rows past the end
+          xn2 = fmaf(v, v, xn2);
+          ysq_acc = fma((double)v, (double)v, ysq_acc);
+        }
+        const float one = valid ? 1.0f : 0.0f;
+        // slot s: 0-1 -> 1, 2 + 3 d + r -> (r == 1 ? y_lo[d] : y_hi[d]); 16-byte stores, 8 lanes
+        // cover one 128-byte core-matrix row: conflict-free
+        auto slot_val = [&](int sl) -> float {
+          if (sl < 2) return one;
+          const int d = (sl - 2) / 3, r = (sl - 2) % 3;
+          if (d >= kTcDReg) return 0.f;
+          const float hi = tf32_rna(y[d]);   // recomputed per use: keeps the producer's register count low
+          return r == 1 ? tf32_rna(y[d] - hi) : hi;
+        };
+        unsigned char* arow = A + (uint32_t)(pt >> 3) * sbo + (uint32_t)(pt & 7) * 16u;
+#pragma unroll
+        for (int j = 0; j < (3 * kTcDReg + 2 + 7) / 8 * 2; ++j) {
+          if (4 * j < KS)
+            *reinterpret_cast<float4*>(arow + (uint32_t)j * lbo) =
+                make_float4(slot_val(4 * j), slot_val(4 * j + 1), slot_val(4 * j + 2), slot_val(4 * j + 3));
         }
       } else {
+        auto put = [&](int slot, float v) {
+          *reinterpret_cast<float*>(A + tc::off_kmajor(pt, slot, lbo, sbo)) = v;
+        };
 #pragma unroll 4
         for (int d = 0; d < D; ++d) {
           const float v = valid ? p.Y[row * p.ld + d] : 0.f;
           xn2 = fmaf(v, v, xn2);
           ysq_acc = fma((double)v, (double)v, ysq_acc);
           const float hi = tf32_rna(v);
-          put(3 * d + 0, hi);
-          put(3 * d + 1, tf32_rna(v - hi));
-          put(3 * d + 2, hi);
+          put(2 + 3 * d + 0, hi);
+          put(2 + 3 * d + 1, tf32_rna(v - hi));
+          put(2 + 3 * d + 2, hi);
         }
+        const float one = valid ? 1.0f : 0.0f;
+        put(0, one);
+        put(1, one);
+        for (int sl = 3 * D + 2; sl < KS; ++sl) put(sl, 0.f);
       }
-      const float one = valid ? 1.0f : 0.0f;
-      put(3 * D + 0, one);
-      put(3 * D + 1, one);
-      put(3 * D + 2, one);
-      const float x1 = tf32_rna(xn2);
-      put(3 * D + 3, x1);
-      put(3 * D + 4, tf32_rna(xn2 - x1));
-      for (int s = 3 * D + 5; s < KS; ++s) put(s, 0.f);
       // screening threshold: the fp32 distance to the hinted centre bounds the best score from above
-      // (up to the envelope E); the margin keeps the certainty test decidable
+      // (up to the envelope E); the margin keeps the certainty test decidable.  TMEM holds score - |y|^2, so the
+      // epilogue compares against thr - |y|^2 and adds |y|^2 back only on the rare slow path
       const float rr = sqrtf(xn2) * 1.0001f + cmax;
-      S->thr[it & 3u][pt] = u * (1.0f + 1.5258789e-5f) + 4.0f * kTcErrScale * rr * rr;
+      S->thr[it & 3u][pt] = (u * (1.0f + 1.5258789e-5f) + 4.0f * kTcErrScale * rr * rr) - xn2;
+      S->xn2[it & 3u][pt] = xn2;
       fence_proxy_async_smem();
       tc::mbar_arrive(&S->a_full[ab]);
+      KM_T(p2);
+      KM_ACC(1, p1, p2);
     }
+    if (warp == kTcMmaWarp + 1) { KM_FLUSH(8, 2); }
     if (p.accumulate) {
       ysq_acc = warp_sum(ysq_acc);
       if (lane == 0 && ysq_acc != 0.0) atomicAdd(p.ysq, ysq_acc);
@@ -352,6 +419,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     const int pt = tid - (kTcMmaWarp + 1 + kTcProdWarps) * 32;
     constexpr bool in_regs = INREG;
     int recheck_acc = 0;
+    KM_DECL;
     float yn[kTcDReg];
     auto prefetch = [&](int64_t tile) {
       const int64_t row = tile * kTcTile + pt;
@@ -366,7 +434,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       for (int d = 0; d < kTcDReg; ++d) y[d] = yn[d];
       if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
       const uint32_t rb = it & 1u;
+      KM_T(f0);
       mbar_wait(&S->r_full[rb], (it >> 1) & 1u);
+      KM_T(f1);
+      KM_ACC(0, f0, f1);
       int b = 0x7fffffff, s2 = 0x7fffffff, bc = 0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -418,13 +489,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
         if (__all_sync(0xffffffffu, lab == lab0)) {
           if (lab0 >= 0) {
             if constexpr (in_regs) {
+              // transpose through shared memory: lane (d, half) adds 16 rows of coordinate d in fp64
+              float* stg = &S->stage[warp - (kTcMmaWarp + 1 + kTcProdWarps)][0][0];
 #pragma unroll
-              for (int d = 0; d < kTcDReg; ++d) {
-                if (d < D) {
-                  const double v = warp_sum((double)y[d]);
-                  if (lane == 0) atomicAdd(p.lsums + (size_t)lab0 * D + d, v);
-                }
-              }
+              for (int d = 0; d < kTcDReg; ++d) stg[lane * (kTcDReg + 1) + d] = y[d];
+              __syncwarp();
+              const int dd = lane & 15, r0 = (lane >> 4) * 16;
+              double acc = 0.0;
+#pragma unroll
+              for (int r = 0; r < 16; ++r) acc += (double)stg[(r0 + r) * (kTcDReg + 1) + dd];
+              acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+              if (lane < D) atomicAdd(p.lsums + (size_t)lab0 * D + lane, acc);
+              __syncwarp();
             } else {
               for (int d = 0; d < D; ++d) {
                 const double v = warp_sum((double)p.Y[row * p.ld + d]);
@@ -444,7 +520,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
           atomicAdd(p.lcounts + lab, 1ull);
         }
       }
+      KM_T(f2);
+      KM_ACC(1, f1, f2);
     }
+    if (warp == kTcMmaWarp + 1 + kTcProdWarps) { KM_FLUSH(10, 2); }
     if (p.n_rechecked != nullptr) {
       int r = recheck_acc;
 #pragma unroll
@@ -525,7 +604,14 @@ __global__ void __launch_bounds__(256) kmeans_tc_commit_kernel(KmTcParams p) {
   }
 }
 
-static inline int tc_slots(int D) { return ((3 * D + 5) + 7) / 8 * 8; }
+int kmeans_tc_debug_counters(int64_t* out16) {
+  long long h[16];
+  PMB_CUDA(cudaMemcpyFromSymbol(h, g_km_dbg, sizeof(h)));
+  for (int i = 0; i < 16; ++i) out16[i] = h[i];
+  return PMB_OK;
+}
+
+static inline int tc_slots(int D) { return ((3 * D + 2) + 7) / 8 * 8; }
 static inline int tc_kpad(int K) { return (K + kTcChunk - 1) / kTcChunk * kTcChunk; }
 static inline size_t tc_smem_bytes(int D, int K) {
   return (size_t)tc_kpad(K) * tc_slots(D) * 4 + (size_t)2 * kTcTile * tc_slots(D) * 4 + sizeof(TcSmem) + 16;

@@ -378,6 +378,13 @@ int sym_eigvals_launch(double* A, int n, int batch, double* evals, double* scrat
 
 }  // namespace pmb
 
+namespace pmb { int tica_grid_debug_counters(int64_t* out8); }
+extern "C" int pmb_debug_counters_tica(int64_t* out8) {
+  using namespace pmb;
+  PMB_REQUIRE(out8 != nullptr, "pmb_debug_counters_tica: null pointer");
+  return tica_grid_debug_counters(out8);
+}
+
 extern "C" size_t pmb_tica_solve_ws_bytes(int d) {
   if (d <= 0) return 0;
   return ((size_t)5 * d * d + d) * sizeof(double) + (size_t)d * sizeof(int) + 64;
@@ -387,7 +394,7 @@ extern "C" int pmb_tica_solve(const double* C00, const double* C0t, int d, doubl
                               double* evecs, int32_t* rank, void* ws, size_t ws_bytes,
                               pmb_stream_t stream) {
   using namespace pmb;
-  PMB_REQUIRE(d > 0 && d <= 4096, "pmb_tica_solve: bad d=%d", d);
+  PMB_REQUIRE(d > 0 && d <= 1024, "pmb_tica_solve: bad d=%d (supported: 1..1024)", d);
   PMB_REQUIRE(C00 && C0t && evals && evecs && rank && ws, "pmb_tica_solve: null pointer");
   if (ws_bytes < pmb_tica_solve_ws_bytes(d)) {
     set_error("pmb_tica_solve: workspace too small");

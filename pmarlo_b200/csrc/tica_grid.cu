@@ -25,6 +25,9 @@ struct TicaGridWs {
 
 __device__ __forceinline__ double ldg_cg(const double* p) { return __ldcg(p); }
 
+// phase cycle counters of the last solve (CTA 0, thread 0): load, local sweep, store, grid barrier, total, block rounds
+__device__ long long g_tg_dbg[8];
+
 // 1/sqrt(x) and 1/x for x in [2^-8, 2^8]: fp32 seed (MUFU) + two fp64 Newton steps.  The IEEE fp64
 // divide / sqrt sequences cost ~300 dependent cycles each, and the rotation angle sits on the critical
 // path of every Jacobi round; these are ~100 cycles and accurate to a few ulp.
@@ -73,6 +76,9 @@ __device__ __forceinline__ void tg_rotation(double a, double b, double g, double
 // cyclic sweep over those 2b rows there (2b - 1 local rounds separated by __syncthreads, one warp
 // per row pair) and writes them back.  A sweep therefore costs nb - 1 grid barriers instead of
 // n - 1, and every rotation works on shared memory instead of L2.
+// NPL = elements of a row per lane (n <= 32 NPL): the loops are fully unrolled, a warp holds its two
+// rows of W and V in registers for the duration of a rotation and the global loads are batched.
+template <int NPL>
 __device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, int b, int* flags, double* sm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   int nb = (n + b - 1) / b;
@@ -85,9 +91,11 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, in
   if (blockIdx.x == 0 && threadIdx.x == 0) { flags[0] = 0; flags[1] = 0; }
   grid.sync();
   int sweep = 0;
+  long long cyc[4] = {0, 0, 0, 0}, n_rounds = 0;
   for (; sweep < kTgMaxSweeps; ++sweep) {
     int rotated = 0;
     for (int r = 0; r < nb - 1; ++r) {
+      long long t0 = clock64();
       for (int k = blockIdx.x; k < npairs; k += gridDim.x) {
         int bi, bj;
         if (k == 0) { bi = nb - 1; bj = r; }
@@ -96,13 +104,27 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, in
         auto grow = [&](int li) { return li < b ? bi * b + li : bj * b + (li - b); };
         for (int li = warp; li < rows; li += nwarps) {
           const int gr = grow(li);
-          if (gr < n)
-            for (int e = lane; e < n; e += 32) {
-              sW[(size_t)li * n + e] = ldg_cg(W + (size_t)gr * n + e);
-              if (V != nullptr) sV[(size_t)li * n + e] = ldg_cg(V + (size_t)gr * n + e);
+          if (gr < n) {
+            double tw[NPL], tv[NPL];
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+              const int e = lane + 32 * q;
+              tw[q] = e < n ? ldg_cg(W + (size_t)gr * n + e) : 0.0;
+              tv[q] = (V != nullptr && e < n) ? ldg_cg(V + (size_t)gr * n + e) : 0.0;
             }
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+              const int e = lane + 32 * q;
+              if (e < n) {
+                sW[(size_t)li * n + e] = tw[q];
+                if (V != nullptr) sV[(size_t)li * n + e] = tv[q];
+              }
+            }
+          }
         }
         __syncthreads();
+        const long long t1 = clock64();
+        cyc[0] += t1 - t0;
         const int lm = rows - 1;   // local tournament over `rows` players (rows is even)
         for (int lr = 0; lr < lm; ++lr) {
           for (int kk = warp; kk < b; kk += nwarps) {
@@ -114,12 +136,19 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, in
             if (gp > gq) { const int t = lp; lp = lq; lq = t; }
             double* wp = sW + (size_t)lp * n;
             double* wq = sW + (size_t)lq * n;
+            double x[NPL], y[NPL];
             double a = 0.0, bb = 0.0, g = 0.0;
-            for (int e = lane; e < n; e += 32) {
-              const double x = wp[e], y = wq[e];
-              a = fma(x, x, a);
-              bb = fma(y, y, bb);
-              g = fma(x, y, g);
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+              const int e = lane + 32 * q;
+              x[q] = e < n ? wp[e] : 0.0;
+              y[q] = e < n ? wq[e] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+              a = fma(x[q], x[q], a);
+              bb = fma(y[q], y[q], bb);
+              g = fma(x[q], y[q], g);
             }
             a = warp_sum(a);
             bb = warp_sum(bb);
@@ -128,34 +157,62 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, in
             rotated = 1;
             double c, s;
             tg_rotation(a, bb, g, c, s);
-            for (int e = lane; e < n; e += 32) {
-              const double x = wp[e], y = wq[e];
-              wp[e] = c * x - s * y;
-              wq[e] = s * x + c * y;
+            // de Rijk's ordering: the row with the larger norm goes first (rotation followed by a swap when
+            // a < b); helps on graded matrices such as a covariance with eigenvalues over 8 decades.
+            const bool sw = a < bb;
+            const double c0 = sw ? s : c, s0 = sw ? c : -s;    // row p <- c0 x + s0 y
+            const double c1 = sw ? c : s, s1 = sw ? -s : c;    // row q <- c1 x + s1 y
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+              const int e = lane + 32 * q;
+              if (e < n) {
+                wp[e] = c0 * x[q] + s0 * y[q];
+                wq[e] = c1 * x[q] + s1 * y[q];
+              }
             }
             if (V != nullptr) {
               double* vp = sV + (size_t)lp * n;
               double* vq = sV + (size_t)lq * n;
-              for (int e = lane; e < n; e += 32) {
-                const double x = vp[e], y = vq[e];
-                vp[e] = c * x - s * y;
-                vq[e] = s * x + c * y;
+#pragma unroll
+              for (int q = 0; q < NPL; ++q) {
+                const int e = lane + 32 * q;
+                x[q] = e < n ? vp[e] : 0.0;
+                y[q] = e < n ? vq[e] : 0.0;
+              }
+#pragma unroll
+              for (int q = 0; q < NPL; ++q) {
+                const int e = lane + 32 * q;
+                if (e < n) {
+                  vp[e] = c0 * x[q] + s0 * y[q];
+                  vq[e] = c1 * x[q] + s1 * y[q];
+                }
               }
             }
           }
           __syncthreads();
         }
+        const long long t2 = clock64();
+        cyc[1] += t2 - t1;
         for (int li = warp; li < rows; li += nwarps) {
           const int gr = grow(li);
-          if (gr < n)
-            for (int e = lane; e < n; e += 32) {
-              __stcg(W + (size_t)gr * n + e, sW[(size_t)li * n + e]);
-              if (V != nullptr) __stcg(V + (size_t)gr * n + e, sV[(size_t)li * n + e]);
+          if (gr < n) {
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+              const int e = lane + 32 * q;
+              if (e < n) {
+                __stcg(W + (size_t)gr * n + e, sW[(size_t)li * n + e]);
+                if (V != nullptr) __stcg(V + (size_t)gr * n + e, sV[(size_t)li * n + e]);
+              }
             }
+          }
         }
         __syncthreads();
+        t0 = clock64();
+        cyc[2] += t0 - t2;
       }
       grid.sync();
+      cyc[3] += clock64() - t0;
+      ++n_rounds;
     }
     if (rotated && lane == 0) atomicOr(&flags[sweep & 1], 1);
     grid.sync();
@@ -163,6 +220,12 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, in
     if (blockIdx.x == 0 && threadIdx.x == 0) flags[(sweep + 1) & 1] = 0;
     grid.sync();
     if (!any) { ++sweep; break; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int base = (V != nullptr && g_tg_dbg[7] == 1) ? 0 : 0;
+    (void)base;
+    for (int q = 0; q < 4; ++q) g_tg_dbg[q] += cyc[q];
+    g_tg_dbg[4] += n_rounds;
   }
   return sweep;
 }
@@ -183,12 +246,16 @@ __device__ void rank_grid(cg::grid_group& grid, const double* vals, int n, int* 
   grid.sync();
 }
 
+template <int NPL>
 __global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
     const double* __restrict__ C00, const double* __restrict__ C0t, int d, double eps,
     double* __restrict__ evals, double* __restrict__ evecs, int32_t* __restrict__ rank_out, TicaGridWs ws,
     int blk) {
   extern __shared__ __align__(16) double tg_sm[];
   cg::grid_group grid = cg::this_grid();
+  const long long t_begin = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int q = 0; q < 8; ++q) g_tg_dbg[q] = 0;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gnt = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31, gwarp = gtid >> 5, nwarps = gnt >> 5;
   const size_t dd = (size_t)d * d;
@@ -197,15 +264,66 @@ __global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
   for (size_t i = gtid; i < dd; i += gnt) {
     const int r = (int)(i / d), c = (int)(i - (size_t)r * d);
     ws.W[i] = 0.5 * (C00[i] + C00[(size_t)c * d + r]);
-    ws.V[i] = (r == c) ? 1.0 : 0.0;
   }
   grid.sync();
-  const int sweeps1 = jacobi_grid(grid, ws.W, ws.V, d, blk, ws.ctrl + 1, tg_sm);
-  for (int j = gwarp; j < d; j += nwarps) {   // Rayleigh quotients v_j . w_j
+  // Rotations are NOT accumulated: at convergence row j of W is lambda_j v_j^T, so v_j = w_j / |w_j| and the
+  // signed eigenvalue is the Rayleigh quotient v_j^T C00 v_j.  (Rows whose norm is at rounding level carry no
+  // direction; they get eigenvalue 0 and are removed by the rank cut.)  This halves the shared-memory
+  // traffic that bounds a local Jacobi round.
+  const int sweeps1 = jacobi_grid<NPL>(grid, ws.W, nullptr, d, blk, ws.ctrl + 1, tg_sm);
+  for (int j = gwarp; j < d; j += nwarps) {
     double acc = 0.0;
-    for (int e = lane; e < d; e += 32) acc = fma(ldg_cg(ws.V + (size_t)j * d + e), ldg_cg(ws.W + (size_t)j * d + e), acc);
+    for (int e = lane; e < d; e += 32) { const double w = ldg_cg(ws.W + (size_t)j * d + e); acc = fma(w, w, acc); }
     acc = warp_sum(acc);
-    if (lane == 0) ws.s[j] = acc;
+    if (lane == 0) ws.s[j] = sqrt(acc);
+  }
+  grid.sync();
+  {
+    double mx = 0.0;
+    for (int j = lane; j < d; j += 32) mx = fmax(mx, ldg_cg(ws.s + j));
+    mx = warp_max(mx);
+    const double floor_norm = 16.0 * 2.220446049250313e-16 * (double)d * mx;
+    grid.sync();   // every warp has read the norms before they are replaced by eigenvalues
+    for (int j = gwarp; j < d; j += nwarps) {
+      double nrm2 = 0.0;
+      double v[NPL];
+#pragma unroll
+      for (int q = 0; q < NPL; ++q) {
+        const int e = lane + 32 * q;
+        v[q] = e < d ? ldg_cg(ws.W + (size_t)j * d + e) : 0.0;
+        nrm2 = fma(v[q], v[q], nrm2);
+      }
+      const double nrm = sqrt(warp_sum(nrm2));
+      const bool live = nrm > floor_norm && nrm > 0.0;
+      const double inv = live ? 1.0 / nrm : 0.0;
+#pragma unroll
+      for (int q = 0; q < NPL; ++q) {
+        const int e = lane + 32 * q;
+        v[q] *= inv;
+        if (e < d) ws.V[(size_t)j * d + e] = v[q];
+      }
+      double acc = 0.0;
+      if (live) {
+#pragma unroll
+        for (int q2 = 0; q2 < NPL; ++q2) {
+          for (int l = 0; l < 32; ++l) {
+            const int i = l + 32 * q2;
+            const double vi = __shfl_sync(0xffffffffu, v[q2], l);
+            if (i >= d) continue;
+            const double* row = C00 + (size_t)i * d;
+            double part = 0.0;
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+              const int e = lane + 32 * q;
+              if (e < d) part = fma(row[e], v[q], part);
+            }
+            acc = fma(vi, part, acc);
+          }
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) ws.s[j] = acc;
+    }
   }
   grid.sync();
   rank_grid(grid, ws.s, d, ws.order);
@@ -285,15 +403,17 @@ __global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
   for (size_t i = gtid; i < (size_t)m * m; i += gnt) {
     const int r = (int)(i / m), c = (int)(i - (size_t)r * m);
     ws.W[i] = 0.5 * (ldg_cg(ws.M + i) + ldg_cg(ws.M + (size_t)c * m + r)) + ((r == c) ? sigma : 0.0);
-    ws.V[i] = (r == c) ? 1.0 : 0.0;
   }
   grid.sync();
-  const int sweeps2 = jacobi_grid(grid, ws.W, ws.V, m, blk, ws.ctrl + 1, tg_sm);
+  // W = sym(M) + sigma I is positive definite: eigenvalue_j = |w_j| - sigma, v_j = w_j / |w_j|
+  const int sweeps2 = jacobi_grid<NPL>(grid, ws.W, nullptr, m, blk, ws.ctrl + 1, tg_sm);
   for (int j = gwarp; j < m; j += nwarps) {
     double acc = 0.0;
-    for (int e = lane; e < m; e += 32) acc = fma(ldg_cg(ws.V + (size_t)j * m + e), ldg_cg(ws.W + (size_t)j * m + e), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) ws.s[j] = acc - sigma;
+    for (int e = lane; e < m; e += 32) { const double w = ldg_cg(ws.W + (size_t)j * m + e); acc = fma(w, w, acc); }
+    const double nrm = sqrt(warp_sum(acc));
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    for (int e = lane; e < m; e += 32) ws.V[(size_t)j * m + e] = ldg_cg(ws.W + (size_t)j * m + e) * inv;
+    if (lane == 0) ws.s[j] = nrm - sigma;
   }
   grid.sync();
   rank_grid(grid, ws.s, m, ws.order);
@@ -326,7 +446,14 @@ __global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
     if (lane == 0) evals[k] = ldg_cg(ws.s + __ldcg(ws.order + k));
   }
   for (int k = m + gtid; k < d; k += gnt) evals[k] = 0.0;
-  if (gtid == 0) { rank_out[0] = m; rank_out[1] = sweeps1; rank_out[2] = sweeps2; }
+  if (gtid == 0) { rank_out[0] = m; rank_out[1] = sweeps1; rank_out[2] = sweeps2; g_tg_dbg[5] = clock64() - t_begin; }
+}
+
+int tica_grid_debug_counters(int64_t* out8) {
+  long long h[8];
+  PMB_CUDA(cudaMemcpyFromSymbol(h, g_tg_dbg, sizeof(h)));
+  for (int i = 0; i < 8; ++i) out8[i] = h[i];
+  return PMB_OK;
 }
 
 int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double eps, double* evals, double* evecs,
@@ -346,8 +473,18 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   while (blk > 1 && (size_t)4 * blk * d * sizeof(double) > (size_t)200 * 1024) blk >>= 1;
   const size_t smem = (size_t)4 * blk * d * sizeof(double);
   PMB_REQUIRE(smem <= (size_t)227 * 1024, "pmb_tica_solve: d=%d too large for the block-Jacobi kernel", d);
-  PMB_CUDA(cudaFuncSetAttribute(tica_solve_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tica_solve_grid_kernel, kTgThreads, smem));
+  void* kern = nullptr;
+  if (d <= 64) kern = (void*)tica_solve_grid_kernel<2>;
+  else if (d <= 128) kern = (void*)tica_solve_grid_kernel<4>;
+  else if (d <= 256) kern = (void*)tica_solve_grid_kernel<8>;
+  else if (d <= 512) kern = (void*)tica_solve_grid_kernel<16>;
+  else if (d <= 1024) kern = (void*)tica_solve_grid_kernel<32>;
+  else {
+    set_error("pmb_tica_solve: d=%d > 1024 is not supported by the block-Jacobi kernel", d);
+    return PMB_EUNSUPPORTED;
+  }
+  PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTgThreads, smem));
   PMB_REQUIRE(per_sm >= 1, "pmb_tica_solve: kernel does not fit on an SM");
   int nb = (d + blk - 1) / blk;
   if (nb & 1) ++nb;
@@ -356,7 +493,7 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   if (grid < 1) grid = 1;
   void* args[] = {(void*)&C00, (void*)&C0t, (void*)&d, (void*)&eps, (void*)&evals, (void*)&evecs, (void*)&rank, (void*)&w,
                   (void*)&blk};
-  PMB_CUDA(cudaLaunchCooperativeKernel((void*)tica_solve_grid_kernel, dim3(grid), dim3(kTgThreads), args, smem, st));
+  PMB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kTgThreads), args, smem, st));
   count_launch();
   return PMB_OK;
 }

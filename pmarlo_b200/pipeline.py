@@ -82,7 +82,8 @@ def seeded_initial_centers(Y: torch.Tensor, K: int, seed: int, comm: Comm) -> to
 def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | None, cfg: PipelineConfig,
                  comm: Comm | None = None, features: torch.Tensor | None = None,
                  initial_centers: torch.Tensor | None = None, timer: StageTimer | None = None,
-                 read_back: bool = True, buffers: dict | None = None) -> PipelineResult:
+                 read_back: bool = True, buffers: dict | None = None,
+                 tica_model: TicaModel | None = None) -> PipelineResult:
     """Run the whole path on this rank's shard.  Either ``xyz`` (+ ``plan``) or
     precomputed ``features`` (N,d) float32 must be given; with ``cfg.tica_dim <= 0``
     the features are clustered directly (config C2: 2-D Mueller-Brown data).
@@ -108,11 +109,11 @@ def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | N
             features = featurize_device(xyz, plan, out=out)
     X = features
 
-    tica_model = None
     if cfg.tica_dim > 0:
-        with timer.stage("tica_fit"):
-            est = TICA(cfg.tica_lag, cfg.tica_dim, preprocess=cfg.preprocess, comm=comm, gram_impl=cfg.gram_impl)
-            tica_model = est.fit_device(X, segs, off, timer=timer)
+        est = TICA(cfg.tica_lag, cfg.tica_dim, preprocess=cfg.preprocess, comm=comm, gram_impl=cfg.gram_impl)
+        if tica_model is None:
+            with timer.stage("tica_fit"):
+                tica_model = est.fit_device(X, segs, off, timer=timer)
         with timer.stage("project"):
             Y = est.transform_device(tica_model, X, out_f64=False,
                                      out=_buf("Y", (int(X.shape[0]), tica_model.dim), torch.float32))
@@ -152,26 +153,65 @@ def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | N
 
 
 def estimate_msm_from_host(xyz_host, lengths, plan: FeaturePlan, cfg: PipelineConfig, comm: Comm | None = None,
-                           device=None, buffers: dict | None = None) -> dict:
+                           device=None, buffers: dict | None = None, chunk_frames: int = 1_000_000) -> dict:
     """The call a user of the host-buffer API makes: coordinates of this rank's
     trajectories in (pinned) host memory -> timescales, eigenvalues, stationary
     vector and MLE diagnostics as numpy arrays.  The host->device copy of the
     coordinates and the device->host read of the results happen inside."""
     device = device if device is not None else kernels.require_cuda()
+    comm = comm if comm is not None else Comm()
     if isinstance(xyz_host, np.ndarray):
         xyz_host = torch.from_numpy(np.ascontiguousarray(xyz_host, dtype=np.float32))
-    if buffers is not None:
-        xyz = buffers.get("xyz")
-        if xyz is None or tuple(xyz.shape) != tuple(xyz_host.shape) or xyz.device != device:
-            xyz = torch.empty(tuple(xyz_host.shape), dtype=torch.float32, device=device)
-            buffers["xyz"] = xyz
-        xyz.copy_(xyz_host, non_blocking=True)
-    else:
-        xyz = xyz_host.to(device, non_blocking=True)
     segs = Segments.from_lengths(lengths)
-    if segs.n_frames != int(xyz.shape[0]):
+    n = segs.n_frames
+    if n != int(xyz_host.shape[0]):
         raise ValueError("lengths do not add up to the number of frames")
-    res = run_pipeline(xyz, segs, plan, cfg, comm, read_back=False, buffers=buffers)
+    bufs = buffers if buffers is not None else {}
+
+    def _buf(name, shape, dtype):
+        t = bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            bufs[name] = t
+        return t
+
+    xyz = _buf("xyz", tuple(xyz_host.shape), torch.float32)
+    X = _buf("features", (n, plan.n_cols), torch.float32)
+    # chunks of whole trajectories, about chunk_frames each: the copy of chunk c+1 (side stream) overlaps
+    # featurization and the moment / Gram accumulation of chunk c (compute stream)
+    bounds = [0]
+    for end in segs.offsets[1:]:
+        if int(end) - bounds[-1] >= chunk_frames:
+            bounds.append(int(end))
+    if bounds[-1] != n:
+        bounds.append(n)
+    main = torch.cuda.current_stream(device)
+    copy_stream = bufs.get("copy_stream")
+    if copy_stream is None:
+        copy_stream = torch.cuda.Stream(device=device)
+        bufs["copy_stream"] = copy_stream
+    copy_stream.wait_stream(main)          # the previous call may still be reading xyz
+    events = []
+    with torch.cuda.stream(copy_stream):
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            xyz[a:b].copy_(xyz_host[a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            events.append(ev)
+    streaming = cfg.tica_dim > 0
+    acc = None
+    if streaming:
+        est = TICA(cfg.tica_lag, cfg.tica_dim, preprocess=cfg.preprocess, comm=comm, gram_impl=cfg.gram_impl)
+        acc = est.accumulator(plan.n_cols, device)
+    offs = segs.offsets
+    for (a, b), ev in zip(zip(bounds[:-1], bounds[1:]), events):
+        main.wait_event(ev)
+        featurize_device(xyz[a:b], plan, out=X[a:b])
+        if acc is not None:
+            lo, hi = int(np.searchsorted(offs, a)), int(np.searchsorted(offs, b))
+            acc.add(X[a:b], Segments(offs[lo:hi + 1] - a))
+    model = acc.finish() if acc is not None else None
+    res = run_pipeline(None, segs, plan, cfg, comm, features=X, read_back=False, buffers=buffers, tica_model=model)
     ev = res.eigenvalues.cpu().numpy()
     pi = res.pi.cpu().numpy()
     info = res.mle_info.cpu().numpy()

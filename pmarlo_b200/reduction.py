@@ -33,7 +33,7 @@ from .timing import NULL_TIMER
 
 logger = logging.getLogger("pmarlo")
 
-__all__ = ["TicaModel", "TICA", "tica_reduce", "reduce_features", "maybe_apply_tica", "train_cv_model",
+__all__ = ["TicaModel", "TICA", "TicaAccumulator", "tica_reduce", "reduce_features", "maybe_apply_tica", "train_cv_model",
            "preprocess"]
 
 
@@ -123,6 +123,11 @@ class TICA:
         return TicaModel(lag, dim, n, n_pairs, moments, stats, C00, C0t, mu, evals, evecs, rank, a,
                          nanfill, W)
 
+    def accumulator(self, d: int, device) -> "TicaAccumulator":
+        """Streaming fit: feed whole-trajectory chunks with ``add`` while later chunks are still being
+        copied or featurized, then ``finish``."""
+        return TicaAccumulator(self, d, device)
+
     @staticmethod
     def transform_device(model: TicaModel, X: torch.Tensor, out_f64: bool = False,
                          out: torch.Tensor | None = None) -> torch.Tensor:
@@ -140,6 +145,108 @@ class TICA:
         model = self.fit_device(X, segs)
         Y = self.transform_device(model, X, out_f64=True)[:, : model.output_dim]
         return segs.split(Y.cpu().numpy()), model
+
+
+class TicaAccumulator:
+    """Chunk-wise TICA fit (same result as :meth:`TICA.fit_device` up to fp64 summation order).
+
+    The column moments and the two Gram matrices are sums over frames, so they can be accumulated
+    chunk by chunk (chunks = whole trajectories: lagged pairs never cross a chunk) while the next chunk
+    is still in flight from the host.  The fp32 conditioning (shift, scale) of the Gram kernel only
+    serves numerics and is undone exactly by ``pmb_tica_covariances``, so it is taken from the FIRST
+    chunk (rank 0's, broadcast) instead of the global statistics.  Two cases fall back to a second pass
+    over the resident features with the global conditioning: NaNs (the kernel imputes at the conditioning
+    shift) and a first chunk whose statistics are far from the global ones.
+    """
+
+    def __init__(self, est: TICA, d: int, device):
+        self.est, self.d, self.device = est, int(d), device
+        self.moments = None
+        self.shift = None
+        self.cond = None
+        self.G = torch.zeros((2, self.d, self.d), dtype=torch.float64, device=device)
+        self._tmp = torch.empty((self.d, self.d), dtype=torch.float64, device=device)
+        self.n_local = 0
+        self.n_pairs_local = 0
+        self.chunks: list[tuple[torch.Tensor, torch.Tensor]] = []   # (X view, mask) for a possible second pass
+
+    def _start(self, X: torch.Tensor) -> None:
+        comm = self.est.comm
+        self.shift = torch.nan_to_num(X[0].to(torch.float64), nan=0.0).contiguous()
+        if comm.size > 1:
+            comm.broadcast(self.shift, src=0)
+
+    def add(self, X: torch.Tensor, segs: Segments, timer=NULL_TIMER) -> None:
+        est, comm, lag = self.est, self.est.comm, self.est.lagtime
+        if self.shift is None:
+            self._start(X)
+        n = int(X.shape[0])
+        mask = kernels.pair_mask(segs.device(self.device), n, lag)
+        with timer.stage("col_moments"):
+            mom = kernels.col_moments(X, mask, self.shift)
+        if self.moments is None:
+            self.moments = mom
+            semantic = 0 if est.preprocess is None else 1
+            _, self.cond = kernels.scaler_from_moments(mom, n, semantic, 1 if est.preprocess == "standard" else 0)
+            if comm.size > 1:
+                comm.broadcast(self.cond, src=0)
+        else:
+            self.moments[0] += mom[0]
+            self.moments[2:] += mom[2:]
+        with timer.stage("gram"):
+            kernels.gram(X, mask, lag, 0, self.cond, est.gram_impl, out=self._tmp)
+            self.G[0] += self._tmp
+            kernels.gram(X, mask, lag, 1, self.cond, est.gram_impl, out=self._tmp)
+            self.G[1] += self._tmp
+        self.n_local += n
+        self.n_pairs_local += segs.n_pairs(lag)
+        self.chunks.append((X, mask))
+
+    def finish(self, timer=NULL_TIMER) -> TicaModel:
+        est, comm, lag, d, dev = self.est, self.est.comm, self.est.lagtime, self.d, self.device
+        if self.moments is None:
+            raise ValueError("no frames given")
+        n = comm.sum_int(self.n_local, dev)
+        n_pairs = comm.sum_int(self.n_pairs_local, dev)
+        if n_pairs <= 0:
+            raise ValueError("no trajectory longer than the lag time")
+        moments, G = self.moments, self.G
+        if comm.size > 1:
+            comm.allreduce_sum(moments)
+            moments[1].copy_(self.shift)
+            comm.allreduce_sum(G)
+        semantic = 0 if est.preprocess is None else 1
+        with_std = 1 if est.preprocess == "standard" else 0
+        stats, cond_global = kernels.scaler_from_moments(moments, n, semantic, with_std)
+        # is the first chunk's conditioning good enough?  |z| must stay O(1): scales within 4x, means within
+        # 4 sigma, and no NaNs (one device->host read of three booleans)
+        ratio = self.cond[1].to(torch.float64) / cond_global[1].to(torch.float64)
+        drift = (self.cond[0].to(torch.float64) - cond_global[0].to(torch.float64)).abs() * cond_global[1].to(torch.float64)
+        ok = torch.stack([(ratio.max() <= 4.0) & (ratio.min() >= 0.25), drift.max() <= 4.0,
+                          (moments[0] == float(n)).all()]).all()
+        cond = self.cond
+        self.fell_back = not bool(ok.item())
+        if self.fell_back:
+            cond = cond_global
+            G.zero_()
+            for X, mask in self.chunks:
+                with timer.stage("gram"):
+                    kernels.gram(X, mask, lag, 0, cond, est.gram_impl, out=self._tmp)
+                    G[0] += self._tmp
+                    kernels.gram(X, mask, lag, 1, cond, est.gram_impl, out=self._tmp)
+                    G[1] += self._tmp
+            if comm.size > 1:
+                comm.allreduce_sum(G)
+        self.chunks = []
+        C00, C0t, mu = kernels.tica_covariances(G[0], G[1], moments, stats, cond, n, n_pairs, semantic)
+        with timer.stage("tica_solve"):
+            evals, evecs, rank = kernels.tica_solve(C00, C0t, est.epsilon)
+        dim = d if est.dim is None else int(est.dim)
+        dim = max(1, min(dim, d))
+        a, nanfill, W = kernels.tica_finalize(evals, evecs, moments, stats, mu, dim,
+                                              est.scaling in ("kinetic_map", "km"))
+        return TicaModel(lag, dim, n, n_pairs, moments, stats, C00, C0t, mu, evals, evecs, rank, a,
+                         nanfill, W)
 
 
 def _as_2d(X) -> tuple[np.ndarray, bool]:
