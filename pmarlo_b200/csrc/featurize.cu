@@ -13,7 +13,8 @@
 
 namespace pmb {
 
-constexpr int kFeatThreads = 256;
+constexpr int kFeatThreads = 256;   // default; the launch picks a multiple of n_units (see pmb_featurize)
+constexpr int kFeatMaxThreads = 512;
 
 struct FeatParams {
   const float* xyz;
@@ -29,8 +30,11 @@ struct FeatParams {
   int bulk_out_ok;   // out base 16B aligned and ld_out == n_cols
 };
 
-__device__ __forceinline__ void feat_unit(const float* __restrict__ fr, const int32_t* __restrict__ u,
+struct FeatUnit { int32_t v[8]; };   // kind, 4 atoms, angle / cos / sin (or distance) output columns
+
+__device__ __forceinline__ void feat_unit(const float* __restrict__ fr, const FeatUnit uu,
                                           float* __restrict__ orow) {
+  const int32_t* u = uu.v;
   const int kind = u[0];
   const float* p0 = fr + 3 * u[1];
   const float* p1 = fr + 3 * u[2];
@@ -69,7 +73,7 @@ __device__ __forceinline__ void feat_unit(const float* __restrict__ fr, const in
   }
 }
 
-__global__ void __launch_bounds__(kFeatThreads, 2) featurize_kernel(FeatParams p) {
+__global__ void __launch_bounds__(kFeatMaxThreads) featurize_kernel(FeatParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x;
   const int A3 = p.n_atoms * 3;
@@ -82,7 +86,8 @@ __global__ void __launch_bounds__(kFeatThreads, 2) featurize_kernel(FeatParams p
   const size_t otile_bytes = ((size_t)p.ft * p.n_cols * 4 + 127) & ~(size_t)127;
   int32_t* s_units = reinterpret_cast<int32_t*>(smem + 128 + 2 * stage_stride + otile_bytes);
 
-  for (int i = tid; i < p.n_units * 8; i += kFeatThreads) s_units[i] = p.units[i];
+  const int nthreads = blockDim.x;
+  for (int i = tid; i < p.n_units * 8; i += nthreads) s_units[i] = p.units[i];
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -119,18 +124,34 @@ __global__ void __launch_bounds__(kFeatThreads, 2) featurize_kernel(FeatParams p
       else            { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
     } else {
       const float* src = p.xyz + f0 * A3;
-      for (int i = tid; i < nf * A3; i += kFeatThreads) in_cur[i] = ldg_stream_f(src + i);
+      for (int i = tid; i < nf * A3; i += nthreads) in_cur[i] = ldg_stream_f(src + i);
       __syncthreads();
     }
     // the previous tile's bulk store must have finished reading otile
     if (tid == 0) bulk_wait_read<0>();
     __syncthreads();
 
-    const int work = nf * p.n_units;
-    for (int w = tid; w < work; w += kFeatThreads) {
-      const int f = w / p.n_units;
-      const int u = w - f * p.n_units;
-      feat_unit(in_cur + f * A3, s_units + u * 8, otile + f * p.n_cols);
+    if (p.n_units <= nthreads) {
+      // a thread owns ONE unit (decoded once per tile into registers) and walks the tile's frames with
+      // stride fl_n: no per-item division, no per-item unit decode
+      const int fl_n = nthreads / p.n_units;
+      const int fl = tid / p.n_units;
+      if (fl < fl_n) {
+        FeatUnit u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u.v[q] = s_units[(tid - fl * p.n_units) * 8 + q];
+        for (int f = fl; f < nf; f += fl_n) feat_unit(in_cur + f * A3, u, otile + f * p.n_cols);
+      }
+    } else {
+      const int work = nf * p.n_units;
+      for (int w = tid; w < work; w += nthreads) {
+        const int f = w / p.n_units;
+        const int u = w - f * p.n_units;
+        FeatUnit uu;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) uu.v[q] = s_units[u * 8 + q];
+        feat_unit(in_cur + f * A3, uu, otile + f * p.n_cols);
+      }
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -142,7 +163,7 @@ __global__ void __launch_bounds__(kFeatThreads, 2) featurize_kernel(FeatParams p
         bulk_commit();
       }
     } else {
-      for (int i = tid; i < nf * p.n_cols; i += kFeatThreads) {
+      for (int i = tid; i < nf * p.n_cols; i += nthreads) {
         const int f = i / p.n_cols;
         const int c = i - f * p.n_cols;
         p.out[(f0 + f) * p.ld_out + c] = otile[i];
@@ -222,7 +243,15 @@ extern "C" int pmb_featurize(const float* xyz, int64_t n_frames, int n_atoms, co
   PMB_CUDA(cudaFuncSetAttribute(featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (n_frames + ft - 1) / ft;
   int grid = (int)(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
-  featurize_kernel<<<grid, kFeatThreads, smem, as_stream(stream)>>>(p);
+  // block size: the largest multiple of n_units that fits 384 threads (all threads own a unit), rounded up
+  // to a whole warp; unit lists longer than that use the generic item loop
+  int threads = kFeatThreads;
+  if (n_units <= 384) {
+    threads = (384 / n_units) * n_units;
+    threads = ((threads + 31) / 32) * 32;
+    if (threads < 128) threads = 128;
+  }
+  featurize_kernel<<<grid, threads, smem, as_stream(stream)>>>(p);
   PMB_LAUNCH_CHECK();
   return PMB_OK;
 }

@@ -70,6 +70,85 @@ __global__ void __launch_bounds__(kMomThreads) col_moments_kernel(
   }
 }
 
+// float4 path (d % 4 == 0, 16-byte aligned rows): a thread owns FOUR adjacent columns, so a frame costs
+// one 16-byte load per thread instead of four 4-byte ones and the mask byte is shared by four columns;
+// counts are integers and the edge sums are only touched on the (rare) edge frames.
+constexpr int kMomU = 4;   // rows in flight per thread
+
+__global__ void __launch_bounds__(kMomThreads, 3) col_moments_v4_kernel(
+    const float* __restrict__ X, int64_t n, int d, int64_t ld, const uint8_t* __restrict__ mask,
+    const double* __restrict__ shift_in, int cw, double* __restrict__ part /* [grid.x][5][cw] */) {
+  extern __shared__ double red[];   // [rpp][5][d]
+  const int tid = threadIdx.x;
+  const int tpr = d >> 2;                 // threads per row
+  const int rpp = kMomThreads / tpr;      // rows per pass
+  const int r = tid / tpr, cg = tid - r * tpr, c = cg * 4;
+  const bool active = r < rpp;
+  double shift[4] = {0.0, 0.0, 0.0, 0.0};
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (shift_in != nullptr) {
+        shift[q] = shift_in[c + q];
+      } else {
+        const float x0 = X[c + q];
+        shift[q] = (x0 == x0) ? (double)x0 : 0.0;
+      }
+    }
+  }
+  int cnt[4] = {0, 0, 0, 0}, ecnt[4] = {0, 0, 0, 0};
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, es1[4] = {0, 0, 0, 0};
+  const int64_t stride = (int64_t)gridDim.x * rpp * kMomU;
+  if (active) {
+    for (int64_t row0 = (int64_t)blockIdx.x * rpp * kMomU + r; row0 < n; row0 += stride) {
+      float4 v[kMomU];
+      int e[kMomU];
+#pragma unroll
+      for (int u = 0; u < kMomU; ++u) {
+        const int64_t row = row0 + (int64_t)u * rpp;
+        const bool ok = row < n;
+        const float qnan = __int_as_float(0x7fc00000);
+        v[u] = ok ? ldg_stream_f4(reinterpret_cast<const float4*>(X + row * ld + c)) : make_float4(qnan, qnan, qnan, qnan);
+        e[u] = (ok && mask) ? 2 - __popc(mask[row] & 3) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < kMomU; ++u) {
+        const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (x[q] == x[q]) {
+            const double dx = (double)x[q] - shift[q];
+            cnt[q] += 1;
+            s1[q] += dx;
+            s2[q] = fma(dx, dx, s2[q]);
+            if (e[u]) {
+              es1[q] = fma((double)e[u], dx, es1[q]);
+              ecnt[q] += e[u];
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double* dst = red + (size_t)r * 5 * d + c + q;
+      dst[0 * d] = (double)cnt[q];
+      dst[1 * d] = s1[q];
+      dst[2 * d] = s2[q];
+      dst[3 * d] = es1[q];
+      dst[4 * d] = (double)ecnt[q];
+    }
+  }
+  __syncthreads();
+  double* out = part + (size_t)blockIdx.x * 5 * cw;
+  for (int i = tid; i < 5 * d; i += kMomThreads) {
+    const int q = i / d, col = i - q * d;
+    double acc = 0.0;
+    for (int rr = 0; rr < rpp; ++rr) acc += red[(size_t)rr * 5 * d + i];   // fixed order
+    out[q * cw + col] = acc;
+  }
+}
+
 __global__ void col_moments_reduce_kernel(const float* __restrict__ X, const double* __restrict__ shift_in,
                                           int d, int cw, int gx, const double* __restrict__ part,
                                           double* __restrict__ out) {
@@ -155,10 +234,24 @@ extern "C" int pmb_col_moments(const float* X, int64_t n, int d, int64_t ld, con
   const int rpp = kMomThreads / cw;
   const int64_t groups = (n + (int64_t)rpp * 8 - 1) / ((int64_t)rpp * 8);
   if (gx > groups) gx = (int)groups;
-  dim3 grid(gx, gy);
-  col_moments_kernel<<<grid, kMomThreads, 0, as_stream(stream)>>>(X, n, d, ld, mask, shift_in, cw,
-                                                                 static_cast<double*>(ws));
-  PMB_LAUNCH_CHECK();
+  const bool v4 = (d % 4 == 0) && d >= 16 && d <= 4 * kMomThreads && (ld % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && gy == 1;
+  if (v4) {
+    const int rpp4 = kMomThreads / (d / 4);
+    const int64_t groups4 = (n + (int64_t)rpp4 * kMomU - 1) / ((int64_t)rpp4 * kMomU);
+    gx = 3 * kNumSMs;   // 80 registers x 256 threads: three resident CTAs per SM, one wave
+    if (gx > groups4) gx = (int)groups4;
+    const size_t smem = (size_t)rpp4 * 5 * d * sizeof(double);
+    PMB_CUDA(cudaFuncSetAttribute(col_moments_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    col_moments_v4_kernel<<<gx, kMomThreads, smem, as_stream(stream)>>>(X, n, d, ld, mask, shift_in, cw,
+                                                                        static_cast<double*>(ws));
+    PMB_LAUNCH_CHECK();
+  } else {
+    dim3 grid(gx, gy);
+    col_moments_kernel<<<grid, kMomThreads, 0, as_stream(stream)>>>(X, n, d, ld, mask, shift_in, cw,
+                                                                   static_cast<double*>(ws));
+    PMB_LAUNCH_CHECK();
+  }
   col_moments_reduce_kernel<<<(d + 127) / 128, 128, 0, as_stream(stream)>>>(
       X, shift_in, d, cw, gx, static_cast<const double*>(ws), out);
   PMB_LAUNCH_CHECK();

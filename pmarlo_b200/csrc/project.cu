@@ -75,6 +75,98 @@ __global__ void __launch_bounds__(kPrjFrames) project_kernel(
   }
 }
 
+// fp32-output fast path (the pipeline's Y): thread per frame, the frame's row is read straight from
+// global memory as 32-byte pieces (every sector is consumed completely, so no shared-memory transpose and
+// no barriers), W lives in shared memory as fp32 and is read with 16-byte broadcasts.  Precision: the
+// row is centred in fp32 against a32 = float(a) (exact for values near the mean), products are
+// accumulated in fp32 over 32 columns and then folded into fp64, and the fp64 remainder
+// - sum_j (a_j - a32_j) W_jc is added once per frame.
+constexpr int kPfThreads = 128;
+
+template <int MP>   // outputs padded to a multiple of 4
+__global__ void __launch_bounds__(kPfThreads) project_fast_kernel(
+    const float* __restrict__ X, int64_t n, int d, int64_t ld, const double* __restrict__ a,
+    const double* __restrict__ nanfill, const double* __restrict__ W, int m, int ldw,
+    float* __restrict__ Y, int64_t ldy) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sW = reinterpret_cast<float*>(smem_raw);              // d x MP
+  float* sa = sW + (size_t)d * MP;                             // d
+  float* sfz = sa + d;                                         // d: imputed value, centred
+  double* scorr = reinterpret_cast<double*>(sfz + d);          // MP
+  const int tid = threadIdx.x;
+  for (int i = tid; i < d * MP; i += kPfThreads) {
+    const int j = i / MP, c = i - j * MP;
+    sW[i] = (c < m) ? (float)W[(size_t)j * ldw + c] : 0.f;
+  }
+  for (int i = tid; i < d; i += kPfThreads) {
+    const float a32 = (float)a[i];
+    sa[i] = a32;
+    sfz[i] = (float)(nanfill[i] - a[i]);
+  }
+  if (tid < MP) {
+    double acc = 0.0;
+    if (tid < m)
+      for (int j = 0; j < d; ++j) acc = fma(a[j] - (double)(float)a[j], W[(size_t)j * ldw + tid], acc);
+    scorr[tid] = -acc;
+  }
+  __syncthreads();
+  for (int64_t row = (int64_t)blockIdx.x * kPfThreads + tid; row < n; row += (int64_t)gridDim.x * kPfThreads) {
+    const float4* xr = reinterpret_cast<const float4*>(X + row * ld);
+    double acc64[MP];
+#pragma unroll
+    for (int c = 0; c < MP; ++c) acc64[c] = scorr[c];
+    for (int j0 = 0; j0 < d; j0 += 32) {
+      float acc[MP];
+#pragma unroll
+      for (int c = 0; c < MP; ++c) acc[c] = 0.f;
+      float4 xv[8];
+#pragma unroll
+      // default caching: a lane's eight 16-byte loads walk one 128-byte line, the second half of every
+      // 32-byte sector must hit L1 instead of going back to L2
+      for (int q = 0; q < 8; ++q) xv[q] = (j0 + 4 * q < d) ? __ldg(xr + (j0 >> 2) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = j0 + 4 * q;
+        if (j >= d) break;
+        const float4 av = *reinterpret_cast<const float4*>(sa + j);
+        const float x[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
+        const float aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float z = (x[e] == x[e]) ? x[e] - aa[e] : sfz[j + e];
+          const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)(j + e) * MP);
+#pragma unroll
+          for (int c4 = 0; c4 < MP / 4; ++c4) {
+            const float4 w = w4[c4];
+            acc[4 * c4 + 0] = fmaf(z, w.x, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(z, w.y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(z, w.z, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(z, w.w, acc[4 * c4 + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < MP; ++c) acc64[c] += (double)acc[c];
+    }
+    float* y = Y + row * ldy;
+#pragma unroll
+    for (int c = 0; c < MP; ++c)
+      if (c < m) y[c] = (float)acc64[c];
+  }
+}
+
+template <int MP>
+static int launch_project_fast(const float* X, int64_t n, int d, int64_t ld, const double* a, const double* nanfill,
+                               const double* W, int m, float* Y, int64_t ldy, cudaStream_t st) {
+  const size_t smem = ((size_t)d * MP + 2 * (size_t)d) * sizeof(float) + MP * sizeof(double) + 16;
+  PMB_CUDA(cudaFuncSetAttribute(project_fast_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = (n + kPfThreads - 1) / kPfThreads;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  project_fast_kernel<MP><<<(unsigned)blocks, kPfThreads, smem, st>>>(X, n, d, ld, a, nanfill, W, m, m, Y, ldy);
+  PMB_LAUNCH_CHECK();
+  return PMB_OK;
+}
+
 template <int MP>
 static int launch_project(const float* X, int64_t n, int d, int64_t ld, const double* a,
                           const double* nanfill, const double* W, int m, int c_off, void* Y,
@@ -103,6 +195,14 @@ extern "C" int pmb_project(const float* X, int64_t n, int d, int64_t ld, const d
   if (n == 0) return PMB_OK;
   PMB_REQUIRE(X && a && nanfill && W && Y, "pmb_project: null pointer");
   cudaStream_t st = as_stream(stream);
+  if (!out_f64 && m <= 16 && d % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+      (size_t)d * 16 * 4 <= 160 * 1024) {
+    float* Yf = static_cast<float*>(Y);
+    if (m <= 4) return launch_project_fast<4>(X, n, d, ld, a, nanfill, W, m, Yf, ldy, st);
+    if (m <= 8) return launch_project_fast<8>(X, n, d, ld, a, nanfill, W, m, Yf, ldy, st);
+    if (m <= 12) return launch_project_fast<12>(X, n, d, ld, a, nanfill, W, m, Yf, ldy, st);
+    return launch_project_fast<16>(X, n, d, ld, a, nanfill, W, m, Yf, ldy, st);
+  }
   for (int c_off = 0; c_off < m; c_off += 16) {
     const int rem = m - c_off;
     int rc;
