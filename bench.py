@@ -398,8 +398,11 @@ def kmeans_debug_counters():
 
 
 def roofline(stages, counts, frames, cfg, peaks, args):
-    """Roofline of the dominant kernel, from the CUDA-event time of its launches inside the
-    timed region.  Algorithmic work per frame (DESIGN.md section 5 / SURVEY.md 8d)."""
+    """Roofline of the dominant kernel (largest share of the step), from the CUDA-event time of its
+    launches inside the timed region, plus the same figures for every other per-frame kernel under
+    ``all``.  Algorithmic work per frame: DESIGN.md section 3 / SURVEY.md 8d.  ``traffic`` is the DRAM
+    traffic per launch measured by ncu (profiles/ncu_traffic.json: bytes per frame of one ``--set full``
+    capture, scaled to this run's frames)."""
     kernels_alg = {
         # name: (bound, bytes or flops per frame per launch)
         "featurize": ("hbm", 12 * 3 * N_RES + 4 * 256),
@@ -409,29 +412,46 @@ def roofline(stages, counts, frames, cfg, peaks, args):
         "kmeans_assign": ("tensor", 2 * cfg.tica_dim * cfg.n_states),
         "count": ("hbm", 4),
     }
-    cand = {k: stages.get(k, 0.0) for k in kernels_alg}
-    top = max(cand, key=cand.get)
-    bound, per_frame = kernels_alg[top]
-    n_launch = max(1, counts.get(top, 1))
-    ms_per_launch = cand[top] * args.steps / n_launch if n_launch else 0.0
-    work = per_frame * frames
-    if bound == "hbm":
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = work / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch else 0.0
-        unit = "GB/s"
-        src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"
-    else:
-        # fp32-exact tensor work is issued as TF32 (3 passes for the split): peak = measured bf16 / 2
-        key = "bf16_tflops_sustained"
-        peak = float(peaks.get(key, 1400.0)) / 2.0
-        achieved = work / (ms_per_launch * 1e-3) / 1e12 if ms_per_launch else 0.0
-        unit = "TFLOP/s"
-        src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 rate; kernel timed inside a long step)"
-               if peaks else "fallback 1.4 PFLOP/s / 2")
-    return {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-            "frac": achieved / peak if peak else None, "traffic": None, "ms_per_launch": ms_per_launch,
-            "launches_per_step": n_launch / args.steps, "algorithmic_per_frame": per_frame, "peak_source": src,
-            "share_of_step": cand[top] / max(1e-9, sum(v for k, v in stages.items() if k in TOP_LEVEL_STAGES))}
+    traffic_pf = {}
+    tp = ROOT / "profiles" / "ncu_traffic.json"
+    if tp.exists():
+        try:
+            traffic_pf = json.loads(tp.read_text()).get("dram_bytes_per_frame", {})
+        except Exception:
+            traffic_pf = {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+    step_ms = max(1e-9, sum(v for k, v in stages.items() if k in TOP_LEVEL_STAGES))
+
+    def one(name):
+        bound, per_frame = kernels_alg[name]
+        n_launch = max(1, counts.get(name, 1))
+        ms_per_launch = stages.get(name, 0.0) * args.steps / n_launch
+        work = per_frame * frames
+        if bound == "hbm":
+            peak, unit = hbm_peak, "GB/s"
+            achieved = work / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch else 0.0
+            src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)"
+        else:
+            # fp32-exact tensor work is issued as TF32: peak = measured bf16 / 2
+            peak, unit = tf32_peak, "TFLOP/s"
+            achieved = work / (ms_per_launch * 1e-3) / 1e12 if ms_per_launch else 0.0
+            src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 rate, of measured; kernel timed inside a "
+                   "long step)" if peaks else "fallback 1.4 PFLOP/s / 2 (of fallback)")
+        tr = traffic_pf.get(name)
+        return {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                "frac": achieved / peak if peak else None,
+                "traffic": (float(tr) * frames) if tr is not None else None,
+                "ms_per_launch": ms_per_launch, "launches_per_step": n_launch / args.steps,
+                "algorithmic_per_frame": per_frame, "peak_source": src,
+                "share_of_step": stages.get(name, 0.0) / step_ms}
+
+    top = max(kernels_alg, key=lambda k: stages.get(k, 0.0))
+    out = one(top)
+    out["all"] = {k: {kk: vv for kk, vv in one(k).items() if kk in ("bound", "achieved", "unit", "frac", "ms_per_launch",
+                                                                     "share_of_step", "traffic")}
+                  for k in kernels_alg}
+    return out
 
 
 TOP_LEVEL_STAGES = ("featurize", "tica_fit", "project", "kmeans", "count", "mle", "eig")

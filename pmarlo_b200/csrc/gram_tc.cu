@@ -21,10 +21,10 @@
 // Every kWindow frames the two 128 x d accumulators are drained into a per-CTA fp64 workspace.
 //
 // One CTA per (128-row block of G, frame chunk); 148 CTAs = 2 row blocks x 74 chunks for d = 256.
-//   warps 0-7  producers: coalesced float4 loads (next stage prefetched in registers), conditioning,
+//   warps 0-15 producers: coalesced float4 loads (next stage prefetched in registers), conditioning,
 //              split, 16-byte stores into the MN-major 128B-swizzled operand tiles; drain TMEM at the
 //              end of a window
-//   warp  8    MMA issuer: 8 tcgen05.mma (M = 128, N = d, K = 8) per 16-frame stage
+//   warp  16   MMA issuer: 8 tcgen05.mma (M = 128, N = d, K = 8) per 16-frame stage
 // 3-stage shared-memory ring, mbarrier full/empty hand-off, tcgen05.commit frees a stage.
 #include "tc05.cuh"
 
@@ -32,8 +32,9 @@ namespace pmb {
 
 constexpr int kGtBK = 16;            // frames per stage
 constexpr int kGtStages = 3;
-constexpr int kGtProdWarps = 8;
-constexpr int kGtThreads = (kGtProdWarps + 1) * 32;   // 288
+constexpr int kGtProdWarps = 16;     // 4 producer warps per scheduler: the producers must keep ~60% of the issue slots busy
+constexpr int kGtF4 = 64 / (kGtProdWarps * 32 / kGtBK);   // float4 groups per thread and stage (2)
+constexpr int kGtThreads = (kGtProdWarps + 1) * 32;   // 544
 constexpr int kGtWindow = 4096;      // frames per TMEM accumulation window (multiple of kGtBK)
 constexpr uint32_t kGtTileB = 256 * kGtBK * 4;        // bytes of one N-side tile (256 features x 16 frames)
 constexpr uint32_t kGtTileA = 128 * kGtBK * 4;
@@ -102,13 +103,14 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
 
   if (warp < kGtProdWarps) {
     // ============================================================ producers
-    const int fr = tid >> 4;          // frame within the stage
-    const int g4 = tid & 15;          // float4 group: handles float4 indices g4 + 16 j
+    constexpr int kTpf = kGtProdWarps * 32 / kGtBK;   // threads per frame (32)
+    const int fr = tid / kTpf;        // frame within the stage
+    const int g4 = tid % kTpf;        // float4 group: handles float4 indices g4 + kTpf j
     const int nf4 = d >> 2;
-    float4 sh[4], sc[4];
+    float4 sh[kGtF4], sc[kGtF4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = (g4 + 16 * j) * 4;
+    for (int j = 0; j < kGtF4; ++j) {
+      const int c = (g4 + kTpf * j) * 4;
       if (c < d) {
         sh[j] = *reinterpret_cast<const float4*>(p.shift + c);
         sc[j] = *reinterpret_cast<const float4*>(p.scale + c);
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
         sc[j] = sh[j];
       }
     }
-    float4 xa[4], xb[4];
+    float4 xa[kGtF4], xb[kGtF4];
     int mk = 0;
     auto prefetch = [&](int s) {
       const int64_t g = g_begin + (int64_t)s * kGtBK + fr;
@@ -125,10 +127,10 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
       if (g < g_end) mk = p.mask[g];
       const int w = (p.mode == 0) ? __popc(mk & 3) : (mk & 1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kGtF4; ++j) {
         xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         xb[j] = xa[j];
-        const int idx = g4 + 16 * j;
+        const int idx = g4 + kTpf * j;
         if (w && idx < nf4) {
           xa[j] = ldg_stream_f4(reinterpret_cast<const float4*>(p.X + g * p.ld) + idx);
           if (p.mode == 1) xb[j] = ldg_stream_f4(reinterpret_cast<const float4*>(p.X + (g + p.lag) * p.ld) + idx);
@@ -142,9 +144,9 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
     };
     auto drain = [&](bool first) {
       // warp w: lane quarter w % 4, accumulator (w / 4): 0 = P (columns 0..d), 1 = Q (columns 256..256+d)
-      const int quarter = warp & 3, which = warp >> 2;
+      const int quarter = warp & 3, which = (warp >> 2) & 1, part = warp >> 3, nparts = kGtProdWarps / 8;
       double* dst = ws + (size_t)which * d * 128 + quarter * 32 + lane;
-      for (int c0 = 0; c0 < d; c0 += 32) {
+      for (int c0 = part * 32; c0 < d; c0 += 32 * nparts) {
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(which * 256 + c0), v);
 #pragma unroll
@@ -161,9 +163,9 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
       const int slot = s % kGtStages;
       const uint32_t use = (uint32_t)(s / kGtStages);
       // current stage data -> registers, then prefetch the next stage
-      float4 ca[4], cb[4];
+      float4 ca[kGtF4], cb[kGtF4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { ca[j] = xa[j]; cb[j] = xb[j]; }
+      for (int j = 0; j < kGtF4; ++j) { ca[j] = xa[j]; cb[j] = xb[j]; }
       const int w = mk;
       if (s + 1 < n_stages) prefetch(s + 1);
       mbar_wait(&B->empty[slot], (use & 1u) ^ 1u);
@@ -184,8 +186,8 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
         dith = __uint_as_float((h >> 9) | 0x3f800000u) - 1.5f;   // uniform in [-0.5, 0.5)
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int idx = g4 + 16 * j;
+      for (int j = 0; j < kGtF4; ++j) {
+        const int idx = g4 + kTpf * j;
         if (idx >= nf4) continue;
         float z[4];
         z[0] = gt_cond(ca[j].x, sh[j].x, sc[j].x);

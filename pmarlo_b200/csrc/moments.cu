@@ -149,18 +149,23 @@ __global__ void __launch_bounds__(kMomThreads, 3) col_moments_v4_kernel(
   }
 }
 
+// One WARP per column: the lanes split the CTA partials (fixed assignment, fixed shuffle tree: the result
+// is bit-reproducible), so the dependent chain is gx / 32 L2 loads instead of gx.
 __global__ void col_moments_reduce_kernel(const float* __restrict__ X, const double* __restrict__ shift_in,
                                           int d, int cw, int gx, const double* __restrict__ part,
                                           double* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= d) return;
   const int by = c / cw, cl = c - by * cw;
   double acc[5] = {0, 0, 0, 0, 0};
-  for (int b = 0; b < gx; ++b) {
+  for (int b = lane; b < gx; b += 32) {
     const double* src = part + ((size_t)by * gx + b) * 5 * cw;
 #pragma unroll
     for (int q = 0; q < 5; ++q) acc[q] += src[q * cw + cl];
   }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) acc[q] = warp_sum(acc[q]);
+  if (lane != 0) return;
   double sh;
   if (shift_in != nullptr) {
     sh = shift_in[c];
@@ -252,7 +257,7 @@ extern "C" int pmb_col_moments(const float* X, int64_t n, int d, int64_t ld, con
                                                                    static_cast<double*>(ws));
     PMB_LAUNCH_CHECK();
   }
-  col_moments_reduce_kernel<<<(d + 127) / 128, 128, 0, as_stream(stream)>>>(
+  col_moments_reduce_kernel<<<(d * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(
       X, shift_in, d, cw, gx, static_cast<const double*>(ws), out);
   PMB_LAUNCH_CHECK();
   return PMB_OK;
