@@ -82,10 +82,13 @@ def synth_xyz_device(n_traj, frames_per_traj, device, seed, rho=0.9995, sigma=0.
     device chunk by chunk: x_t = rho^t (x_0 + sum_{s<=t} rho^-s e_s) inside a chunk."""
     import torch
 
+    # the molecule (mean structure) is the same on every rank; only the dynamics are seeded per rank
+    g0 = torch.Generator(device=device)
+    g0.manual_seed(4)
     g = torch.Generator(device=device)
     g.manual_seed(int(seed))
     A = 3 * N_RES
-    steps = torch.randn((A, 3), generator=g, device=device, dtype=torch.float64)
+    steps = torch.randn((A, 3), generator=g0, device=device, dtype=torch.float64)
     steps /= steps.norm(dim=1, keepdim=True)
     base = torch.cumsum(0.15 * steps, dim=0).to(torch.float32)
     out = torch.empty((n_traj, frames_per_traj, A, 3), dtype=torch.float32, device=device)

@@ -488,9 +488,12 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   PMB_REQUIRE(per_sm >= 1, "pmb_tica_solve: kernel does not fit on an SM");
   int nb = (d + blk - 1) / blk;
   if (nb & 1) ++nb;
-  int grid = nb / 2;
-  if (grid > sms) grid = sms;
-  if (grid < 1) grid = 1;
+  // One CTA per SM even though only nb / 2 of them own a block pair: the others join the grid barriers and
+  // the dense phases.  (With 8 busy SMs out of 148 the measured SM clock during this kernel dropped to
+  // 0.7-1.4 GHz on some runs -- same cycle count, up to 3x the wall time.)
+  int grid = sms;
+  if (grid < nb / 2) grid = nb / 2;
+  if (grid > sms * per_sm) grid = sms * per_sm;
   void* args[] = {(void*)&C00, (void*)&C0t, (void*)&d, (void*)&eps, (void*)&evals, (void*)&evecs, (void*)&rank, (void*)&w,
                   (void*)&blk};
   PMB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kTgThreads), args, smem, st));
