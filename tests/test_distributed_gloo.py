@@ -147,3 +147,90 @@ def test_two_rank_gloo_pipeline_matches_oracle():
         np.testing.assert_allclose(r["pi"], pi, atol=1e-8)
     np.testing.assert_array_equal(r0["counts"], r1["counts"])
     np.testing.assert_allclose(r0["T"], r1["T"], atol=1e-14)
+
+
+# ----------------------------------------------------------------------------- streaming TICA accumulator
+def _stream_fit(feats, comm, chunks):
+    """Chunk-wise fit as estimate_msm_from_host does it: ``chunks`` = list of lists of trajectory indices."""
+    from pmarlo_b200.reduction import TICA
+    from pmarlo_b200.shards import Segments
+
+    cfg = _cfg()
+    est = TICA(cfg.tica_lag, cfg.tica_dim, preprocess=cfg.preprocess, comm=comm)
+    acc = est.accumulator(feats[0].shape[1], torch.device("cpu"))
+    for idx in chunks:
+        X = torch.from_numpy(np.concatenate([feats[i] for i in idx], axis=0))
+        acc.add(X, Segments.from_lengths([feats[i].shape[0] for i in idx]))
+    return acc.finish(), acc
+
+
+def _check_model(m, om):
+    assert m.n_pairs == om.n_pairs
+    np.testing.assert_allclose(m.C00.numpy(), om.C00, rtol=0, atol=1e-6 * np.abs(om.C00).max())
+    np.testing.assert_allclose(m.C0t.numpy(), om.C0t, rtol=0, atol=1e-6 * np.abs(om.C0t).max())
+    np.testing.assert_allclose(m.eigenvalues.numpy()[:3], om.eigenvalues[:3], atol=1e-6)
+
+
+def test_streaming_accumulator_matches_oracle(monkeypatch):
+    """Conditioning from the first chunk (clean data) and the second-pass fallback (NaN in the data)."""
+    from pmarlo_b200.distributed import Comm
+
+    fake_kernels.install(monkeypatch)
+    feats = _feats()
+    c0 = _c0(feats)
+    om = _oracle(feats, c0)[0]
+    m, acc = _stream_fit(feats, Comm(), [[0, 1], [2], [3, 4]])
+    assert acc.fell_back            # feats[0] holds a NaN
+    _check_model(m, om)
+    clean = [f.copy() for f in feats]
+    clean[0][17, 2] = 0.25
+    om2 = _oracle(clean, _c0(clean))[0]
+    m2, acc2 = _stream_fit(clean, Comm(), [[0], [1, 2, 3], [4]])
+    assert not acc2.fell_back
+    _check_model(m2, om2)
+
+
+def _stream_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pmarlo_b200.distributed import Comm
+        from pmarlo_b200.shards import partition_trajectories
+
+        fake_kernels.install(None)
+        feats = [f.copy() for f in _feats()]
+        feats[0][17, 2] = 0.25
+        parts = partition_trajectories([f.shape[0] for f in feats], world)
+        mine = [feats[i] for i in parts[rank]]
+        # ranks use different chunkings; the broadcasts of shift / conditioning come from rank 0's first chunk
+        chunks = [[i] for i in range(len(mine))] if rank == 0 else [list(range(len(mine)))]
+        m, acc = _stream_fit(mine, Comm(), chunks)
+        np.savez(f"{out_path}.{rank}.npz", C00=m.C00.numpy(), C0t=m.C0t.numpy(), ev=m.eigenvalues.numpy(),
+                 n_pairs=m.n_pairs, fell_back=int(acc.fell_back))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_streaming_accumulator_matches_oracle():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "res")
+        mp.spawn(_stream_worker, args=(2, port, out), nprocs=2, join=True)
+        r0, r1 = np.load(out + ".0.npz"), np.load(out + ".1.npz")
+    feats = [f.copy() for f in _feats()]
+    feats[0][17, 2] = 0.25
+    om = _oracle(feats, _c0(feats))[0]
+    for r in (r0, r1):
+        assert int(r["n_pairs"]) == om.n_pairs and int(r["fell_back"]) == 0
+        np.testing.assert_allclose(r["C00"], om.C00, rtol=0, atol=1e-6 * np.abs(om.C00).max())
+        np.testing.assert_allclose(r["C0t"], om.C0t, rtol=0, atol=1e-6 * np.abs(om.C0t).max())
+        np.testing.assert_allclose(r["ev"][:3], om.eigenvalues[:3], atol=1e-6)
+    np.testing.assert_allclose(r0["C00"], r1["C00"], rtol=0, atol=1e-14)
