@@ -240,11 +240,11 @@ __device__ __forceinline__ void ll_store(unsigned long long* slot, double v, uns
   const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
   const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)tag << 32);
   const unsigned long long w1 = (bits >> 32) | ((unsigned long long)tag << 32);
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");   // gpu scope: ld/st.volatile compile to .STRONG.SYS
 }
 __device__ __forceinline__ bool ll_try_load(const unsigned long long* slot, unsigned int tag, double& out) {
   unsigned long long w0, w1;
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
   out = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
   return (unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag;
 }

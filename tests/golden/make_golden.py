@@ -174,7 +174,57 @@ def make_assign():
     print("assign ok", np.bincount(lab_train))
 
 
+def make_discretize():
+    """analysis.discretize.discretize_dataset (discretize.py:901-1120) end to end: whitening, k-means fit
+    (sklearn, not reproducible elsewhere -> the fitted centres are stored), per-split assignment,
+    weighted lagged counts over segments, zero-row pruning, row-normalised T."""
+    from pmarlo.analysis.discretize import discretize_dataset
+
+    rng = np.random.default_rng(11)
+    K = 9
+    centers0 = rng.standard_normal((K, 4)) * 3
+    centers0[K - 1] = 40.0            # far away: k-means gives the sink its own cluster
+    # a jump process between the blobs; blob K-1 is only ever entered at the very end of a segment,
+    # so its row of the count matrix is empty and the reference prunes it
+    def traj(n, last_to_sink):
+        s = np.empty(n, dtype=int)
+        s[0] = rng.integers(0, K - 1)
+        for t in range(1, n):
+            s[t] = s[t - 1] if rng.random() < 0.8 else rng.integers(0, K - 1)
+        if last_to_sink:
+            s[-3:] = K - 1
+        return centers0[s] + 0.3 * rng.standard_normal((n, 4))
+    seg = [400, 250, 350]
+    Xtr = np.concatenate([traj(seg[0], True), traj(seg[1], False), traj(seg[2], False)])
+    Xte = traj(500, False)
+    w = rng.uniform(0.5, 1.5, size=Xtr.shape[0])
+    dataset = {"splits": {
+        "train": {"X": Xtr, "feature_schema": {"names": ["a", "b", "c", "d"], "n_features": 4},
+                  "segments": [{"length": L, "stride": 1} for L in seg]},
+        "test": {"X": Xte, "feature_schema": {"names": ["a", "b", "c", "d"], "n_features": 4},
+                 "segments": [{"length": 500}]},
+    }}
+    out = {}
+    for tag, kw in (("plain", dict()), ("weighted", dict(frame_weights={"train": w}, min_out_count=2))):
+        r = discretize_dataset(dataset, cluster_mode="kmeans", n_microstates=K, lag_time=3, random_state=0, **kw)
+        out[f"{tag}_centers"] = r.centers
+        out[f"{tag}_lab_train"] = r.assignments["train"]
+        out[f"{tag}_lab_test"] = r.assignments["test"]
+        out[f"{tag}_counts"] = r.counts
+        out[f"{tag}_T"] = r.transition_matrix
+        out[f"{tag}_diag_mass"] = r.diag_mass
+        out[f"{tag}_counts_before_prune"] = r.counts_before_prune
+        out[f"{tag}_state_counts"] = r.state_counts
+        out[f"{tag}_pruned"] = (np.asarray([], dtype=np.int32) if r.pruned_state_indices is None
+                                 else r.pruned_state_indices)
+        out[f"{tag}_counted_pairs"] = r.counted_pairs["train"]
+        out[f"{tag}_expected_pairs"] = r.expected_pairs["train"]
+        print("discretize", tag, r.counts.shape, out[f"{tag}_pruned"], r.counted_pairs, r.expected_pairs, r.diag_mass)
+    np.savez_compressed(OUT / "discretize.npz", Xtr=Xtr, Xte=Xte, seg=np.asarray(seg), w=w, **out)
+
+
 if __name__ == "__main__":
+    make_discretize()
     make_topologies()
     make_counts()
     make_timescales()

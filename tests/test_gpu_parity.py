@@ -631,3 +631,128 @@ def test_pipeline_properties_at_scale():
     sl = slice(0, 20000)
     lo, _ = oracle.kmeans.assign(res.Y[sl].cpu().numpy().astype(np.float64), res.centers.cpu().numpy())
     np.testing.assert_array_equal(lab[sl], lo)
+
+
+# ----------------------------------------------------------------------------- discretize_dataset (a7)
+def _discretize_dataset_inputs(z):
+    seg = [int(v) for v in z["seg"]]
+    names = {"names": ["a", "b", "c", "d"], "n_features": 4}
+    return {"splits": {
+        "train": {"X": z["Xtr"], "feature_schema": names, "segments": [{"length": L, "stride": 1} for L in seg]},
+        "test": {"X": z["Xte"], "feature_schema": names, "segments": [{"length": 500}]},
+    }}
+
+
+@pytest.mark.parametrize("tag", ["plain", "weighted"])
+def test_discretize_dataset_matches_reference_given_its_centres(golden, tag):
+    """pmarlo.analysis.discretize.discretize_dataset run in the reference (tests/golden/make_golden.py):
+    with the reference's fitted centres injected, assignments, pruning, counts, T and the pair bookkeeping
+    are reproduced (labels and unweighted counts bit-exactly)."""
+    from pmarlo_b200.discretize import discretize_dataset
+
+    z = golden("discretize")
+    kw = dict(frame_weights={"train": z["w"]}, min_out_count=2) if tag == "weighted" else {}
+    r = discretize_dataset(_discretize_dataset_inputs(z), cluster_mode="kmeans", n_microstates=9, lag_time=3,
+                           random_state=0, centers=z[f"{tag}_centers"], **kw)
+    np.testing.assert_array_equal(r.assignments["train"], z[f"{tag}_lab_train"])
+    np.testing.assert_array_equal(r.assignments["test"], z[f"{tag}_lab_test"])
+    np.testing.assert_array_equal(r.pruned_state_indices, z[f"{tag}_pruned"])
+    assert r.counted_pairs["train"] == int(z[f"{tag}_counted_pairs"])
+    assert r.expected_pairs["train"] == int(z[f"{tag}_expected_pairs"])
+    if tag == "plain":
+        np.testing.assert_array_equal(r.counts, z["plain_counts"])
+        np.testing.assert_array_equal(r.counts_before_prune, z["plain_counts_before_prune"])
+        np.testing.assert_array_equal(r.transition_matrix, z["plain_T"])
+    else:
+        np.testing.assert_allclose(r.counts, z["weighted_counts"], rtol=1e-13, atol=0)
+        np.testing.assert_allclose(r.counts_before_prune, z["weighted_counts_before_prune"], rtol=1e-13, atol=0)
+        np.testing.assert_allclose(r.transition_matrix, z["weighted_T"], rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(r.state_counts, z[f"{tag}_state_counts"], rtol=1e-13)
+    assert abs(r.diag_mass - float(z[f"{tag}_diag_mass"])) < 1e-13
+    assert r.assignments["train"].dtype == np.int32 and r.counts.dtype == np.float64
+
+
+def test_discretize_dataset_fit_path_and_errors(golden):
+    from pmarlo_b200.discretize import discretize_dataset
+
+    z = golden("discretize")
+    ds = _discretize_dataset_inputs(z)
+    r = discretize_dataset(ds, n_microstates=9, lag_time=3, random_state=0, n_init=3)
+    # own fit: different centres than sklearn's, same invariants
+    n = r.counts.shape[0]
+    assert r.centers.shape == (9, 4) and 1 <= n <= 9
+    assert r.counted_pairs["train"] == int(r.counts.sum()) <= r.expected_pairs["train"]
+    rows = r.transition_matrix.sum(axis=1)
+    assert np.all((np.abs(rows - 1.0) < 1e-12) | (rows == 0.0))
+    assert set(r.assignments) == {"train", "test"} and r.assignments["test"].max() < n
+    r2 = discretize_dataset(ds, n_microstates=9, lag_time=3, random_state=0, n_init=3)
+    np.testing.assert_array_equal(r.assignments["train"], r2.assignments["train"])     # seeded -> reproducible
+    with pytest.raises(ValueError):
+        discretize_dataset(ds, lag_time=0)
+    with pytest.raises(ValueError):
+        discretize_dataset({"splits": {}})
+    with pytest.raises(NotImplementedError):
+        discretize_dataset(ds, cluster_mode="grid")
+    bad = {"splits": {"train": ds["splits"]["train"], "test": {"X": z["Xte"][:, :3]}}}
+    with pytest.raises(ValueError):
+        discretize_dataset(bad, n_microstates=9, centers=z["plain_centers"])
+    # a plain (n, d) array is a dataset with one split called "all"
+    r3 = discretize_dataset(z["Xtr"], n_microstates=5, lag_time=2, random_state=1, n_init=1)
+    assert list(r3.assignments) == ["all"] and r3.segment_lengths["all"] == [z["Xtr"].shape[0]]
+
+
+# ----------------------------------------------------------------------------- EnhancedMSM interface (8b)
+def test_enhanced_msm_build_and_its_match_oracle():
+    from pmarlo_b200 import EnhancedMSM
+
+    rng = np.random.default_rng(7)
+    P = np.array([[0.92, 0.06, 0.02, 0.0], [0.05, 0.9, 0.05, 0.0], [0.02, 0.08, 0.9, 0.0], [0.0, 0.0, 0.0, 1.0]])
+    dtrajs = []
+    for n in (4000, 2500, 3000):
+        s = np.empty(n, dtype=np.int64)
+        s[0] = rng.integers(0, 3)
+        for t in range(1, n):
+            s[t] = rng.choice(4, p=P[s[t - 1]])
+        dtrajs.append(s)
+    dtrajs[1][100:103] = -1                       # unassigned frames split the trajectory
+    m = EnhancedMSM(dtrajs, n_states=5)           # state 3, 4 never visited
+    m.build_msm(lag_time=4)
+    # oracle: split at invalid labels, sliding counts, +alpha on the active block, row normalisation
+    parts = []
+    for d in dtrajs:
+        ok = (d >= 0) & (d < 5)
+        edges = np.flatnonzero(np.diff(np.concatenate([[0], ok.astype(np.int8), [0]])))
+        parts += [d[a:b] for a, b in zip(edges[::2], edges[1::2])]
+    C = oracle.counts.count_lagged(parts, 5, 4).astype(float)
+    Ca, act = oracle.msm.ensure_connected_counts(C)
+    Ta = oracle.msm.transition_matrix_nonrev(Ca)
+    T = np.eye(5)
+    T[np.ix_(act, act)] = Ta
+    pi = np.zeros(5)
+    pi[act] = oracle.msm.stationary_distribution(Ta)
+    np.testing.assert_allclose(m.transition_matrix, T, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(m.stationary_distribution, pi, rtol=1e-9, atol=1e-14)
+    cm = np.zeros((5, 5))
+    cm[np.ix_(act, act)] = Ca
+    np.testing.assert_array_equal(m.count_matrix, cm)
+    assert m.stationary_distribution[3] == 0.0 and m.transition_matrix[4, 4] == 1.0
+    assert m.free_energies.min() == 0.0
+    # ITS: per-lag reversible MLE on the largest connected set (ck_its_selector.py:397-399)
+    m.compute_implied_timescales([1, 2, 4, 8, 100000], n_timescales=2, plateau_m=2, plateau_epsilon=0.5)
+    its = m.implied_timescales
+    np.testing.assert_array_equal(its.lag_times, [1, 2, 4, 8])
+    ref = oracle.msm.its_rev_mle(dtrajs, 5, [1, 2, 4, 8], 2)
+    np.testing.assert_allclose(its.timescales, ref, rtol=1e-6, equal_nan=True)
+    assert its.timescales_ci.shape == (4, 2, 2) and np.all(np.isnan(its.timescales_ci))
+    np.testing.assert_allclose(its.rates, 1.0 / ref, rtol=1e-6, equal_nan=True)
+    # reference error / empty behaviour
+    with pytest.raises(ValueError):
+        EnhancedMSM([], n_states=0).build_msm()
+    with pytest.raises(ValueError):
+        m.build_msm(method="tram")
+    e = EnhancedMSM([], n_states=3)
+    e.compute_implied_timescales()
+    assert e.implied_timescales.lag_times.size == 0 and e.implied_timescales.timescales.shape == (0, 5)
+    short = EnhancedMSM([np.array([0, 1])], n_states=2)
+    short.build_msm(lag_time=20)                   # lag capped at 1
+    assert short.transition_matrix.shape == (2, 2)

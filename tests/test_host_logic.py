@@ -168,3 +168,54 @@ def test_lloyd_host_loop_matches_oracle_semantics(monkeypatch):
         assert res.cost == pytest.approx(cost, rel=1e-12)
     res = clustering.lloyd_device(torch.from_numpy(Y), torch.from_numpy(c0), max_iter=4, tolerance=None)
     assert res.n_iter == 4 and res.cost is None
+
+
+# ----------------------------------------------------------------------------- discretize host logic (CPU)
+def test_expected_pairs_matches_simulation_like_the_reference_tests():
+    """Restates tests/unit/analysis/test_counting.py:23-66 of the reference (brute-force simulation of the
+    (t, t+tau) pairs per segment, single and per-segment strides, error behaviour)."""
+    from pmarlo_b200.discretize import expected_pairs
+
+    def simulate(lengths, tau, strides):
+        total = 0
+        for length, stride in zip(lengths, strides):
+            for idx in range(0, max(0, length - tau), max(1, stride)):
+                total += idx + tau < length
+        return total
+
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        lengths = [int(v) for v in rng.integers(0, 51, size=rng.integers(1, 6))]
+        tau = int(rng.integers(0, 11))
+        stride = int(rng.integers(1, 11))
+        assert expected_pairs(lengths, tau, stride) == simulate(lengths, tau, [stride] * len(lengths))
+        strides = [int(v) for v in rng.integers(1, 11, size=rng.integers(1, 6))]
+        full = (strides + [strides[-1]] * len(lengths))[: len(lengths)]
+        assert expected_pairs(lengths, tau, strides) == simulate(lengths, tau, full)
+    with pytest.raises(ValueError, match="lengths must be non-negative"):
+        expected_pairs([5, -1], tau=1)
+    with pytest.raises(ValueError, match="stride values must be positive"):
+        expected_pairs([5], tau=1, stride=0)
+    with pytest.raises(ValueError, match="stride iterable must not be empty"):
+        expected_pairs([5], tau=1, stride=[])
+
+
+def test_discretize_split_and_segment_bookkeeping():
+    from pmarlo_b200 import discretize as dz
+
+    X = np.random.default_rng(1).normal(size=(50, 3))
+    ds = {"splits": {"train": {"X": X, "segments": [{"length": 20}, {"start": 20, "stop": 45, "stride": 2}, 30]},
+                     "bad": {"X": np.full((4, 3), np.nan)}, "val": X[:10]}}
+    sp = dz._find_splits(ds)
+    assert list(sp) == ["train", "val"]                       # non-finite splits are ignored
+    assert dz._segments_of(sp["train"], 50) == ([20, 25, 5], [1, 2, 1])      # truncated to the frames present
+    assert dz._segments_of(sp["val"], 10) == ([10], [1])
+    assert dz._segments_of({"X": X, "segment_lengths": [7, 8]}, 50) == ([7, 8], [1, 1])
+    assert list(dz._find_splits({"a": X, "__meta__": X})) == ["a"]
+    assert list(dz._find_splits(X)) == ["all"]
+    with pytest.raises(ValueError):
+        dz._find_splits({"splits": {"t": np.zeros((0, 3))}})
+    assert dz._schema_of({"X": X, "cv_names": ["p", "q", "r"]}, 3)["names"] == ["p", "q", "r"]
+    assert dz._schema_of(X, 3)["names"] == ["feature_0", "feature_1", "feature_2"]
+    with pytest.raises(ValueError):
+        dz._check_schema({"names": ["a"], "n_features": 1}, {"names": ["b"], "n_features": 1}, "s")
