@@ -30,6 +30,20 @@ struct FeatParams {
   int bulk_out_ok;   // out base 16B aligned and ld_out == n_cols
 };
 
+// MUFU-based square roots: max relative error 2^-22 (sqrt.approx) resp. 2 ulp (rsqrt.approx), against test
+// tolerances of 2e-6 (distances) and 1e-4 rad (angles); the IEEE sequences cost ~10 instructions each and
+// the kernel is issue-bound.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct FeatUnit { int32_t v[8]; };   // kind, 4 atoms, angle / cos / sin (or distance) output columns
 
 __device__ __forceinline__ void feat_unit(const float* __restrict__ fr, const FeatUnit uu,
@@ -40,7 +54,7 @@ __device__ __forceinline__ void feat_unit(const float* __restrict__ fr, const Fe
   const float* p1 = fr + 3 * u[2];
   if (kind == 1) {
     float dx = p1[0] - p0[0], dy = p1[1] - p0[1], dz = p1[2] - p0[2];
-    float d = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
     if (u[5] >= 0) orow[u[5]] = d;
     return;
   }
@@ -51,7 +65,7 @@ __device__ __forceinline__ void feat_unit(const float* __restrict__ fr, const Fe
   float b3x = p3[0] - p2[0], b3y = p3[1] - p2[1], b3z = p3[2] - p2[2];
   float c1x = b2y * b3z - b2z * b3y, c1y = b2z * b3x - b2x * b3z, c1z = b2x * b3y - b2y * b3x;
   float c2x = b1y * b2z - b1z * b2y, c2y = b1z * b2x - b1x * b2z, c2z = b1x * b2y - b1y * b2x;
-  float nb2 = sqrtf(fmaf(b2x, b2x, fmaf(b2y, b2y, b2z * b2z)));
+  float nb2 = fast_sqrt(fmaf(b2x, b2x, fmaf(b2y, b2y, b2z * b2z)));
   float y = (b1x * c1x + b1y * c1y + b1z * c1z) * nb2;
   float x = c1x * c2x + c1y * c2y + c1z * c2z;
   if (u[5] >= 0) {
@@ -64,7 +78,7 @@ __device__ __forceinline__ void feat_unit(const float* __restrict__ fr, const Fe
     float h2 = fmaf(x, x, y * y);
     float c = 1.0f, s = 0.0f;
     if (h2 > 0.0f) {
-      float rh = 1.0f / sqrtf(h2);
+      float rh = fast_rsqrt(h2);
       c = x * rh;
       s = y * rh;
     }
@@ -86,6 +100,8 @@ __global__ void __launch_bounds__(kFeatMaxThreads) featurize_kernel(FeatParams p
   const size_t otile_bytes = ((size_t)p.ft * p.n_cols * 4 + 127) & ~(size_t)127;
   int32_t* s_units = reinterpret_cast<int32_t*>(smem + 128 + 2 * stage_stride + otile_bytes);
 
+  int* s_order = s_units + p.n_units * 8;     // unit ids: dihedrals first, then distances (stable)
+  __shared__ int s_ndih;
   const int nthreads = blockDim.x;
   for (int i = tid; i < p.n_units * 8; i += nthreads) s_units[i] = p.units[i];
   if (tid == 0) {
@@ -94,6 +110,16 @@ __global__ void __launch_bounds__(kFeatMaxThreads) featurize_kernel(FeatParams p
     fence_barrier_init();
   }
   __syncthreads();
+  if (tid == 0) {
+    int nd = 0;
+    for (int u = 0; u < p.n_units; ++u)
+      if (s_units[u * 8] != 1) s_order[nd++] = u;
+    s_ndih = nd;
+    for (int u = 0; u < p.n_units; ++u)
+      if (s_units[u * 8] == 1) s_order[nd++] = u;
+  }
+  __syncthreads();
+  const int n_dih = s_ndih;
 
   const int64_t n_tiles = (p.n_frames + p.ft - 1) / p.ft;
   auto tile_frames = [&](int64_t t) -> int {
@@ -131,26 +157,34 @@ __global__ void __launch_bounds__(kFeatMaxThreads) featurize_kernel(FeatParams p
     if (tid == 0) bulk_wait_read<0>();
     __syncthreads();
 
-    if (p.n_units <= nthreads) {
-      // a thread owns ONE unit (decoded once per tile into registers) and walks the tile's frames with
-      // stride fl_n: no per-item division, no per-item unit decode
-      const int fl_n = nthreads / p.n_units;
-      const int fl = tid / p.n_units;
-      if (fl < fl_n) {
-        FeatUnit u;
+    // Two phases, dihedrals then distances (a dihedral costs ~3x a distance: mixing the kinds in one pass
+    // leaves the distance warps idle while the dihedral warps finish).  In each phase a thread owns ONE unit
+    // of that kind (decoded once into registers) and walks the tile's frames with the phase's stride.
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      const int cnt = phase == 0 ? n_dih : p.n_units - n_dih;
+      const int* list = s_order + (phase == 0 ? 0 : n_dih);
+      if (cnt == 0) continue;
+      if (cnt <= nthreads) {
+        const int fl_n = nthreads / cnt;
+        const int fl = tid / cnt;
+        if (fl < fl_n) {
+          const int uid = list[tid - fl * cnt];
+          FeatUnit u;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) u.v[q] = s_units[(tid - fl * p.n_units) * 8 + q];
-        for (int f = fl; f < nf; f += fl_n) feat_unit(in_cur + f * A3, u, otile + f * p.n_cols);
-      }
-    } else {
-      const int work = nf * p.n_units;
-      for (int w = tid; w < work; w += nthreads) {
-        const int f = w / p.n_units;
-        const int u = w - f * p.n_units;
-        FeatUnit uu;
+          for (int q = 0; q < 8; ++q) u.v[q] = s_units[uid * 8 + q];
+          for (int f = fl; f < nf; f += fl_n) feat_unit(in_cur + f * A3, u, otile + f * p.n_cols);
+        }
+      } else {
+        const int work = nf * cnt;
+        for (int w = tid; w < work; w += nthreads) {
+          const int f = w / cnt;
+          const int uid = list[w - f * cnt];
+          FeatUnit uu;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) uu.v[q] = s_units[u * 8 + q];
-        feat_unit(in_cur + f * A3, uu, otile + f * p.n_cols);
+          for (int q = 0; q < 8; ++q) uu.v[q] = s_units[uid * 8 + q];
+          feat_unit(in_cur + f * A3, uu, otile + f * p.n_cols);
+        }
       }
     }
     fence_proxy_async_smem();
@@ -222,7 +256,7 @@ extern "C" int pmb_featurize(const float* xyz, int64_t n_frames, int n_atoms, co
   PMB_REQUIRE(xyz && units && out, "pmb_featurize: null pointer");
 
   const size_t frame_in = (size_t)n_atoms * 12, frame_out = (size_t)n_cols * 4;
-  const size_t fixed = 128 + 3 * 128 + (size_t)n_units * 32;
+  const size_t fixed = 128 + 3 * 128 + (size_t)n_units * 36;
   const size_t budget = 100 * 1024;  // 2 CTAs per SM
   int ft = (int)((budget - fixed) / (2 * frame_in + frame_out));
   ft = (ft / 4) * 4;
@@ -239,7 +273,7 @@ extern "C" int pmb_featurize(const float* xyz, int64_t n_frames, int n_atoms, co
 
   const size_t stage_stride = (((size_t)ft * frame_in) + 127) & ~(size_t)127;
   const size_t otile = (((size_t)ft * frame_out) + 127) & ~(size_t)127;
-  const size_t smem = 128 + 2 * stage_stride + otile + (size_t)n_units * 32;
+  const size_t smem = 128 + 2 * stage_stride + otile + (size_t)n_units * 36;
   PMB_CUDA(cudaFuncSetAttribute(featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (n_frames + ft - 1) / ft;
   int grid = (int)(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
