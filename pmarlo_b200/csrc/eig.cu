@@ -103,13 +103,16 @@ struct LanParams {
   double* ritz;        // 2 x m
 };
 
+// Sum of the per-CTA partials, evaluated by every warp with the loads spread over its lanes (fixed lane
+// assignment and shuffle tree: the same value in every warp of the grid).  A per-thread sequential loop over
+// the 125 partials was a chain of 125 dependent L2 round trips and took a quarter of the kernel (ncu).
 __device__ __forceinline__ double grid_sum_partials(const double* part, int n) {
   double r = 0.0;
-  for (int i = 0; i < n; ++i) r += __ldcg(part + i);
-  return r;
+  for (int i = threadIdx.x & 31; i < n; i += 32) r += __ldcg(part + i);
+  return warp_sum(r);
 }
 
-__global__ void __launch_bounds__(kLanThreads) lanczos_kernel(LanParams p) {
+__global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double s_red[32];
   __shared__ int s_order[1024];
@@ -160,8 +163,17 @@ __global__ void __launch_bounds__(kLanThreads) lanczos_kernel(LanParams p) {
       double s = 0.0;
       if (pe > 0.0) {
         const double* Trow = p.T + (size_t)i * K;
-        for (int c = lane; c < K; c += 32) s = fma(Trow[c], __ldcg(p.z + c), s);
-        s = warp_sum(s) * sqrt(pe);
+        // four independent accumulators: four L2 round trips in flight instead of one
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int c = lane;
+        for (; c + 96 < K; c += 128) {
+          s = fma(Trow[c], __ldcg(p.z + c), s);
+          s1 = fma(Trow[c + 32], __ldcg(p.z + c + 32), s1);
+          s2 = fma(Trow[c + 64], __ldcg(p.z + c + 64), s2);
+          s3 = fma(Trow[c + 96], __ldcg(p.z + c + 96), s3);
+        }
+        for (; c < K; c += 32) s = fma(Trow[c], __ldcg(p.z + c), s);
+        s = warp_sum((s + s1) + (s2 + s3)) * sqrt(pe);
       }
       if (lane == 0) p.w[i] = s;
     }
@@ -173,8 +185,16 @@ __global__ void __launch_bounds__(kLanThreads) lanczos_kernel(LanParams p) {
       for (int i = gwarp; i <= j; i += nwarps) {
         const double* vi = p.V + (size_t)i * K;
         double s = 0.0;
-        for (int c = lane; c < K; c += 32) s = fma(__ldcg(vi + c), __ldcg(p.w + c), s);
-        s = warp_sum(s);
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int c = lane;
+        for (; c + 96 < K; c += 128) {
+          s = fma(__ldcg(vi + c), __ldcg(p.w + c), s);
+          s1 = fma(__ldcg(vi + c + 32), __ldcg(p.w + c + 32), s1);
+          s2 = fma(__ldcg(vi + c + 64), __ldcg(p.w + c + 64), s2);
+          s3 = fma(__ldcg(vi + c + 96), __ldcg(p.w + c + 96), s3);
+        }
+        for (; c < K; c += 32) s = fma(__ldcg(vi + c), __ldcg(p.w + c), s);
+        s = warp_sum((s + s1) + (s2 + s3));
         if (lane == 0) h[i] = s;
       }
       grid.sync();
@@ -182,7 +202,16 @@ __global__ void __launch_bounds__(kLanThreads) lanczos_kernel(LanParams p) {
       double nn = 0.0;
       for (int e = gtid; e < K; e += gthreads) {
         double v = __ldcg(p.w + e);
-        for (int i = 0; i <= j; ++i) v = fma(-__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), v);
+        double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        int i = 0;
+        for (; i + 3 <= j; i += 4) {
+          v = fma(-__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), v);
+          v1 = fma(-__ldcg(h + i + 1), __ldcg(p.V + (size_t)(i + 1) * K + e), v1);
+          v2 = fma(-__ldcg(h + i + 2), __ldcg(p.V + (size_t)(i + 2) * K + e), v2);
+          v3 = fma(-__ldcg(h + i + 3), __ldcg(p.V + (size_t)(i + 3) * K + e), v3);
+        }
+        for (; i <= j; ++i) v = fma(-__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), v);
+        v += (v1 + v2) + v3;
         p.w[e] = v;
         nn = fma(v, v, nn);
       }
