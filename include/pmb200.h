@@ -201,6 +201,20 @@ PMB_API int pmb_count_lagged_weighted(const int32_t* labels, const double* weigh
                               const int64_t* seg_offsets, int n_seg, int K, int lag,
                               int step, double* C, pmb_stream_t stream);
 
+/* ---- state relabelling with frame removal (Chapman-Kolmogorov test) -------------
+ * Replaces the per-frame Python loops
+ *   [state_map[s] for s in traj if s in state_map]   ck_runner.py:150-153, :235-238, _ck.py:86-90
+ *   macro_labels[traj]                                 ck_runner.py:204
+ * labels_out receives, in order, lut[labels[t]] for every frame with 0 <= labels[t] < n_lut and
+ * lut[labels[t]] >= 0; the other frames are dropped.  new_seg_offsets (n_seg + 1, device) are the shard
+ * offsets of the shortened trajectories, new_seg_offsets[n_seg] = frames kept.  seg_offsets must start at
+ * 0 and end at n.  labels_out has room for n entries and must not alias labels. */
+PMB_API size_t pmb_relabel_compact_ws_bytes(int64_t n);
+PMB_API int pmb_relabel_compact(const int32_t* labels, int64_t n, const int64_t* seg_offsets, int n_seg,
+                        const int32_t* lut, int n_lut, int32_t* labels_out,
+                        int64_t* new_seg_offsets, void* workspace, size_t workspace_bytes,
+                        pmb_stream_t stream);
+
 /* int64 counts -> fp64 matrix + active mask (utils/msm_utils.py:150-156):
  * active[i] = (rowsum_i + colsum_i > eps).  Cf: K x K fp64, active: K bytes. */
 PMB_API int pmb_counts_active(const int64_t* C, int K, double eps, double* Cf, uint8_t* active,

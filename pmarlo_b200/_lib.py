@@ -47,6 +47,8 @@ PROTOTYPES = {
     "pmb_kmeans_update": (_i32, [_p, _p, _p, _i32, _i32, _p, _p]),
     "pmb_count_lagged": (_i32, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "pmb_count_lagged_weighted": (_i32, [_p, _p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p]),
+    "pmb_relabel_compact_ws_bytes": (_sz, [_i64]),
+    "pmb_relabel_compact": (_i32, [_p, _i64, _p, _i32, _p, _i32, _p, _p, _p, _sz, _p]),
     "pmb_tc_selftest": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p]),
     "pmb_mle_rev_ws_bytes": (_sz, [_i32, _i32]),
     "pmb_mle_rev": (_i32, [_p, _p, _i32, _i32, _f64, _f64, _i64, _p, _p, _p, _p, _sz, _p]),

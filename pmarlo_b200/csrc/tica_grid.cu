@@ -20,7 +20,7 @@ constexpr double kTgTol = 4.5e-16;  // x sqrt(n), as in tica.cu
 struct TicaGridWs {
   double *W, *V, *L, *TMP, *M, *s;
   int* order;
-  int* ctrl;  // [0] rank m, [1..2] sweep flags, [3] spare
+  int* ctrl;  // [0] rank m, [1..2] sweep flags, [4..5] big-rotation flags
 };
 
 __device__ __forceinline__ double ldg_cg(const double* p) { return __ldcg(p); }
@@ -28,28 +28,23 @@ __device__ __forceinline__ double ldg_cg(const double* p) { return __ldcg(p); }
 // phase cycle counters of the last solve (CTA 0, thread 0): load, local sweep, store, grid barrier, total, block rounds
 __device__ long long g_tg_dbg[8];
 
-// 1/sqrt(x) and 1/x for x in [2^-8, 2^8]: fp32 seed (MUFU) + two fp64 Newton steps.  The IEEE fp64
-// divide / sqrt sequences cost ~300 dependent cycles each, and the rotation angle sits on the critical
-// path of every Jacobi round; these are ~100 cycles and accurate to a few ulp.
+// 1/sqrt(x) for x in [2^-8, 2^8]: fp32 seed (MUFU) and ONE third-order step, y <- y (1 + e/2 + 3 e^2 / 8) with
+// e = 1 - x y^2 ~ 2^-21, error O(e^3).  The IEEE fp64 divide / sqrt sequences cost ~300 dependent cycles
+// each and the rotation sits on the critical path of every Jacobi round (ncu: the round is bound by the
+// dependent fp64 chain -- 'wait' and 'short_scoreboard' stalls -- not by fp64 throughput); this is 7
+// dependent instructions and accurate to a few ulp.
 __device__ __forceinline__ double tg_rsqrt(double x) {
-  double y = (double)rsqrtf((float)x);
-  double e = fma(-x * y, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  e = fma(-x * y, y, 1.0);
-  return fma(0.5 * y, e, y);
+  const double y = (double)rsqrtf((float)x);
+  const double e = fma(-x * y, y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 }
-__device__ __forceinline__ double tg_rcp(double x) {
-  double y = (double)__frcp_rn((float)x);
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
-}
-// Rotation (c, s) that orthogonalises two rows with squared norms a, b and inner product g != 0:
-// t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2 g), written without a division:
-// t = sign(alpha) g / (|alpha| + sqrt(alpha^2 + g^2)), alpha = (b - a) / 2, after scaling alpha and g
-// by a power of two so that the fp32 seeds cannot under- or overflow.
-__device__ __forceinline__ void tg_rotation(double a, double b, double g, double& c, double& s) {
+// Rotation (c, s), t = s / c = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2 g), that
+// orthogonalises two rows with squared norms a, b and inner product g != 0.  With alpha = (b - a) / 2 and
+// r = sqrt(alpha^2 + g^2) the double angle has cos = |alpha| / r and sin = sign(alpha) g / r, so
+//   c^2 = (1 + |alpha| / r) / 2,   s = sign(alpha) g / (2 r c):
+// two reciprocal square roots, no division, no cancellation.  alpha and g are first scaled by a power of
+// two so that the fp32 seeds cannot under- or overflow.
+__device__ __forceinline__ void tg_rotation(double a, double b, double g, double& c, double& s, double& t_out) {
   const double alpha = 0.5 * (b - a);
   const double mx = fmax(fabs(alpha), fabs(g));
   const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
@@ -58,35 +53,42 @@ __device__ __forceinline__ void tg_rotation(double a, double b, double g, double
     const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     c = 1.0 / sqrt(1.0 + t * t);
     s = c * t;
+    t_out = t;
     return;
   }
   const double sc = __hiloint2double((2046 - ex) << 20, 0);   // 2^(1023 - ex): mx * sc in [1, 2)
   const double as = alpha * sc, gs = g * sc;
-  const double q = fma(as, as, gs * gs);                      // [1, 8)
-  const double r = q * tg_rsqrt(q);
-  const double inv = tg_rcp(fabs(as) + r);
-  const double t = ((__double2hiint(alpha) < 0) ? -gs : gs) * inv;
-  c = tg_rsqrt(fma(t, t, 1.0));
-  s = c * t;
+  const double y = tg_rsqrt(fma(as, as, gs * gs));            // 1 / r, r^2 in [1, 8)
+  const double c2 = fma(0.5 * fabs(as), y, 0.5);              // [0.5, 1]
+  const double z = tg_rsqrt(c2);
+  c = c2 * z;
+  const double h = 0.5 * gs * y * z;
+  s = (__double2hiint(alpha) < 0) ? -h : h;
+  t_out = s * z;   // z = 1 / c
 }
 
-// One-sided BLOCK Jacobi on the rows of W (n x n, symmetric input), rotations accumulated in V.
-// The rows are cut into blocks of `b`; a CTA takes one block PAIR per block round (round-robin
-// tournament over the blocks), loads its 2b rows of W and V into shared memory, runs one complete
-// cyclic sweep over those 2b rows there (2b - 1 local rounds separated by __syncthreads, one warp
-// per row pair) and writes them back.  A sweep therefore costs nb - 1 grid barriers instead of
-// n - 1, and every rotation works on shared memory instead of L2.
+// One-sided BLOCK Jacobi on the rows of W (n x n, symmetric input); the rotations are not accumulated.
+// The rows are cut into blocks of `b`.  A sweep visits every row pair exactly once:
+//   A. every block on its own CTA: the b (b - 1) / 2 pairs inside the block (b - 1 local rounds of a
+//      round-robin tournament, b / 2 warps busy), then one grid barrier;
+//   B. nb - 1 block rounds (round-robin tournament over the blocks), a CTA per block PAIR: it loads its
+//      2 b rows into shared memory and orthogonalises every row of one block against every row of the
+//      other -- b local rounds, in round lr row i meets row (i + lr) mod b, one warp per pair, separated
+//      by __syncthreads -- writes them back, grid barrier.
+// The sequential depth of a sweep is (nb - 1) b + (b - 1) = n - 1 local rounds, the minimum for n rows,
+// with nb grid barriers instead of n - 1, and every rotation works on shared memory instead of L2.
+// (Sweeping ALL pairs of the 2 b resident rows in every block round, 2 b - 1 local rounds, repeats the
+// in-block pairs nb - 1 times per sweep: 1.8x the depth for the same number of sweeps.)
 // NPL = elements of a row per lane (n <= 32 NPL): the loops are fully unrolled, a warp holds its two
-// rows of W and V in registers for the duration of a rotation and the global loads are batched.
+// rows in registers for the duration of a rotation and the global loads are batched.
 template <int NPL>
-__device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, int b, int* flags, double* sm) {
+__device__ int jacobi_grid(cg::grid_group& grid, double* W, int n, int b, int* flags, double* sm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   int nb = (n + b - 1) / b;
   if (nb & 1) ++nb;
   if (nb < 2) nb = 2;
-  const int npairs = nb >> 1, rows = 2 * b;
+  const int npairs = nb >> 1;
   double* sW = sm;
-  double* sV = sm + (size_t)rows * n;
   const double tol2 = kTgTol * kTgTol * (double)n;
   // flags[0..1]: "some pair was rotated" per sweep parity; flags[3..4]: "some rotated pair had a relative
   // off-diagonal |g| / sqrt(a b) above 1e-10", also per sweep parity
@@ -95,122 +97,236 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, in
   grid.sync();
   int sweep = 0;
   long long cyc[4] = {0, 0, 0, 0}, n_rounds = 0;
-  for (; sweep < kTgMaxSweeps; ++sweep) {
-    int rotated = 0;
-    int big = 0;
-    for (int r = 0; r < nb - 1; ++r) {
-      long long t0 = clock64();
-      for (int k = blockIdx.x; k < npairs; k += gridDim.x) {
-        int bi, bj;
-        if (k == 0) { bi = nb - 1; bj = r; }
-        else { bi = (r + k) % (nb - 1); bj = (r - k + (nb - 1)) % (nb - 1); }
-        if (bi > bj) { const int t = bi; bi = bj; bj = t; }
-        auto grow = [&](int li) { return li < b ? bi * b + li : bj * b + (li - b); };
-        for (int li = warp; li < rows; li += nwarps) {
-          const int gr = grow(li);
-          if (gr < n) {
-            double tw[NPL], tv[NPL];
+  int rotated = 0, big = 0;
+
+  // global row of local row li when blocks bi (local rows 0..b-1) and bj (b..2b-1) are resident
+  auto grow = [&](int bi, int bj, int li) { return li < b ? bi * b + li : bj * b + (li - b); };
+  auto load_rows = [&](int bi, int bj, int rows) {
+    for (int li = warp; li < rows; li += nwarps) {
+      const int gr = grow(bi, bj, li);
+      if (gr < n) {
+        double tw[NPL];
 #pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-              const int e = lane + 32 * q;
-              tw[q] = e < n ? ldg_cg(W + (size_t)gr * n + e) : 0.0;
-              tv[q] = (V != nullptr && e < n) ? ldg_cg(V + (size_t)gr * n + e) : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-              const int e = lane + 32 * q;
-              if (e < n) {
-                sW[(size_t)li * n + e] = tw[q];
-                if (V != nullptr) sV[(size_t)li * n + e] = tv[q];
-              }
-            }
-          }
+        for (int q = 0; q < NPL; ++q) {
+          const int e = lane + 32 * q;
+          tw[q] = e < n ? ldg_cg(W + (size_t)gr * n + e) : 0.0;
         }
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+          const int e = lane + 32 * q;
+          if (e < n) sW[(size_t)li * n + e] = tw[q];
+        }
+      }
+    }
+  };
+  auto store_rows = [&](int bi, int bj, int rows) {
+    for (int li = warp; li < rows; li += nwarps) {
+      const int gr = grow(bi, bj, li);
+      if (gr < n) {
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+          const int e = lane + 32 * q;
+          if (e < n) __stcg(W + (size_t)gr * n + e, sW[(size_t)li * n + e]);
+        }
+      }
+    }
+  };
+  // orthogonalise local rows lp, lq (global rows gp, gq, both < n)
+  auto rotate_pair = [&](int lp, int lq, int gp, int gq) {
+    if (gp > gq) { const int t = lp; lp = lq; lq = t; }
+    double* wp = sW + (size_t)lp * n;
+    double* wq = sW + (size_t)lq * n;
+    double x[NPL], y[NPL];
+    double a = 0.0, bb = 0.0, g = 0.0;
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) {
+      const int e = lane + 32 * q;
+      x[q] = e < n ? wp[e] : 0.0;
+      y[q] = e < n ? wq[e] : 0.0;
+    }
+    {
+      // two accumulators per sum: half the dependent fp64 chain
+      double a1 = 0.0, b1 = 0.0, g1 = 0.0;
+#pragma unroll
+      for (int q = 0; q + 1 < NPL; q += 2) {
+        a = fma(x[q], x[q], a);
+        bb = fma(y[q], y[q], bb);
+        g = fma(x[q], y[q], g);
+        a1 = fma(x[q + 1], x[q + 1], a1);
+        b1 = fma(y[q + 1], y[q + 1], b1);
+        g1 = fma(x[q + 1], y[q + 1], g1);
+      }
+      if (NPL & 1) {
+        a = fma(x[NPL - 1], x[NPL - 1], a);
+        bb = fma(y[NPL - 1], y[NPL - 1], bb);
+        g = fma(x[NPL - 1], y[NPL - 1], g);
+      }
+      a += a1;
+      bb += b1;
+      g += g1;
+    }
+    a = warp_sum(a);
+    bb = warp_sum(bb);
+    g = warp_sum(g);
+    if (g * g <= tol2 * (a * bb) || g == 0.0) return;
+    rotated = 1;
+    if (g * g > 1e-20 * (a * bb)) big = 1;
+    double c, s, t_unused;
+    tg_rotation(a, bb, g, c, s, t_unused);
+    // de Rijk's ordering: the row with the larger norm goes first (rotation followed by a swap when
+    // a < b); helps on graded matrices such as a covariance with eigenvalues over 8 decades.
+    const bool sw = a < bb;
+    const double c0 = sw ? s : c, s0 = sw ? c : -s;    // row p <- c0 x + s0 y
+    const double c1 = sw ? c : s, s1 = sw ? -s : c;    // row q <- c1 x + s1 y
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) {
+      const int e = lane + 32 * q;
+      if (e < n) {
+        wp[e] = c0 * x[q] + s0 * y[q];
+        wq[e] = c1 * x[q] + s1 * y[q];
+      }
+    }
+  };
+
+  for (; sweep < kTgMaxSweeps; ++sweep) {
+    rotated = 0;
+    big = 0;
+    // A. pairs inside a block
+    long long t0 = clock64();
+    if (b >= 2) {
+      for (int k = blockIdx.x; k < nb; k += gridDim.x) {
+        load_rows(k, k, b);
         __syncthreads();
         const long long t1 = clock64();
         cyc[0] += t1 - t0;
-        const int lm = rows - 1;   // local tournament over `rows` players (rows is even)
+        const int lm = b - 1;   // tournament over b players (b is a power of two)
         for (int lr = 0; lr < lm; ++lr) {
-          for (int kk = warp; kk < b; kk += nwarps) {
+          for (int kk = warp; kk < (b >> 1); kk += nwarps) {
             int lp, lq;
             if (kk == 0) { lp = lm; lq = lr; }
             else { lp = (lr + kk) % lm; lq = (lr - kk + lm) % lm; }
-            int gp = grow(lp), gq = grow(lq);
-            if (gp >= n || gq >= n) continue;
-            if (gp > gq) { const int t = lp; lp = lq; lq = t; }
-            double* wp = sW + (size_t)lp * n;
-            double* wq = sW + (size_t)lq * n;
-            double x[NPL], y[NPL];
-            double a = 0.0, bb = 0.0, g = 0.0;
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-              const int e = lane + 32 * q;
-              x[q] = e < n ? wp[e] : 0.0;
-              y[q] = e < n ? wq[e] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-              a = fma(x[q], x[q], a);
-              bb = fma(y[q], y[q], bb);
-              g = fma(x[q], y[q], g);
-            }
-            a = warp_sum(a);
-            bb = warp_sum(bb);
-            g = warp_sum(g);
-            if (g * g <= tol2 * (a * bb) || g == 0.0) continue;
-            rotated = 1;
-            if (g * g > 1e-20 * (a * bb)) big = 1;
-            double c, s;
-            tg_rotation(a, bb, g, c, s);
-            // de Rijk's ordering: the row with the larger norm goes first (rotation followed by a swap when
-            // a < b); helps on graded matrices such as a covariance with eigenvalues over 8 decades.
-            const bool sw = a < bb;
-            const double c0 = sw ? s : c, s0 = sw ? c : -s;    // row p <- c0 x + s0 y
-            const double c1 = sw ? c : s, s1 = sw ? -s : c;    // row q <- c1 x + s1 y
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-              const int e = lane + 32 * q;
-              if (e < n) {
-                wp[e] = c0 * x[q] + s0 * y[q];
-                wq[e] = c1 * x[q] + s1 * y[q];
-              }
-            }
-            if (V != nullptr) {
-              double* vp = sV + (size_t)lp * n;
-              double* vq = sV + (size_t)lq * n;
-#pragma unroll
-              for (int q = 0; q < NPL; ++q) {
-                const int e = lane + 32 * q;
-                x[q] = e < n ? vp[e] : 0.0;
-                y[q] = e < n ? vq[e] : 0.0;
-              }
-#pragma unroll
-              for (int q = 0; q < NPL; ++q) {
-                const int e = lane + 32 * q;
-                if (e < n) {
-                  vp[e] = c0 * x[q] + s0 * y[q];
-                  vq[e] = c1 * x[q] + s1 * y[q];
-                }
-              }
-            }
+            const int gp = k * b + lp, gq = k * b + lq;
+            if (gp < n && gq < n) rotate_pair(lp, lq, gp, gq);
           }
           __syncthreads();
         }
         const long long t2 = clock64();
         cyc[1] += t2 - t1;
-        for (int li = warp; li < rows; li += nwarps) {
-          const int gr = grow(li);
-          if (gr < n) {
+        store_rows(k, k, b);
+        __syncthreads();
+        t0 = clock64();
+        cyc[2] += t0 - t2;
+      }
+      grid.sync();
+      cyc[3] += clock64() - t0;
+      ++n_rounds;
+    }
+    // B. pairs across two blocks
+    for (int r = 0; r < nb - 1; ++r) {
+      t0 = clock64();
+      for (int k = blockIdx.x; k < npairs; k += gridDim.x) {
+        int bi, bj;
+        if (k == 0) { bi = nb - 1; bj = r; }
+        else { bi = (r + k) % (nb - 1); bj = (r - k + (nb - 1)) % (nb - 1); }
+        if (bi > bj) { const int t = bi; bi = bj; bj = t; }
+        load_rows(bi, bj, 2 * b);
+        __syncthreads();
+        const long long t1 = clock64();
+        cyc[0] += t1 - t0;
+        if (b <= nwarps) {
+          // Warp kk keeps row kk of block bi in REGISTERS for all b local rounds (its partner changes, it
+          // does not), and the squared norms travel with the rows -- exact at the start of the block round,
+          // then updated by a' = a - t g, b' = b + t g -- so a local round moves one row instead of two
+          // through shared memory and reduces one inner product instead of three.  (ncu: the round was
+          // bound by the LDS / STS / SHFL issue rate of the SM, not by fp64 throughput.)
+          double* sN = sW + (size_t)2 * b * n;   // b squared norms of the rows of bj
+          const int kk = warp;
+          const int gp = bi * b + kk;
+          const bool have_p = kk < b && gp < n;
+          double x[NPL];
+          double a = 0.0;
+          if (kk < b) {
+            double bn = 0.0;
+            const double* wp = sW + (size_t)kk * n;
+            const double* wq = sW + (size_t)(b + kk) * n;
 #pragma unroll
             for (int q = 0; q < NPL; ++q) {
               const int e = lane + 32 * q;
-              if (e < n) {
-                __stcg(W + (size_t)gr * n + e, sW[(size_t)li * n + e]);
-                if (V != nullptr) __stcg(V + (size_t)gr * n + e, sV[(size_t)li * n + e]);
+              x[q] = e < n ? wp[e] : 0.0;
+              const double yv = e < n ? wq[e] : 0.0;
+              a = fma(x[q], x[q], a);
+              bn = fma(yv, yv, bn);
+            }
+            a = warp_sum(a);
+            bn = warp_sum(bn);
+            if (lane == 0) sN[kk] = bn;
+          }
+          __syncthreads();
+          for (int lr = 0; lr < b; ++lr) {
+            int lq = kk + lr;
+            if (lq >= b) lq -= b;
+            if (have_p && bj * b + lq < n) {
+              double* wq = sW + (size_t)(b + lq) * n;
+              const double bb = sN[lq];
+              double y[NPL];
+              double g = 0.0, g1 = 0.0;
+#pragma unroll
+              for (int q = 0; q < NPL; ++q) {
+                const int e = lane + 32 * q;
+                y[q] = e < n ? wq[e] : 0.0;
+              }
+#pragma unroll
+              for (int q = 0; q + 1 < NPL; q += 2) {
+                g = fma(x[q], y[q], g);
+                g1 = fma(x[q + 1], y[q + 1], g1);
+              }
+              if (NPL & 1) g = fma(x[NPL - 1], y[NPL - 1], g);
+              g = warp_sum(g + g1);
+              if (!(g * g <= tol2 * (a * bb) || g == 0.0)) {
+                rotated = 1;
+                if (g * g > 1e-20 * (a * bb)) big = 1;
+                double c, s, t;
+                tg_rotation(a, bb, g, c, s, t);
+                const bool sw = a < bb;                            // de Rijk: the larger norm goes to row p
+                const double c0 = sw ? s : c, s0 = sw ? c : -s;    // row p <- c0 x + s0 y
+                const double c1 = sw ? c : s, s1 = sw ? -s : c;    // row q <- c1 x + s1 y
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) {
+                  const int e = lane + 32 * q;
+                  const double xn = c0 * x[q] + s0 * y[q];
+                  if (e < n) wq[e] = c1 * x[q] + s1 * y[q];
+                  x[q] = xn;
+                }
+                const double lo = fmax(a - t * g, 0.0), hi = fmax(bb + t * g, 0.0);   // |c x - s y|^2, |s x + c y|^2
+                a = sw ? hi : lo;
+                if (lane == 0) sN[lq] = sw ? lo : hi;
               }
             }
+            __syncthreads();
+          }
+          if (have_p) {
+            double* wp = sW + (size_t)kk * n;
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+              const int e = lane + 32 * q;
+              if (e < n) wp[e] = x[q];
+            }
+          }
+          __syncthreads();
+        } else {
+          for (int lr = 0; lr < b; ++lr) {
+            for (int kk = warp; kk < b; kk += nwarps) {
+              int lq = kk + lr;
+              if (lq >= b) lq -= b;
+              const int gp = bi * b + kk, gq = bj * b + lq;
+              if (gp < n && gq < n) rotate_pair(kk, b + lq, gp, gq);
+            }
+            __syncthreads();
           }
         }
+        const long long t2 = clock64();
+        cyc[1] += t2 - t1;
+        store_rows(bi, bj, 2 * b);
         __syncthreads();
         t0 = clock64();
         cyc[2] += t0 - t2;
@@ -234,32 +350,29 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, double* V, int n, in
     if (!any || !anybig) { ++sweep; break; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const int base = (V != nullptr && g_tg_dbg[7] == 1) ? 0 : 0;
-    (void)base;
     for (int q = 0; q < 4; ++q) g_tg_dbg[q] += cyc[q];
     g_tg_dbg[4] += n_rounds;
   }
   return sweep;
 }
 
-// order[rk] = index of the rk-th largest |vals| (stable); CTA 0 only, followed by a grid barrier
+// order[rk] = index of the rk-th largest |vals| (stable); one value per thread over the grid, then a grid barrier
 __device__ void rank_grid(cg::grid_group& grid, const double* vals, int n, int* order) {
-  if (blockIdx.x == 0) {
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const double aj = fabs(ldg_cg(vals + j));
-      int rk = 0;
-      for (int i = 0; i < n; ++i) {
-        const double ai = fabs(ldg_cg(vals + i));
-        rk += (ai > aj) || (ai == aj && i < j);
-      }
-      order[rk] = j;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const double aj = fabs(ldg_cg(vals + j));
+    int rk = 0;
+#pragma unroll 8
+    for (int i = 0; i < n; ++i) {
+      const double ai = fabs(ldg_cg(vals + i));
+      rk += (ai > aj) || (ai == aj && i < j);
     }
+    order[rk] = j;
   }
   grid.sync();
 }
 
 template <int NPL>
-__global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
+__global__ void __launch_bounds__(kTgThreads, 1) tica_solve_grid_kernel(
     const double* __restrict__ C00, const double* __restrict__ C0t, int d, double eps,
     double* __restrict__ evals, double* __restrict__ evecs, int32_t* __restrict__ rank_out, TicaGridWs ws,
     int blk) {
@@ -282,7 +395,7 @@ __global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
   // signed eigenvalue is the Rayleigh quotient v_j^T C00 v_j.  (Rows whose norm is at rounding level carry no
   // direction; they get eigenvalue 0 and are removed by the rank cut.)  This halves the shared-memory
   // traffic that bounds a local Jacobi round.
-  const int sweeps1 = jacobi_grid<NPL>(grid, ws.W, nullptr, d, blk, ws.ctrl + 1, tg_sm);
+  const int sweeps1 = jacobi_grid<NPL>(grid, ws.W, d, blk, ws.ctrl + 1, tg_sm);
   for (int j = gwarp; j < d; j += nwarps) {
     double acc = 0.0;
     for (int e = lane; e < d; e += 32) { const double w = ldg_cg(ws.W + (size_t)j * d + e); acc = fma(w, w, acc); }
@@ -418,7 +531,7 @@ __global__ void __launch_bounds__(kTgThreads) tica_solve_grid_kernel(
   }
   grid.sync();
   // W = sym(M) + sigma I is positive definite: eigenvalue_j = |w_j| - sigma, v_j = w_j / |w_j|
-  const int sweeps2 = jacobi_grid<NPL>(grid, ws.W, nullptr, m, blk, ws.ctrl + 1, tg_sm);
+  const int sweeps2 = jacobi_grid<NPL>(grid, ws.W, m, blk, ws.ctrl + 1, tg_sm);
   for (int j = gwarp; j < m; j += nwarps) {
     double acc = 0.0;
     for (int e = lane; e < m; e += 32) { const double w = ldg_cg(ws.W + (size_t)j * m + e); acc = fma(w, w, acc); }
@@ -480,10 +593,10 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   int dev = 0, sms = 0, per_sm = 0;
   PMB_CUDA(cudaGetDevice(&dev));
   PMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // rows per block: the 2 b rows of W and of V (n doubles each) must fit in shared memory
+  // rows per block: the 2 b rows of a block pair (d doubles each) must fit in shared memory
   int blk = 16;
-  while (blk > 1 && (size_t)4 * blk * d * sizeof(double) > (size_t)200 * 1024) blk >>= 1;
-  const size_t smem = (size_t)4 * blk * d * sizeof(double);
+  while (blk > 1 && (size_t)2 * blk * d * sizeof(double) > (size_t)200 * 1024) blk >>= 1;
+  const size_t smem = (size_t)2 * blk * (d + 1) * sizeof(double);   // rows + their squared norms
   PMB_REQUIRE(smem <= (size_t)227 * 1024, "pmb_tica_solve: d=%d too large for the block-Jacobi kernel", d);
   void* kern = nullptr;
   if (d <= 64) kern = (void*)tica_solve_grid_kernel<2>;
@@ -501,8 +614,11 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   int nb = (d + blk - 1) / blk;
   if (nb & 1) ++nb;
   // One CTA per SM even though only nb / 2 of them own a block pair: the others join the grid barriers and
-  // the dense phases.  (With 8 busy SMs out of 148 the measured SM clock during this kernel dropped to
-  // 0.7-1.4 GHz on some runs -- same cycle count, up to 3x the wall time.)
+  // the dense phases.  The wall time of this kernel is bimodal between (and sometimes within) processes on
+  // the same GPU: identical clock64 cycle count, but an effective SM clock of 0.6-1.2 GHz instead of
+  // 1.96 GHz in the slow state.  A grid of 8 CTAs made it worse; a hand-written arrival-counter barrier and
+  // keeping the idle SMs busy with FMA chains (light or heavy) did not remove it (A/B on one box, round 1),
+  // so the plain cooperative-groups barrier stays and the remedy is the cycle count itself.
   int grid = sms;
   if (grid < nb / 2) grid = nb / 2;
   if (grid > sms * per_sm) grid = sms * per_sm;

@@ -79,7 +79,8 @@ class EnhancedMSM:
     """The estimation / ITS slice of pmarlo's ``EnhancedMSM`` (markov_state_model/enhanced_msm.py)."""
 
     def __init__(self, dtrajs: Sequence[np.ndarray] | None = None, n_states: int | None = None,
-                 count_mode: str = "sliding", random_state: int | None = None, temperature: float = 300.0):
+                 count_mode: str = "sliding", random_state: int | None = None, temperature: float = 300.0,
+                 output_dir: str | None = None):
         self.dtrajs: List[np.ndarray] = [np.asarray(d) for d in (dtrajs or [])]
         self.n_states = infer_n_states(self.dtrajs, n_states)
         self.count_mode = str(count_mode)
@@ -93,6 +94,7 @@ class EnhancedMSM:
         self.free_energies = None
         self.implied_timescales = None
         self.estimator_backend = "b200"
+        self.output_dir = output_dir
 
     # ---------------------------------------------------------------- build_msm
     def build_msm(self, lag_time: int = 20, method: str = "standard") -> None:
@@ -184,6 +186,29 @@ class EnhancedMSM:
         if plateau_m is not None:
             result.recommended_lag_window = _plateau_window(lags, ts, int(plateau_m), float(plateau_epsilon))
         self.implied_timescales = result
+
+
+def _ck_methods():
+    """``CKMixin`` (_ck.py:61-110, 159-175) on the device kernels; see pmarlo_b200/ck.py."""
+    from . import ck
+
+    def compute_ck_test_micro(self, factors: Optional[List[int]] = None, max_states: int = 50,
+                              min_transitions: int = 5) -> "ck.CKTestResult":
+        return ck.compute_ck_test_micro(self.dtrajs, int(self.n_states), int(self.lag_time), factors,
+                                        max_states, min_transitions)
+
+    def select_lag_time_ck(self, tau_candidates: List[int], factor: int = 2, mse_epsilon: float = 0.05) -> int:
+        selected, _, _, _ = ck.select_lag_time_ck(self.dtrajs, int(self.n_states), tau_candidates, factor,
+                                                  mse_epsilon, output_dir=self.output_dir)
+        self.lag_time = int(selected)
+        print(f"Selected τ = {int(selected)}")       # _ck.py:261
+        return int(selected)
+
+    EnhancedMSM.compute_ck_test_micro = compute_ck_test_micro
+    EnhancedMSM.select_lag_time_ck = select_lag_time_ck
+
+
+_ck_methods()
 
 
 def _plateau_window(lags: Sequence[int], ts: np.ndarray, m: int, eps: float):

@@ -281,6 +281,23 @@ def count_lagged_weighted(labels, weights, seg_offsets, K: int, lag: int, step: 
     return out
 
 
+def relabel_compact(labels: torch.Tensor, seg_offsets: torch.Tensor, lut: torch.Tensor):
+    """``[lut[s] for s in traj if lut[s] >= 0]`` for every shard (ck_runner.py:150-153): returns the
+    shortened label shard (int32, device) and its offsets (int64, device, length n_seg + 1)."""
+    _dev(labels, torch.int32, "labels")
+    _dev(seg_offsets, torch.int64, "seg_offsets")
+    _dev(lut, torch.int32, "lut")
+    n, n_seg = int(labels.numel()), int(seg_offsets.numel()) - 1
+    out = torch.empty((max(n, 1),), dtype=torch.int32, device=labels.device)
+    new_off = torch.empty((n_seg + 1,), dtype=torch.int64, device=labels.device)
+    nbytes = int(_lib.lib().pmb_relabel_compact_ws_bytes(n))
+    ws = _ws(nbytes, labels.device)
+    check(_lib.lib().pmb_relabel_compact(ptr(labels), n, ptr(seg_offsets), n_seg, ptr(lut), int(lut.numel()),
+                                         ptr(out), ptr(new_off), ptr(ws), nbytes,
+                                         stream_handle(labels.device)), "pmb_relabel_compact")
+    return out, new_off
+
+
 def counts_active(C: torch.Tensor, eps: float = 1e-12):
     """int64 counts -> (fp64 counts, active mask uint8)."""
     _dev(C, torch.int64, "C")

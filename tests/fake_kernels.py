@@ -154,6 +154,17 @@ def count_lagged(labels, seg_offsets, K, lag, step=1, out=None):
     return out
 
 
+def relabel_compact(labels, seg_offsets, lut):
+    off, lab, table = _np(seg_offsets), _np(labels).astype(np.int64), _np(lut).astype(np.int64)
+    ok = (lab >= 0) & (lab < table.size)
+    m = np.where(ok, table[np.clip(lab, 0, table.size - 1)], -1)
+    keep = m >= 0
+    before = np.concatenate([[0], np.cumsum(keep)])
+    out = np.zeros(max(lab.size, 1), dtype=np.int32)
+    out[: int(keep.sum())] = m[keep]
+    return torch.from_numpy(out), torch.from_numpy(before[off].astype(np.int64))
+
+
 def counts_active(C, eps=1e-12):
     c = _np(C).astype(np.float64)
     act = ((c.sum(0) + c.sum(1)) > eps).astype(np.uint8)
@@ -183,7 +194,8 @@ def install(monkeypatch_or_module):
     from pmarlo_b200 import kernels
 
     names = ["pair_mask", "col_moments", "scaler_from_moments", "gram", "tica_covariances", "tica_solve",
-             "tica_finalize", "project", "kmeans_assign", "kmeans_update", "count_lagged", "counts_active",
+             "tica_finalize", "project", "kmeans_assign", "kmeans_update", "count_lagged", "relabel_compact",
+             "counts_active",
              "mle_rev", "eig_rev_topk"]
     for n in names:
         if hasattr(monkeypatch_or_module, "setattr"):

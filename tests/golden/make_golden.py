@@ -18,6 +18,8 @@ It imports the reference functions that run without deeptime/mdtraj
                      used only as a loose cross-check of the oracle
 * assign.npz      -- analysis.discretize._KMeansDiscretizer fit/transform
                      (discretize.py:406-514; sklearn KMeans.predict labels)
+* ck.npz          -- markov_state_model.ck_runner.run_ck (ck_runner.py:293-332) and
+                     CKMixin.compute_ck_test_micro / select_lag_time_ck (_ck.py:61-228)
 * topologies.npz  -- atom names / residue ids / coordinates (nm) parsed from
                      data/alanine-dipeptide.pdb and data/chignolin.pdb (model 1)
 """
@@ -223,7 +225,139 @@ def make_discretize():
     np.savez_compressed(OUT / "discretize.npz", Xtr=Xtr, Xte=Xte, seg=np.asarray(seg), w=w, **out)
 
 
+def _load_reference_ck():
+    """ck_runner.py and _ck.py import matplotlib, mdtraj (via _base.py) and deeptime (via _msm_utils.py),
+    none of which is installed here.  The two files are loaded straight from the reference tree under a
+    throw-away package name with those imports stubbed: matplotlib / mdtraj by inert mocks (plots are not
+    part of the fixture), and ``_msm_utils`` by a two-function module -- ``_row_normalize`` restating
+    deeptime 0.4.5 ``transition_matrix_non_reversible`` (strictly positive row sums or ValueError) and
+    ``pcca_like_macrostates`` returning None (PCCA+ unavailable -> the micro branch, ck_runner.py:201-203).
+    Everything else that runs is the reference's own code."""
+    import importlib.util
+    from unittest import mock
+
+    for name in ("matplotlib", "matplotlib.pyplot", "mdtraj"):
+        sys.modules.setdefault(name, mock.MagicMock(name=name))
+    pkg = types.ModuleType("_refmsm")
+    pkg.__path__ = [str(REF / "src" / "pmarlo" / "markov_state_model")]
+    sys.modules["_refmsm"] = pkg
+    utils = types.ModuleType("_refmsm._msm_utils")
+
+    def _row_normalize(C):
+        arr = np.asarray(C, dtype=float)
+        if arr.size == 0:
+            return arr.copy()
+        rows = 1.0 * np.sum(arr, axis=1)
+        if np.min(rows) <= 0:
+            raise ValueError("Transition matrix has row sum of " + str(np.min(rows))
+                             + ". Must have strictly positive row sums.")
+        return np.divide(arr, rows[:, np.newaxis])
+
+    utils._row_normalize = _row_normalize
+    utils.pcca_like_macrostates = lambda T, n_macrostates=4, random_state=42: None
+    sys.modules["_refmsm._msm_utils"] = utils
+    mods = {}
+    for name in ("_base", "_ck", "ck_runner"):
+        spec = importlib.util.spec_from_file_location(f"_refmsm.{name}", pkg.__path__[0] + f"/{name}.py")
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"_refmsm.{name}"] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods
+
+
+def _markov_dtrajs(rng, K, lengths, stay=0.7, rare=()):
+    """Seeded jump process on K states; states in ``rare`` are only entered with small probability."""
+    P = rng.random((K, K)) ** 3 + 1e-3
+    for r in rare:
+        P[:, r] *= 0.01
+    P = P / P.sum(axis=1, keepdims=True)
+    P = stay * np.eye(K) + (1 - stay) * P
+    cum = np.cumsum(P, axis=1)
+    out = []
+    for n in lengths:
+        s = np.empty(n, dtype=np.int64)
+        s[0] = rng.integers(0, K)
+        u = rng.random(n)
+        for t in range(1, n):
+            s[t] = min(int(np.searchsorted(cum[s[t - 1]], u[t])), K - 1)
+        out.append(s)
+    return out
+
+
+def make_ck():
+    """ck_runner.run_ck (ck_runner.py:293-332) and CKMixin.compute_ck_test_micro / select_lag_time_ck
+    (_ck.py:61-110,159-175) on seeded label trajectories."""
+    import tempfile
+
+    mods = _load_reference_ck()
+    run_ck = mods["ck_runner"].run_ck
+    CKMixin = mods["_ck"].CKMixin
+
+    class Host(CKMixin):
+        def __init__(self, dtrajs, n_states, lag, out):
+            self.dtrajs, self.n_states, self.lag_time = dtrajs, n_states, lag
+            self.transition_matrix, self.output_dir = None, out
+
+    rng = np.random.default_rng(20260519)
+    cases = {
+        # name: (dtrajs, kwargs for run_ck)
+        "dense12": (_markov_dtrajs(rng, 12, [4000, 2500, 3500]), dict(lag_time=2, min_trans=20, top_n_micro=50)),
+        "top8of20": (_markov_dtrajs(rng, 20, [6000, 5000], rare=(3, 11, 17)),
+                     dict(lag_time=3, min_trans=10, top_n_micro=8, factors=(2, 3, 5))),
+        "gaps": (None, dict(lag_time=1, min_trans=5, top_n_micro=6)),
+        "scarce": (_markov_dtrajs(rng, 15, [300, 200], rare=(1, 2)), dict(lag_time=4, min_trans=40, top_n_micro=10)),
+        "cycle": ([np.array([0, 1, 2] * 1000, dtype=int)], dict(lag_time=1, macro_k=3, min_trans=5, top_n_micro=3)),
+        "tiny": ([np.array([0, 1, 0, 1], dtype=int)], dict(lag_time=1, macro_k=2, min_trans=50, top_n_micro=2)),
+        # the longest lag multiples run out of pairs: some factors are reported, others flagged
+        "partial": (_markov_dtrajs(rng, 4, [60] * 40, stay=0.5), dict(lag_time=10, min_trans=30, top_n_micro=4)),
+        # test_ck_tau_selection.py: tau=2 replaces tau=1 on an MSE tie
+        "pattern": ([np.array([0, 0, 1, 1] * 500, dtype=int)], dict(lag_time=1, min_trans=5, top_n_micro=2)),
+    }
+    # "gaps": labels with unused ids (never visited) and negative (unassigned) frames
+    g = _markov_dtrajs(rng, 9, [3000, 3000])
+    remap = np.array([0, 2, 3, 5, 8, 9, 12, 13, 14])
+    g = [remap[t] for t in g]
+    g[0][100:130] = -1
+    cases["gaps"] = (g, cases["gaps"][1])
+
+    out = {"case_names": np.array(sorted(cases))}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (dtrajs, kw) in cases.items():
+            r = run_ck(dtrajs, output_dir=tmp, **kw)
+            ks = sorted(r.mse)
+            out[f"{name}_lens"] = np.array([len(t) for t in dtrajs])
+            out[f"{name}_labels"] = np.concatenate(dtrajs).astype(np.int32)
+            out[f"{name}_kw"] = np.array(repr(kw))
+            out[f"{name}_ks"] = np.array(ks, dtype=np.int64)
+            out[f"{name}_mse"] = np.array([r.mse[k] for k in ks], dtype=np.float64)
+            out[f"{name}_insufficient"] = np.array(r.insufficient_k, dtype=np.int64)
+            out[f"{name}_mode"] = np.array(r.mode)
+            print("ck", name, r.mode, {k: float(f"{v:.3e}") for k, v in r.mse.items()}, r.insufficient_k)
+            # the mixin's micro test and lag selection on the same labels
+            K = int(max(int(t.max()) for t in dtrajs)) + 1
+            h = Host([np.asarray(t) for t in dtrajs], K, int(kw["lag_time"]), tmp)
+            m = h.compute_ck_test_micro(factors=[2, 3, 4], max_states=int(kw["top_n_micro"]), min_transitions=5)
+            mk = sorted(m.mse)
+            out[f"{name}_mixin_ks"] = np.array(mk, dtype=np.int64)
+            out[f"{name}_mixin_mse"] = np.array([m.mse[k] for k in mk], dtype=np.float64)
+            out[f"{name}_mixin_insufficient"] = np.array(bool(m.insufficient_data))
+            if name in ("dense12", "top8of20", "gaps", "pattern"):
+                import contextlib, io
+                with contextlib.redirect_stdout(io.StringIO()):
+                    cand = [1, 2, 3] if name == "pattern" else [1, 2, 3, 5, 8]
+                    taus, mses, its = h._evaluate_candidates(tau_candidates=cand, factor=2)
+                    sel = h.select_lag_time_ck(cand, factor=2)
+                out[f"{name}_sel_taus"] = np.array(cand)
+                out[f"{name}_sel"] = np.array(sel)
+                out[f"{name}_sel_mses"] = np.array(mses)
+                out[f"{name}_sel_its"] = np.array(its)
+                print("   select", sel, np.round(mses, 6))
+    np.savez_compressed(OUT / "ck.npz", **out)
+
+
 if __name__ == "__main__":
+    make_ck()
     make_discretize()
     make_topologies()
     make_counts()

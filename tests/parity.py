@@ -184,3 +184,35 @@ def run_and_check_small(seed: int = 1, n_traj: int = 4, n_frames: int = 600, n_r
     report["kmeans"] = rep
     report["msm"] = check_counts_msm(labels, segs, K, lag, 4)
     return report
+
+
+# ----------------------------------------------------------------------------- CK golden cases
+def ck_cases(z):
+    """Yield (name, dtrajs, run_ck kwargs) from tests/golden/ck.npz."""
+    for name in [str(s) for s in z["case_names"]]:
+        lens = [int(v) for v in z[f"{name}_lens"]]
+        flat = z[f"{name}_labels"].astype(np.int64)
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        dtrajs = [flat[offs[i]:offs[i + 1]] for i in range(len(lens))]
+        kw = eval(str(z[f"{name}_kw"]), {"__builtins__": {}}, {"dict": dict})  # repr of a plain dict
+        yield name, dtrajs, kw
+
+
+def check_ck_case(z, name, dtrajs, kw, run_ck, micro, select, rtol=1e-9):
+    """``run_ck`` / ``micro`` / ``select`` are the implementation under test (oracle or device)."""
+    r = run_ck(dtrajs, **kw)
+    assert r.mode == str(z[f"{name}_mode"]), name
+    assert sorted(r.mse) == [int(k) for k in z[f"{name}_ks"]], name
+    np.testing.assert_allclose([r.mse[k] for k in sorted(r.mse)], z[f"{name}_mse"], rtol=rtol, atol=1e-15)
+    assert list(r.insufficient_k) == [int(k) for k in z[f"{name}_insufficient"]], name
+    K = int(max(int(t.max()) for t in dtrajs)) + 1
+    m = micro(dtrajs, K, int(kw["lag_time"]), factors=[2, 3, 4], max_states=int(kw["top_n_micro"]),
+              min_transitions=5)
+    assert bool(m.insufficient_data) == bool(z[f"{name}_mixin_insufficient"]), name
+    assert sorted(m.mse) == [int(k) for k in z[f"{name}_mixin_ks"]], name
+    np.testing.assert_allclose([m.mse[k] for k in sorted(m.mse)], z[f"{name}_mixin_mse"], rtol=rtol, atol=1e-15)
+    if f"{name}_sel" in z.files:
+        sel, taus, mses, its = select(dtrajs, K, [int(t) for t in z[f"{name}_sel_taus"]], factor=2)
+        assert sel == int(z[f"{name}_sel"]), name
+        np.testing.assert_allclose(mses, z[f"{name}_sel_mses"], rtol=rtol, atol=1e-15)
+        np.testing.assert_allclose(its, z[f"{name}_sel_its"], rtol=1e-8)

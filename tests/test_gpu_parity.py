@@ -756,3 +756,92 @@ def test_enhanced_msm_build_and_its_match_oracle():
     short = EnhancedMSM([np.array([0, 1])], n_states=2)
     short.build_msm(lag_time=20)                   # lag capped at 1
     assert short.transition_matrix.shape == (2, 2)
+
+
+# ----------------------------------------------------------------------------- Chapman-Kolmogorov test (8f-1)
+def test_relabel_compact_kernel_is_exact():
+    """pmb_relabel_compact against the reference's list comprehension, shard by shard (bit-exact)."""
+    from pmarlo_b200 import kernels
+
+    rng = np.random.default_rng(7)
+    cases = [
+        ([5000, 0, 4097, 1, 8192, 3], 40, 0.3),      # empty shard, tile-boundary lengths
+        ([100], 7, 0.0),                              # nothing dropped
+        ([4096 * 3], 12, 1.0),                        # everything dropped
+        ([70001, 129999, 50000], 1000, 0.5),
+    ]
+    for lens, K, p_drop in cases:
+        lab = rng.integers(-1, K, size=sum(lens)).astype(np.int32)     # -1 = unassigned frame
+        lut = np.where(rng.random(K) < p_drop, -1, rng.permutation(K)).astype(np.int32)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out, new_off = kernels.relabel_compact(torch.from_numpy(lab).to(dev()), torch.from_numpy(off).to(dev()),
+                                               torch.from_numpy(lut).to(dev()))
+        new_off = new_off.cpu().numpy()
+        out = out.cpu().numpy()
+        for i in range(len(lens)):
+            traj = lab[off[i]:off[i + 1]]
+            want = np.array([lut[s] for s in traj if s >= 0 and lut[s] >= 0], dtype=np.int32)
+            got = out[new_off[i]:new_off[i + 1]]
+            assert np.array_equal(got, want), (lens, i)
+    # a label beyond the table is dropped, not read out of bounds
+    out, new_off = kernels.relabel_compact(torch.tensor([0, 9, 1, 2], dtype=torch.int32, device=dev()),
+                                           torch.tensor([0, 4], dtype=torch.int64, device=dev()),
+                                           torch.tensor([3, 4, -1], dtype=torch.int32, device=dev()))
+    assert new_off.cpu().tolist() == [0, 2] and out[:2].cpu().tolist() == [3, 4]
+
+
+def test_ck_matches_reference_golden(golden, tmp_path):
+    from pmarlo_b200 import ck
+
+    z = golden("ck")
+    for name, dtrajs, kw in parity.ck_cases(z):
+        parity.check_ck_case(z, name, dtrajs, kw, ck.run_ck, ck.compute_ck_test_micro, ck.select_lag_time_ck)
+    r = ck.run_ck([np.array([0, 1, 2] * 1000)], 1, tmp_path, macro_k=3, min_trans=5, top_n_micro=3)
+    assert sorted(r.mse) == [2, 3, 4, 5] and (tmp_path / "ck_mse.json").exists()
+    with pytest.raises(ValueError, match="strictly positive row sums"):
+        ck.run_ck([np.array([0, 1] * 200 + [2])], 1, None, min_trans=1)
+
+
+def test_ck_enhanced_msm_methods(tmp_path, capsys):
+    """tests/unit/markov_state_model/test_ck.py:16-33 and test_ck_tau_selection.py:14-28."""
+    from pmarlo_b200 import EnhancedMSM
+
+    m = EnhancedMSM([np.array([0, 1, 2] * 1000)], n_states=3, output_dir=str(tmp_path))
+    m.lag_time = 1
+    res = m.compute_ck_test_micro()
+    assert sorted(res.mse) == [2, 3, 4, 5] and all(v >= 0.0 for v in res.mse.values())
+    assert res.mse[2] < 1e-6 and not res.insufficient_data
+    m2 = EnhancedMSM([np.array([0, 0, 1, 1] * 500)], n_states=2, output_dir=str(tmp_path))
+    assert m2.select_lag_time_ck([1, 2, 3]) == 2 and m2.lag_time == 2
+    assert (tmp_path / "ck_mse.csv").exists() and "Selected τ =" in capsys.readouterr().out
+
+
+def test_ck_at_scale_against_oracle():
+    """2 M labels, 300 states (some rare, some never visited): the device path and the numpy oracle agree on
+    every MSE, and a label shard already in HBM gives the same answer as host arrays."""
+    from pmarlo_b200 import ck
+
+    rng = np.random.default_rng(12)
+    K, n_traj, L = 300, 8, 250_000
+    P = rng.random((K, K)) ** 6 + 1e-6
+    P[:, 250:] *= 1e-4                         # rare states
+    P[:, 290:] = 0                             # never visited
+    P /= P.sum(axis=1, keepdims=True)
+    cum = np.cumsum(0.5 * np.eye(K) + 0.5 * P, axis=1)
+    dtrajs = []
+    for _ in range(n_traj):                    # vectorised over time is impossible; over blocks of chains is
+        s = np.empty(L, dtype=np.int64)
+        s[0] = rng.integers(0, 250)
+        u = rng.random(L)
+        for t in range(1, L):
+            s[t] = min(int(np.searchsorted(cum[s[t - 1]], u[t])), K - 1)
+        dtrajs.append(s)
+    kw = dict(lag_time=5, min_trans=20, top_n_micro=40, factors=(2, 3, 4))
+    ref = oracle.ck.run_ck(dtrajs, **kw)
+    got = ck.run_ck(dtrajs, output_dir=None, **kw)
+    assert got.mode == ref.mode and sorted(got.mse) == sorted(ref.mse) and got.mse
+    assert got.insufficient_k == ref.insufficient_k
+    np.testing.assert_allclose([got.mse[k] for k in sorted(got.mse)], [ref.mse[k] for k in sorted(ref.mse)], rtol=1e-9)
+    shard = ck.LabelShard.from_dtrajs(dtrajs)
+    again = ck.run_ck(shard, output_dir=None, **kw)
+    assert again.mse == got.mse

@@ -219,3 +219,46 @@ def test_discretize_split_and_segment_bookkeeping():
     assert dz._schema_of(X, 3)["names"] == ["feature_0", "feature_1", "feature_2"]
     with pytest.raises(ValueError):
         dz._check_schema({"names": ["a"], "n_features": 1}, {"names": ["b"], "n_features": 1}, "s")
+
+
+def test_ck_host_bookkeeping_on_the_kernel_contracts(monkeypatch, golden, tmp_path):
+    """pmarlo_b200.ck's control flow (state filtering, top-n selection, insufficient-pair bookkeeping,
+    lag selection, side outputs) against the reference's golden vectors, with the two device kernels
+    replaced by numpy statements of their contracts; the kernels themselves are covered by -m gpu."""
+    import json
+
+    import torch
+
+    from pmarlo_b200 import ck, kernels
+    from tests import fake_kernels, parity
+
+    fake_kernels.install(monkeypatch)
+    monkeypatch.setattr(kernels, "require_cuda", lambda: torch.device("cpu"))
+    z = golden("ck")
+    for name, dtrajs, kw in parity.ck_cases(z):
+        parity.check_ck_case(z, name, dtrajs, kw, ck.run_ck, ck.compute_ck_test_micro, ck.select_lag_time_ck)
+    cyc = [np.array([0, 1, 2] * 1000)]
+    r = ck.run_ck(cyc, 1, tmp_path, macro_k=3, min_trans=5, top_n_micro=3)
+    saved = json.loads((tmp_path / "ck_mse.json").read_text())
+    assert saved["mode"] == "micro" and sorted(saved["mse"]) == ["2", "3", "4", "5"] and saved["insufficient_k"] == []
+    assert (tmp_path / "ck_mse.csv").read_text().splitlines()[0] == "k,mse"
+    assert ck.ck_rms_error(r) == r.max_error and r.has_valid_tests
+    for bad in (dict(dtrajs=[], lag_time=1), dict(dtrajs=cyc, lag_time=0), dict(dtrajs=cyc, lag_time=1, factors=(1,))):
+        with pytest.raises(ValueError):
+            ck.run_ck(bad.pop("dtrajs"), bad.pop("lag_time"), None, **bad)
+    # a state that is only ever the last frame has an empty row: deeptime's row normalisation raises
+    with pytest.raises(ValueError, match="strictly positive row sums"):
+        ck.run_ck([np.array([0, 1] * 200 + [2])], 1, None, min_trans=1)
+    # macro branch with an injected lumping
+    blocks = np.repeat(np.arange(3), 2)
+    rng = np.random.default_rng(0)
+    s = np.empty(30000, dtype=int)
+    s[0] = 0
+    for t in range(1, s.size):
+        u = rng.random()
+        s[t] = s[t - 1] if u < 0.6 else (rng.choice(np.flatnonzero(blocks == blocks[s[t - 1]])) if u < 0.995
+                                          else rng.integers(0, 6))
+    got = ck.run_ck([s], 5, None, macro_k=3, min_trans=20, macro_lumper=lambda T, k: blocks)
+    ref = oracle.ck.run_ck([s], 5, macro_k=3, min_trans=20, macro_lumper=lambda T, k: blocks)
+    assert got.mode == ref.mode == "macro"
+    np.testing.assert_allclose([got.mse[k] for k in (2, 3, 4, 5)], [ref.mse[k] for k in (2, 3, 4, 5)], rtol=1e-9)

@@ -246,3 +246,45 @@ def test_trig_expand_mapping():
         ofeat.trig_expand_periodic(X, np.array([True]))
     w = ofeat.wrap_to_minus_pi_pi(np.array([-np.pi, np.pi, 3 * np.pi, 0.5]))
     np.testing.assert_allclose(w, [np.pi, np.pi, np.pi, 0.5])
+
+
+# ------------------------------------------------------------------ Chapman-Kolmogorov test (8f-1)
+def test_ck_oracle_matches_reference(golden):
+    from oracle import ck as ock
+    from tests import parity
+
+    z = golden("ck")
+    n = 0
+    for name, dtrajs, kw in parity.ck_cases(z):
+        parity.check_ck_case(z, name, dtrajs, kw, ock.run_ck, ock.compute_ck_test_micro, ock.select_lag_time_ck)
+        n += 1
+    assert n == 8
+
+
+def test_ck_oracle_reference_test_cases():
+    """tests/unit/markov_state_model/test_ck_fallback.py:14-38 and test_ck_tau_selection.py:14-19."""
+    from oracle import ck as ock
+
+    cyc = np.array([0, 1, 2] * 1000, dtype=int)
+    r = ock.run_ck([cyc], lag_time=1, macro_k=3, min_trans=5, top_n_micro=3)
+    assert sorted(r.mse) == [2, 3, 4, 5] and r.mse[5] <= r.mse[2] + 1e-12
+    r = ock.run_ck([np.array([0, 1, 0, 1])], lag_time=1, macro_k=2, min_trans=50, top_n_micro=2)
+    assert not r.mse and set(r.insufficient_k) == {2, 3, 4, 5} and r.max_error == float("inf")
+    sel, *_ = ock.select_lag_time_ck([np.array([0, 0, 1, 1] * 500)], 2, [1, 2, 3])
+    assert sel == 2
+    m = ock.compute_ck_test_micro([cyc], 3, 1)
+    assert sorted(m.mse) == [2, 3, 4, 5] and m.mse[2] < 1e-6 and not m.insufficient_data
+    with pytest.raises(ValueError):
+        ock.run_ck([], lag_time=1)
+    with pytest.raises(ValueError):
+        ock.run_ck([cyc], lag_time=0)
+    # a macro lumping supplied by the caller takes the macro branch (ck_runner.py:182-219)
+    rng = np.random.default_rng(0)
+    blocks = np.repeat(np.arange(3), 2)
+    s = np.empty(30000, dtype=int); s[0] = 0
+    for t in range(1, s.size):
+        u = rng.random()
+        s[t] = s[t - 1] if u < 0.6 else (rng.choice(np.flatnonzero(blocks == blocks[s[t - 1]])) if u < 0.995
+                                          else rng.integers(0, 6))
+    r = ock.run_ck([s], lag_time=5, macro_k=3, min_trans=20, macro_lumper=lambda T, k: blocks)
+    assert r.mode == "macro" and sorted(r.mse) == [2, 3, 4, 5]
