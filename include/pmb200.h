@@ -92,7 +92,8 @@ PMB_API int pmb_pair_mask(const int64_t* seg_offsets, int n_seg, int64_t n, int 
  * z = NaN ? 0 : (x - shift) * scale (fp32 conditioning transform).
  * mode 0: G += sum_g popcount(mask[g]&3) z_g z_g^T          (= X0^T X0 + Xt^T Xt)
  * mode 1: G += sum_g (mask[g]&1) (z_g - z_{g+lag})(z_g - z_{g+lag})^T
- * G: d x d fp64, overwritten.  impl: 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32. */
+ * G: d x d fp64, overwritten.  impl: 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32, 4 tcgen05 3xTF32 on CTA pairs
+ * (cta_group::2, d = 256 only; correct but measured slower than 2). */
 PMB_API size_t pmb_gram_ws_bytes(int d);
 PMB_API int pmb_gram(const float* X, int64_t n, int d, int64_t ld, const uint8_t* mask,
              int lag, int mode, const float* shift, const float* scale,

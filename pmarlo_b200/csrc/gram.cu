@@ -220,7 +220,7 @@ static inline int gram_chunks(int d) {
 
 int gram_tcgen05(const float* X, int64_t n, int d, int64_t ld, const uint8_t* mask, int lag,
                  int mode, const float* shift, const float* scale, double* G, void* ws,
-                 size_t ws_bytes, cudaStream_t stream);  // gram_tc.cu
+                 size_t ws_bytes, cudaStream_t stream, bool cta_pairs);  // gram_tc.cu
 bool gram_tcgen05_supported(int d, int64_t ld, const float* X);
 size_t gram_tcgen05_ws_bytes(int d);
 constexpr int64_t kGramTcMinFrames = 65536;   // auto dispatch: below this the SIMT kernel is as fast
@@ -245,12 +245,13 @@ extern "C" int pmb_gram(const float* X, int64_t n, int d, int64_t ld, const uint
     set_error("pmb_gram: workspace too small (%zu < %zu)", ws_bytes, pmb_gram_ws_bytes(d));
     return PMB_EWORKSPACE;
   }
-  if (impl == 2 || (impl == 0 && n >= kGramTcMinFrames && gram_tcgen05_supported(d, ld, X))) {
+  // impl: 0 auto, 1 SIMT, 2 tensor cores, 4 tensor cores with CTA pairs (d = 256; measured slower, see gram_tc.cu)
+  if (impl == 2 || impl == 4 || (impl == 0 && n >= kGramTcMinFrames && gram_tcgen05_supported(d, ld, X))) {
     if (!gram_tcgen05_supported(d, ld, X)) {
       set_error("pmb_gram: tcgen05 path needs d %% 32 == 0, 32 <= d <= 256, 16B-aligned rows");
       return PMB_EUNSUPPORTED;
     }
-    return gram_tcgen05(X, n, d, ld, mask, lag, mode, shift, scale, G, ws, ws_bytes, as_stream(stream));
+    return gram_tcgen05(X, n, d, ld, mask, lag, mode, shift, scale, G, ws, ws_bytes, as_stream(stream), impl == 4);
   }
   GramParams p;
   p.X = X; p.n = n; p.d = d; p.ld = ld; p.mask = mask; p.lag = lag; p.shift = shift; p.scale = scale;

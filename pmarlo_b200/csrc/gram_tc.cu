@@ -286,6 +286,209 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
   if (warp == kGtProdWarps) tc::tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant for d = 256 (cta_group::2), selected with impl = 4.  NOT the default: it is correct
+// (same parity tests) but measured 1.3x SLOWER than the kernel above on B200.
+// Idea: in the kernel above the two row blocks of a frame chunk run on two unrelated SMs and each of them
+// loads, conditions and splits ALL 256 features of every frame for its N side.  Here the two row blocks are
+// the two CTAs of a cluster and issue ONE M = 256, N = 256 MMA: each CTA stages only its own 128 features --
+// they are both its 128 rows of A (2wa, w r_hi) and its half of B (a, r_hi, r_lo) -- so the producer work per
+// frame is halved.  Stage = 5 tiles of 128 features x 16 frames = 40 KB, 5 stages.
+//   producers (16 warps per CTA, one frame each per stage) -> arrive on the LEADER's full barrier
+//   MMA warp of the leader CTA: 8 tcgen05.mma.cta_group::2 per stage, commit multicast to both CTAs'
+//   empty / window barriers; each CTA drains its own TMEM (its 128 rows of P and Q).
+// Measurement (2.5 M frames, both Gram launches): single-CTA 4.92 ms, of which 3.50 ms remain when the
+// producers store nothing -- 204 cycles per M128 N256 K8 MMA, the TF32 rate cuBLAS sustains -- so that kernel
+// is MMA-bound with 1.4 ms of imperfect overlap.  The pair kernel: 6.45 ms, 5.75 ms with idle producers,
+// 335 cycles per MMA with all 74 clusters resident: with 4-byte operands the half of B that every MMA pulls
+// from the peer SM's shared memory is the bound, not the staging work the pairing saves.
+constexpr int kGpStages = 5;
+constexpr uint32_t kGpTile = 128 * kGtBK * 4;        // 8 KB
+constexpr uint32_t kGpStageBytes = 5 * kGpTile;      // a, r_hi, r_lo | 2wa, w r_hi
+static_assert(kGtProdWarps == kGtBK, "one producer warp per frame of a stage");
+
+struct GpBars {
+  uint64_t full[kGpStages], empty[kGpStages], wdone, drained;
+  uint32_t tmem_slot;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGtThreads, 1) gram_tc_pair_kernel(GramTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  GpBars* B = reinterpret_cast<GpBars*>(tiles + (size_t)kGpStages * kGpStageBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int d = 256;
+  const uint32_t rank = tc::cluster_ctarank();   // = row block
+  const int ck = (int)(blockIdx.x >> 1);
+  const int64_t g_begin = (int64_t)ck * p.chunk;
+  int64_t g_end = g_begin + p.chunk;
+  if (g_end > p.n) g_end = p.n;
+  const int n_stages = g_begin < g_end ? (int)((g_end - g_begin + kGtBK - 1) / kGtBK) : 0;
+  const int stages_per_window = kGtWindow / kGtBK;
+  const uint32_t lbo = kGtBK * 128u, sbo = 512u;
+
+  for (uint32_t i = tid; i < kGpStages * kGpStageBytes / 16; i += kGtThreads)
+    reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    for (int s = 0; s < kGpStages; ++s) {
+      mbar_init(&B->full[s], 2 * kGtProdWarps);   // one arrival per producer warp of BOTH CTAs (leader's copy is used)
+      mbar_init(&B->empty[s], 1);
+    }
+    mbar_init(&B->wdone, 1);
+    mbar_init(&B->drained, 2 * kGtProdWarps);
+    fence_barrier_init();
+  }
+  if (warp == kGtProdWarps) tc::tmem_alloc_pair(&B->tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc::fence_before_sync();
+  tc::cluster_sync();
+  tc::fence_after_sync();
+  const uint32_t tmem = B->tmem_slot;
+  double* ws = p.ws + ((size_t)rank * p.n_chunks + ck) * 2 * d * 128;
+
+  if (warp < kGtProdWarps) {
+    // ============================================================ producers: warp = frame of the stage
+    const int fr = warp;
+    const int c = (int)rank * 128 + lane * 4;   // first of this lane's four features
+    const float4 sh = *reinterpret_cast<const float4*>(p.shift + c);
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + c);
+    float4 xa, xb;
+    int mk = 0;
+    auto prefetch = [&](int s) {
+      const int64_t g = g_begin + (int64_t)s * kGtBK + fr;
+      int m = 0;
+      if (g < g_end) m = p.mask[g];
+      const int w = (p.mode == 0) ? __popc(m & 3) : (m & 1);
+      xa = make_float4(0.f, 0.f, 0.f, 0.f);
+      xb = xa;
+      if (w) {
+        xa = ldg_stream_f4(reinterpret_cast<const float4*>(p.X + g * p.ld + c));
+        if (p.mode == 1) xb = ldg_stream_f4(reinterpret_cast<const float4*>(p.X + (g + p.lag) * p.ld + c));
+      }
+      mk = w;
+    };
+    auto drain = [&](bool first) {
+      const int quarter = warp & 3, which = (warp >> 2) & 1, part = warp >> 3, nparts = kGtProdWarps / 8;
+      double* dst = ws + (size_t)which * d * 128 + quarter * 32 + lane;
+      for (int c0 = part * 32; c0 < d; c0 += 32 * nparts) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(which * 256 + c0), v);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          double* e = dst + (size_t)(c0 + q) * 128;
+          *e = first ? (double)v[q] : (*e + (double)v[q]);
+        }
+      }
+    };
+    const uint32_t o = tc::off_mnmajor_sw128b32(lane * 4, fr, lbo, sbo);
+
+    if (n_stages > 0) prefetch(0);
+    int n_windows_done = 0;
+    for (int s = 0; s < n_stages; ++s) {
+      const int slot = s % kGpStages;
+      const uint32_t use = (uint32_t)(s / kGpStages);
+      const float4 ca = xa, cb = xb;
+      const int w = mk;
+      if (s + 1 < n_stages) prefetch(s + 1);
+      float dith;   // one dither per frame, see gram_tc_kernel
+      {
+        uint32_t h = (uint32_t)(g_begin + (int64_t)s * kGtBK + fr) * 0x9E3779B1u;
+        h ^= h >> 15;
+        h *= 0x85EBCA6Bu;
+        h ^= h >> 13;
+        dith = __uint_as_float((h >> 9) | 0x3f800000u) - 1.5f;
+      }
+      float z[4];
+      z[0] = gt_cond(ca.x, sh.x, sc.x);
+      z[1] = gt_cond(ca.y, sh.y, sc.y);
+      z[2] = gt_cond(ca.z, sh.z, sc.z);
+      z[3] = gt_cond(ca.w, sh.w, sc.w);
+      if (p.mode == 1) {
+        z[0] -= gt_cond(cb.x, sh.x, sc.x);
+        z[1] -= gt_cond(cb.y, sh.y, sc.y);
+        z[2] -= gt_cond(cb.z, sh.z, sc.z);
+        z[3] -= gt_cond(cb.w, sh.w, sc.w);
+      }
+      float a[4], rh[4], rl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float zz = w ? z[q] : 0.f;
+        a[q] = fminf(fmaxf(rintf(fmaf(zz, 8.0f, dith)), -64.0f), 64.0f) * 0.125f;
+        const float r = zz - a[q];
+        rh[q] = gt_tf32(r);
+        rl[q] = gt_tf32(r - rh[q]);
+      }
+      const float wf = (float)w, w2 = 2.0f * wf;
+      mbar_wait(&B->empty[slot], (use & 1u) ^ 1u);
+      unsigned char* T = tiles + (size_t)slot * kGpStageBytes + o;
+      *reinterpret_cast<float4*>(T) = make_float4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<float4*>(T + kGpTile) = make_float4(rh[0], rh[1], rh[2], rh[3]);
+      *reinterpret_cast<float4*>(T + 2 * kGpTile) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+      *reinterpret_cast<float4*>(T + 3 * kGpTile) = make_float4(w2 * a[0], w2 * a[1], w2 * a[2], w2 * a[3]);
+      *reinterpret_cast<float4*>(T + 4 * kGpTile) = make_float4(wf * rh[0], wf * rh[1], wf * rh[2], wf * rh[3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(&B->full[slot], 0u);
+
+      const bool window_end = ((s + 1) % stages_per_window == 0) || (s + 1 == n_stages);
+      if (window_end) {
+        mbar_wait(&B->wdone, (uint32_t)(n_windows_done & 1));
+        tc::fence_after_sync();
+        drain(n_windows_done == 0);
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive_cluster(&B->drained, 0u);
+        ++n_windows_done;
+      }
+    }
+    if (n_stages == 0) {
+      for (int i = tid; i < 2 * d * 128; i += kGtProdWarps * 32) ws[i] = 0.0;
+    }
+  } else if (rank == 0) {
+    // ============================================================ MMA issuer of the pair (leader CTA)
+    const uint32_t idesc = tc::idesc_tf32(256, d, 1, 1);
+    const uint32_t base = smem_u32(tiles);
+    int n_windows_done = 0;
+    for (int s = 0; s < n_stages; ++s) {
+      const int slot = s % kGpStages;
+      const uint32_t use = (uint32_t)(s / kGpStages);
+      const bool window_start = (s % stages_per_window) == 0;
+      if (window_start && n_windows_done > 0) {
+        tc::mbar_wait_cluster(&B->drained, (uint32_t)((n_windows_done - 1) & 1));
+        tc::fence_after_sync();
+      }
+      tc::mbar_wait_cluster(&B->full[slot], use & 1u);
+      tc::fence_after_sync();
+      const uint32_t T = base + (uint32_t)slot * kGpStageBytes;
+#pragma unroll
+      for (int ks = 0; ks < kGtBK / 8; ++ks) {
+        const uint32_t off = (uint32_t)ks * 2u * sbo;
+        const uint64_t dBa = tc::smem_desc(T + off, lbo, sbo, tc::kLayoutSw128Base32);
+        const uint64_t dBh = tc::smem_desc(T + kGpTile + off, lbo, sbo, tc::kLayoutSw128Base32);
+        const uint64_t dBl = tc::smem_desc(T + 2 * kGpTile + off, lbo, sbo, tc::kLayoutSw128Base32);
+        const uint64_t dA2a = tc::smem_desc(T + 3 * kGpTile + off, lbo, sbo, tc::kLayoutSw128Base32);
+        const uint64_t dAwh = tc::smem_desc(T + 4 * kGpTile + off, lbo, sbo, tc::kLayoutSw128Base32);
+        const uint32_t acc = (window_start && ks == 0) ? 0u : 1u;
+        tc::mma_tf32_pair_elect(tmem, dA2a, dBa, idesc, acc);
+        tc::mma_tf32_pair_elect(tmem + 256u, dA2a, dBh, idesc, acc);
+        tc::mma_tf32_pair_elect(tmem + 256u, dA2a, dBl, idesc, 1u);
+        tc::mma_tf32_pair_elect(tmem + 256u, dAwh, dBh, idesc, 1u);
+      }
+      tc::mma_commit_pair_elect(&B->empty[slot], 3u);
+      const bool window_end = ((s + 1) % stages_per_window == 0) || (s + 1 == n_stages);
+      if (window_end) {
+        tc::mma_commit_pair_elect(&B->wdone, 3u);
+        ++n_windows_done;
+      }
+      __syncwarp();
+    }
+  }
+
+  tc::fence_before_sync();
+  tc::cluster_sync();
+  if (warp == kGtProdWarps) tc::tmem_dealloc_pair(tmem, 512);
+}
+
 // Pf[i][j], Qf[i][j] = sum over frame chunks (fixed order) of the per-CTA fp64 partials
 __global__ void gram_tc_reduce_kernel(const double* __restrict__ ws, int n_chunks, int d, double* __restrict__ PQ) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;   // i fastest
@@ -325,7 +528,8 @@ size_t gram_tcgen05_ws_bytes(int d) {
 }
 
 int gram_tcgen05(const float* X, int64_t n, int d, int64_t ld, const uint8_t* mask, int lag, int mode,
-                 const float* shift, const float* scale, double* G, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 const float* shift, const float* scale, double* G, void* ws, size_t ws_bytes, cudaStream_t st,
+                 bool cta_pairs) {
   PMB_REQUIRE(ws_bytes >= gram_tcgen05_ws_bytes(d), "pmb_gram: workspace too small for the tcgen05 path");
   PMB_REQUIRE((reinterpret_cast<uintptr_t>(shift) & 15) == 0 && (reinterpret_cast<uintptr_t>(scale) & 15) == 0,
               "pmb_gram: shift/scale must be 16-byte aligned for the tcgen05 path");
@@ -334,13 +538,41 @@ int gram_tcgen05(const float* X, int64_t n, int d, int64_t ld, const uint8_t* ma
   p.ws = static_cast<double*>(ws);
   const int nrb = gt_row_blocks(d);
   int nc = gt_chunks(d);
+  const bool pair = d == 256 && cta_pairs;
+  const size_t smem_pair = (size_t)kGpStages * kGpStageBytes + sizeof(GpBars) + 1024;
+  if (pair) {
+    // One cluster (CTA pair) per frame chunk, all of them resident at once: a pair needs both SMs of a TPC,
+    // and a part with disabled SMs has fewer usable pairs than SMs / 2.
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      PMB_CUDA(cudaFuncSetAttribute(gram_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * nc);
+      cfg.blockDim = dim3(kGtThreads);
+      cfg.dynamicSmemBytes = smem_pair;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int ncl = 0;
+      PMB_CUDA(cudaOccupancyMaxActiveClusters(&ncl, gram_tc_pair_kernel, &cfg));
+      max_clusters = ncl;
+    }
+    PMB_REQUIRE(max_clusters >= 1, "pmb_gram: the CTA-pair kernel does not fit on this device");
+    if (nc > max_clusters) nc = max_clusters;
+  }
   int64_t chunk = (n + nc - 1) / nc;
   chunk = ((chunk + kGtBK - 1) / kGtBK) * kGtBK;
   p.n_chunks = nc;
   p.chunk = chunk;
-  const size_t smem = (size_t)kGtStages * kGtStageBytes + sizeof(GtBars) + 1024;
-  PMB_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gram_tc_kernel<<<nrb * nc, kGtThreads, smem, st>>>(p);
+  if (pair) {
+    gram_tc_pair_kernel<<<2 * nc, kGtThreads, smem_pair, st>>>(p);   // clusters of 2: (row block 0, row block 1) of a chunk
+  } else {
+    const size_t smem = (size_t)kGtStages * kGtStageBytes + sizeof(GtBars) + 1024;
+    PMB_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gram_tc_kernel<<<nrb * nc, kGtThreads, smem, st>>>(p);
+  }
   PMB_LAUNCH_CHECK();
   double* PQ = p.ws + (size_t)nrb * nc * 2 * d * 128;
   gram_tc_reduce_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(p.ws, nc, d, PQ);

@@ -129,6 +129,85 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster on the two SMs of a TPC execute ONE tcgen05.mma: M = 256 rows (each CTA holds 128
+// rows of A in its own shared memory and 128 lanes of D in its own TMEM), B is split along N (each CTA
+// holds N / 2 columns).  Descriptors and TMEM addresses are the same numbers in both CTAs, so both must
+// use identical shared-memory layouts.  Only the CTA of cluster rank 0 issues the instruction.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// executed by the warp of the same index in BOTH CTAs of the pair, same slot address
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// when the pair's MMAs issued so far complete, arrive (once) on the mbarrier at this shared-memory offset in
+// every CTA of `cta_mask`
+__device__ __forceinline__ void mma_commit_pair_elect(uint64_t* bar, uint32_t cta_mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      ".reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %1;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], lo;\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(cta_mask)
+      : "memory");
+}
+// arrive (count 1, release at cluster scope) on the mbarrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// wait with acquire at cluster scope (the arrivals come from both CTAs of the pair)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
 // ---------------------------------------------------------------- operand layouts (byte offsets)
 // K-major, no swizzle: 8-row x 16-byte core matrices (128 contiguous bytes);
 // core matrices adjacent in K are `lbo` apart, adjacent in M/N `sbo` apart.

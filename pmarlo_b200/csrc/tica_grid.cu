@@ -594,7 +594,11 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   PMB_CUDA(cudaGetDevice(&dev));
   PMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // rows per block: the 2 b rows of a block pair (d doubles each) must fit in shared memory
-  int blk = 16;
+  // b = 8: d / 16 CTAs own a block pair.  Measured on B200 for d = 256 (cycles of the whole solve):
+  // b = 16 -> 16.8 M, b = 8 -> 15.6 M (half the warps per SM contend for the fp64 pipe, twice the grid
+  // barriers), b = 4 -> 19.7 M.  b = 8 also keeps 16 instead of 8 SMs working, which matters for the clock
+  // (see the note at the launch below).
+  int blk = 8;
   while (blk > 1 && (size_t)2 * blk * d * sizeof(double) > (size_t)200 * 1024) blk >>= 1;
   const size_t smem = (size_t)2 * blk * (d + 1) * sizeof(double);   // rows + their squared norms
   PMB_REQUIRE(smem <= (size_t)227 * 1024, "pmb_tica_solve: d=%d too large for the block-Jacobi kernel", d);
@@ -616,9 +620,10 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   // One CTA per SM even though only nb / 2 of them own a block pair: the others join the grid barriers and
   // the dense phases.  The wall time of this kernel is bimodal between (and sometimes within) processes on
   // the same GPU: identical clock64 cycle count, but an effective SM clock of 0.6-1.2 GHz instead of
-  // 1.96 GHz in the slow state.  A grid of 8 CTAs made it worse; a hand-written arrival-counter barrier and
-  // keeping the idle SMs busy with FMA chains (light or heavy) did not remove it (A/B on one box, round 1),
-  // so the plain cooperative-groups barrier stays and the remedy is the cycle count itself.
+  // 1.96 GHz in the slow state.  It tracks the number of SMs doing real work: a grid of 8 CTAs was worst,
+  // 8 working CTAs in a full grid (b = 16) still hit it in about half of the processes, 16 working CTAs
+  // (b = 8) rarely, 32 (b = 4) never in the runs made; a hand-written arrival-counter barrier or keeping the
+  // idle SMs busy with FMA chains (light or heavy) changed nothing (A/B on one box, round 1).
   int grid = sms;
   if (grid < nb / 2) grid = nb / 2;
   if (grid > sms * per_sm) grid = sms * per_sm;

@@ -144,6 +144,11 @@ def test_gram_tensor_path_matches_fp64(d, n_frames, lag):
         # stochastic-rounding split is good to a few 1e-7, relative to the matrix scale to ~3e-8
         assert e_tc <= 1e-7 and e_diag <= 5e-7
         np.testing.assert_array_equal(tc, tc.T)
+        if d == 256:
+            # the CTA-pair kernel (cta_group::2, impl=4) must agree with the default single-CTA kernel
+            one = kernels.gram(Xd, mask, lag, mode, cond, impl=4).cpu().numpy()
+            assert np.max(np.abs(one - ref)) / scale_ref <= 1e-7
+            assert np.max(np.abs(one - tc)) / scale_ref <= 2e-8
 
 
 @pytest.mark.parametrize("case", ["stationary", "drifting", "nan"])
