@@ -281,11 +281,16 @@ def gpu_arm(args):
     # ---- device-resident timing -------------------------------------------------
     timer = StageTimer(True)
     bufs: dict = {}
+    # Warm-up runs exactly what the timed loop runs, INCLUDING keeping the previous step's result alive
+    # while the next one is computed: torch's caching allocator then reaches its steady state here.  (With
+    # the result discarded during warm-up the second timed step needed new blocks, and the cudaMalloc inside
+    # a small torch.empty stalled the host for 15-140 ms while the GPU sat idle -- measured, round 1.)
+    res = None
     for _ in range(args.warmup):
-        run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, read_back=True, buffers=bufs)
+        res = run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, timer=StageTimer(True), read_back=True, buffers=bufs)
     sync()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("PMB_BENCH_NO_SAMPLER"):
         sampler.start()
     l0 = _lib.launch_count()
     if args.profile_range:
@@ -313,7 +318,7 @@ def gpu_arm(args):
     del wl.xyz
     torch.cuda.empty_cache()
     lengths = [fpt] * n_traj
-    for _ in range(max(1, min(2, args.warmup))):
+    for _ in range(max(1, min(3, args.warmup))):
         out = estimate_msm_from_host(host, lengths, wl.plan, cfg, comm, buffers=bufs)
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -388,6 +393,18 @@ def tica_debug_counters():
     buf = (ctypes.c_int64 * 8)()
     _lib.check(_lib.lib().pmb_debug_counters_tica(ctypes.cast(buf, ctypes.c_void_p)), "pmb_debug_counters_tica")
     return list(buf)
+
+
+def tica_debug_trace():
+    import ctypes
+
+    from pmarlo_b200 import _lib
+
+    buf = (ctypes.c_int64 * 80)()
+    _lib.check(_lib.lib().pmb_debug_trace_tica(ctypes.cast(buf, ctypes.c_void_p)), "pmb_debug_trace_tica")
+    v = list(buf)
+    sweeps = [(v[16 + 2 * i], v[17 + 2 * i]) for i in range(32) if v[16 + 2 * i] > 0]
+    return {"smid_of_cta_0_15": v[:16], "sweep_ghz": [round(c / max(t, 1), 2) for c, t in sweeps]}
 
 
 def kmeans_debug_counters():

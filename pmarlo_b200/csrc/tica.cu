@@ -385,6 +385,13 @@ extern "C" int pmb_debug_counters_tica(int64_t* out8) {
   return tica_grid_debug_counters(out8);
 }
 
+namespace pmb { int tica_grid_debug_trace(int64_t* out80); }
+extern "C" int pmb_debug_trace_tica(int64_t* out80) {
+  using namespace pmb;
+  PMB_REQUIRE(out80 != nullptr, "pmb_debug_trace_tica: null pointer");
+  return tica_grid_debug_trace(out80);
+}
+
 extern "C" size_t pmb_tica_solve_ws_bytes(int d) {
   if (d <= 0) return 0;
   return ((size_t)5 * d * d + d) * sizeof(double) + (size_t)d * sizeof(int) + 64;

@@ -27,6 +27,14 @@ __device__ __forceinline__ double ldg_cg(const double* p) { return __ldcg(p); }
 
 // phase cycle counters of the last solve (CTA 0, thread 0): load, local sweep, store, grid barrier, total, block rounds
 __device__ long long g_tg_dbg[8];
+// trace of the last solve: [0..15] %smid of CTAs 0..15; then per Jacobi sweep (both solves, up to 32) the pair
+// (clock64 cycles, globaltimer ns) spent in it on CTA 0 -- separates a slow SM clock from time outside the SM
+__device__ long long g_tg_trace[16 + 64];
+__device__ __forceinline__ long long tg_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // 1/sqrt(x) for x in [2^-8, 2^8]: fp32 seed (MUFU) and ONE third-order step, y <- y (1 + e/2 + 3 e^2 / 8) with
 // e = 1 - x y^2 ~ 2^-21, error O(e^3).  The IEEE fp64 divide / sqrt sequences cost ~300 dependent cycles
@@ -191,6 +199,7 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, int n, int b, int* f
   for (; sweep < kTgMaxSweeps; ++sweep) {
     rotated = 0;
     big = 0;
+    const long long sw_c0 = clock64(), sw_t0 = tg_globaltimer();
     // A. pairs inside a block
     long long t0 = clock64();
     if (b >= 2) {
@@ -347,6 +356,14 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, int n, int b, int* f
     // Converged when nothing was rotated, or when every rotation of this sweep started from a relative
     // off-diagonal below 1e-10: cyclic Jacobi converges quadratically, so the sweep leaves ~1e-20, far
     // below the 7e-15 threshold, and the confirmation sweep (dot products only, ~60% of a sweep) is skipped.
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const int slot = (int)g_tg_dbg[7];
+      if (slot < 32) {
+        g_tg_trace[16 + 2 * slot] = clock64() - sw_c0;
+        g_tg_trace[16 + 2 * slot + 1] = tg_globaltimer() - sw_t0;
+        g_tg_dbg[7] = slot + 1;
+      }
+    }
     if (!any || !anybig) { ++sweep; break; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -379,8 +396,16 @@ __global__ void __launch_bounds__(kTgThreads, 1) tica_solve_grid_kernel(
   extern __shared__ __align__(16) double tg_sm[];
   cg::grid_group grid = cg::this_grid();
   const long long t_begin = clock64();
-  if (blockIdx.x == 0 && threadIdx.x == 0)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int q = 0; q < 8; ++q) g_tg_dbg[q] = 0;
+    for (int q = 16; q < 80; ++q) g_tg_trace[q] = 0;
+  }
+  if (blockIdx.x < 16 && threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_tg_trace[blockIdx.x] = smid;
+  }
+  const long long gt_begin = tg_globaltimer();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gnt = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31, gwarp = gtid >> 5, nwarps = gnt >> 5;
   const size_t dd = (size_t)d * d;
@@ -571,7 +596,14 @@ __global__ void __launch_bounds__(kTgThreads, 1) tica_solve_grid_kernel(
     if (lane == 0) evals[k] = ldg_cg(ws.s + __ldcg(ws.order + k));
   }
   for (int k = m + gtid; k < d; k += gnt) evals[k] = 0.0;
-  if (gtid == 0) { rank_out[0] = m; rank_out[1] = sweeps1; rank_out[2] = sweeps2; g_tg_dbg[5] = clock64() - t_begin; }
+  if (gtid == 0) { rank_out[0] = m; rank_out[1] = sweeps1; rank_out[2] = sweeps2; g_tg_dbg[5] = clock64() - t_begin; g_tg_dbg[6] = tg_globaltimer() - gt_begin; }
+}
+
+int tica_grid_debug_trace(int64_t* out80) {
+  long long h[80];
+  PMB_CUDA(cudaMemcpyFromSymbol(h, g_tg_trace, sizeof(h)));
+  for (int i = 0; i < 80; ++i) out80[i] = h[i];
+  return PMB_OK;
 }
 
 int tica_grid_debug_counters(int64_t* out8) {
@@ -596,8 +628,7 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   // rows per block: the 2 b rows of a block pair (d doubles each) must fit in shared memory
   // b = 8: d / 16 CTAs own a block pair.  Measured on B200 for d = 256 (cycles of the whole solve):
   // b = 16 -> 16.8 M, b = 8 -> 15.6 M (half the warps per SM contend for the fp64 pipe, twice the grid
-  // barriers), b = 4 -> 19.7 M.  b = 8 also keeps 16 instead of 8 SMs working, which matters for the clock
-  // (see the note at the launch below).
+  // barriers), b = 4 -> 19.7 M.
   int blk = 8;
   while (blk > 1 && (size_t)2 * blk * d * sizeof(double) > (size_t)200 * 1024) blk >>= 1;
   const size_t smem = (size_t)2 * blk * (d + 1) * sizeof(double);   // rows + their squared norms
@@ -618,12 +649,9 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   int nb = (d + blk - 1) / blk;
   if (nb & 1) ++nb;
   // One CTA per SM even though only nb / 2 of them own a block pair: the others join the grid barriers and
-  // the dense phases.  The wall time of this kernel is bimodal between (and sometimes within) processes on
-  // the same GPU: identical clock64 cycle count, but an effective SM clock of 0.6-1.2 GHz instead of
-  // 1.96 GHz in the slow state.  It tracks the number of SMs doing real work: a grid of 8 CTAs was worst,
-  // 8 working CTAs in a full grid (b = 16) still hit it in about half of the processes, 16 working CTAs
-  // (b = 8) rarely, 32 (b = 4) never in the runs made; a hand-written arrival-counter barrier or keeping the
-  // idle SMs busy with FMA chains (light or heavy) changed nothing (A/B on one box, round 1).
+  // the dense phases.  (The in-kernel trace -- clock64 against %globaltimer per sweep, pmb_debug_trace_tica --
+  // shows the kernel at the full SM clock in every run; stage-time outliers seen in round 1 were host-side
+  // allocator stalls in front of the launch, not the kernel.)
   int grid = sms;
   if (grid < nb / 2) grid = nb / 2;
   if (grid > sms * per_sm) grid = sms * per_sm;

@@ -638,6 +638,54 @@ def test_pipeline_properties_at_scale():
     np.testing.assert_array_equal(lab[sl], lo)
 
 
+def test_pipeline_properties_at_full_size():
+    """The bench configuration itself (C4: 10 M frames x 99 atoms -> 256 features -> 10 TICA dims, K = 1000,
+    20 Lloyd iterations): size-independent properties of every stage's result, plus oracle spot checks on
+    slices the CPU can afford."""
+    from pmarlo_b200.pipeline import run_pipeline
+    import bench
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~40 GB of HBM")
+    n_traj, fpt = 80, 125_000
+    wl = bench.make_workload(n_traj=n_traj, frames_per_traj=fpt, device=dev(), seed=4000)
+    cfg = bench.bench_config()
+    res = run_pipeline(wl.xyz, wl.segs, wl.plan, cfg)
+    K, n = cfg.n_states, n_traj * fpt
+    # counts: every (t, t + lag) pair inside a trajectory is counted exactly once
+    C = res.counts.cpu().numpy()
+    assert int(C.sum()) == n_traj * (fpt - cfg.msm_lag) == wl.segs.n_pairs(cfg.msm_lag)
+    lab = res.labels.cpu().numpy()
+    assert lab.shape == (n,) and lab.min() >= 0 and lab.max() < K
+    # row sums of the count matrix = population of each state over the frames that start a pair
+    starts = np.ones(n, dtype=bool)
+    starts.reshape(n_traj, fpt)[:, fpt - cfg.msm_lag:] = False
+    np.testing.assert_array_equal(C.sum(axis=1), np.bincount(lab[starts], minlength=K))
+    ends = np.ones(n, dtype=bool)
+    ends.reshape(n_traj, fpt)[:, :cfg.msm_lag] = False
+    np.testing.assert_array_equal(C.sum(axis=0), np.bincount(lab[ends], minlength=K))
+    # reversible MSM: stochastic, stationary, detailed balance; spectrum inside the unit disc
+    T, pi = res.T.cpu().numpy(), res.pi.cpu().numpy()
+    np.testing.assert_allclose(T.sum(axis=1), 1.0, atol=1e-12)
+    np.testing.assert_allclose(pi.sum(), 1.0, atol=1e-12)
+    np.testing.assert_allclose(pi @ T, pi, atol=1e-10)
+    F = pi[:, None] * T
+    np.testing.assert_allclose(F, F.T, atol=1e-12)
+    ev = res.eigenvalues.cpu().numpy()
+    assert abs(ev[0] - 1.0) < 1e-9 and np.all(np.abs(ev) <= 1 + 1e-9) and np.all(np.diff(np.abs(ev)) <= 1e-12)
+    # labels are the exact fp64 argmin for the final centres; the assignment is idempotent
+    centers = res.centers.cpu().numpy()
+    for sl in (slice(0, 20000), slice(n - 20000, n), slice(5_000_000, 5_020_000)):
+        lo, _ = oracle.kmeans.assign(res.Y[sl].cpu().numpy().astype(np.float64), centers)
+        np.testing.assert_array_equal(lab[sl], lo)
+    from pmarlo_b200 import kernels
+    again = kernels.kmeans_assign(res.Y, res.centers, hints=res.labels.clone())
+    assert torch.equal(again, res.labels)
+    ts = res.timescales
+    assert ts is None or np.all(np.asarray(ts)[:-1] >= np.asarray(ts)[1:])
+
+
 # ----------------------------------------------------------------------------- discretize_dataset (a7)
 def _discretize_dataset_inputs(z):
     seg = [int(v) for v in z["seg"]]
