@@ -248,3 +248,169 @@ def select_lag_time_ck(dtrajs, n_states: int, tau_candidates: Sequence[int], fac
         if mses[j] <= mses[int(np.nanargmin(mses))] + NUMERIC_MIN_POSITIVE:
             sel = 2
     return sel, taus, mses, its
+
+
+# ----------------------------------------------------------------------------- ck_its_selector.py
+@dataclass
+class LagEvaluationResult:
+    """ck_its_selector.py:23-37."""
+
+    lag: int
+    ck_error: float
+    coverage_fraction: float
+    median_count: int
+    n_macrostates: int
+    n_microstates: int
+    passed_sanity: bool
+    failure_reason: Optional[str] = None
+    timescales: Optional[np.ndarray] = None
+    eigenvalue_gap: Optional[float] = None
+    diag_mass: Optional[float] = None
+
+
+def coverage_fraction(C: np.ndarray) -> float:
+    """ck_its_selector.py:86-102."""
+    if C.size == 0:
+        return 0.0
+    n, labels = connected_components(((C + C.T) > 0).astype(int), directed=False, return_labels=True)
+    if n == 0:
+        return 0.0
+    return float(int(np.max(np.bincount(labels)))) / float(C.shape[0])
+
+
+def median_count(C: np.ndarray) -> int:
+    """ck_its_selector.py:105-114."""
+    if C.size == 0:
+        return 0
+    sc = C.sum(axis=0) + C.sum(axis=1)
+    return int(np.median(sc[sc > 0])) if np.any(sc > 0) else 0
+
+
+def auto_determine_macrostates(T: np.ndarray, min_macro: int = 3, max_macro: int = 6) -> int:
+    """ck_its_selector.py:117-155: the largest eigenvalue gap lambda_{m-1} - lambda_m for m in the range."""
+    if T.size == 0 or T.shape[0] < min_macro:
+        return min_macro
+    evals = np.sort(np.real(np.linalg.eigvals(T)))[::-1]
+    if len(evals) < min_macro + 1:
+        return min_macro
+    max_gap, best = 0.0, min_macro
+    for m in range(min_macro, min(max_macro + 1, len(evals))):
+        gap = float(evals[m - 1] - evals[m])
+        if gap > max_gap:
+            max_gap, best = gap, m
+    return best
+
+
+def ck_l1_error(T_pred: np.ndarray, T_obs: np.ndarray) -> float:
+    """ck_its_selector.py:211-226."""
+    l1_obs = float(np.sum(np.abs(T_obs)))
+    if l1_obs < NUMERIC_MIN_POSITIVE:
+        return float("inf")
+    return float(np.sum(np.abs(T_pred - T_obs))) / l1_obs
+
+
+def rev_msm_summary(dtrajs, lag: int, n_timescales: Optional[int] = None):
+    """What ck_its_selector.py:397-404 takes from deeptime's ``MaximumLikelihoodMSM(lagtime, reversible=True)
+    .fit(dtrajs).fetch_model()``: sliding counts, largest strongly connected set, reversible MLE (oracle.msm),
+    timescales -lag / ln|lambda_i| (i >= 2) and the transition matrix of the active set."""
+    from . import counts as _counts
+    from . import msm as _msm
+
+    K = int(max(int(np.max(t)) for t in dtrajs)) + 1
+    C = _counts.count_lagged(dtrajs, K, int(lag), mode="endpoint").astype(float)
+    lcs = _msm.largest_connected_set(C)
+    T, pi, _ = _msm.mle_rev(C[np.ix_(lcs, lcs)])
+    ev = _msm.eigenvalues_rev(T, pi, None if n_timescales is None else min(n_timescales + 1, T.shape[0]))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ts = -float(lag) / np.log(np.abs(ev[1:]))
+    return ts, T
+
+
+def evaluate_single_lag(dtrajs, lag, horizons, n_states, coverage_threshold, min_median_count,
+                        diag_mass_threshold, macro_lumper=None, n_timescales=None) -> LagEvaluationResult:
+    """ck_its_selector.py:279-459."""
+    from . import msm as _msm
+
+    try:
+        C_tau = count_endpoint(dtrajs, n_states, lag)
+        cov, med = coverage_fraction(C_tau), median_count(C_tau)
+        reason = None
+        if cov < coverage_threshold:
+            reason = f"Coverage {cov:.2%} < {coverage_threshold:.2%}"
+        elif med < min_median_count:
+            reason = f"Median count {med} < {min_median_count}"
+        if reason is not None:
+            return LagEvaluationResult(lag, float("inf"), cov, med, 0, n_states, False, reason)
+        T_tau = row_normalize_strict(C_tau)
+        pi = _msm.stationary_distribution(T_tau)
+        n_cand = auto_determine_macrostates(T_tau, 2, 6)
+        labels = None
+        if macro_lumper is not None:
+            try:
+                labels = macro_lumper(T_tau, n_cand)
+            except Exception:
+                labels = None
+        n_macro, gap = 0, None
+        if labels is not None:
+            labels = np.asarray(labels, dtype=np.int64)
+            n_macro = n_cand
+            chi = np.zeros((T_tau.shape[0], n_macro))
+            chi[np.arange(T_tau.shape[0]), labels] = 1.0
+            err = 0.0
+            for k in horizons:
+                cp = chi.T @ np.diag(pi)
+                den = cp @ chi + np.eye(n_macro) * NUMERIC_MIN_POSITIVE
+                T_pred = cp @ np.linalg.matrix_power(T_tau, k) @ chi @ np.linalg.inv(den)
+                T_obs = row_normalize_strict(count_endpoint([labels[t] for t in dtrajs], n_macro, lag * k))
+                err = max(err, ck_l1_error(T_pred, T_obs))
+            evals = np.sort(np.real(np.linalg.eigvals(T_tau)))[::-1]
+            if len(evals) > n_macro:
+                gap = float(evals[n_macro - 1] - evals[n_macro])
+        else:
+            err = 0.0
+            for k in horizons:
+                T_obs = row_normalize_strict(count_endpoint(dtrajs, n_states, lag * k))
+                err = max(err, ck_l1_error(np.linalg.matrix_power(T_tau, k), T_obs))
+        diag_mass, ts = float("nan"), None
+        try:
+            ts, T_rev = rev_msm_summary(dtrajs, lag, n_timescales)
+            if T_rev.size:
+                diag_mass = float(np.trace(T_rev) / T_rev.shape[0])
+        except Exception:
+            ts = None
+        reason = None
+        if not (np.isfinite(diag_mass) and diag_mass >= diag_mass_threshold):
+            reason = (f"Diagonal mass {diag_mass:.3f} < threshold {diag_mass_threshold:.3f}"
+                      if np.isfinite(diag_mass) else "Diagonal mass undefined")
+        return LagEvaluationResult(lag, err, cov, med, n_macro, n_states, reason is None, reason, ts, gap, diag_mass)
+    except Exception as e:
+        return LagEvaluationResult(lag, float("inf"), 0.0, 0, 0, n_states, False, f"Exception: {str(e)}")
+
+
+def select_optimal_lag_ck_its(dtrajs, tau_candidates=None, horizons=None, ck_threshold=0.15,
+                              coverage_threshold=0.98, min_median_count=100, diag_mass_threshold=0.6,
+                              macro_lumper=None, n_timescales=None):
+    """ck_its_selector.py:462-599."""
+    if not dtrajs:
+        raise ValueError("No discrete trajectories provided")
+    usable = [np.asarray(t) for t in dtrajs if t is not None and np.asarray(t).size > 0]
+    if not usable:
+        raise ValueError("Discrete trajectories contain no frames for CK analysis; "
+                         "provide trajectories with at least two time steps.")
+    tau_candidates = [25, 50, 75, 100] if tau_candidates is None else list(tau_candidates)
+    horizons = [1, 2, 3, 4, 5] if horizons is None else horizons
+    max_lag = max(0, max(int(t.size) for t in usable) - 1)
+    valid = [int(t) for t in tau_candidates if t <= max_lag]
+    if not valid:
+        raise ValueError(f"All tau candidates exceed the available trajectory length (max supported lag {max_lag}). "
+                         "Provide smaller lag values or shorter horizons.")
+    n_states = int(max(np.max(t) for t in usable)) + 1
+    evals = [evaluate_single_lag(usable, lag, horizons, n_states, coverage_threshold, min_median_count,
+                                 diag_mass_threshold, macro_lumper, n_timescales) for lag in sorted(valid)]
+    for r in sorted(evals, key=lambda r: r.lag):
+        if r.passed_sanity and r.ck_error <= ck_threshold:
+            return r.lag, evals
+    passing = [r for r in evals if r.passed_sanity]
+    if passing:
+        return min(passing, key=lambda r: r.ck_error).lag, evals
+    return min(tau_candidates), evals

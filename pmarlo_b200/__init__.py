@@ -9,7 +9,8 @@ from __future__ import annotations
 from ._lib import LIB_PATH, Pmb200Error, launch_count, load as load_library  # noqa: F401
 from .clustering import ClusteringResult, cluster_microstates  # noqa: F401
 from .discretize import MSMDiscretizationResult, discretize_dataset  # noqa: F401
-from .ck import CKRunResult, CKTestResult, ck_rms_error, run_ck  # noqa: F401
+from .ck import (CKRunResult, CKTestResult, LagEvaluationResult, ck_rms_error, run_ck,  # noqa: F401
+                 select_optimal_lag_ck_its)
 from .enhanced_msm import EnhancedMSM  # noqa: F401
 from .features import compute_features, featurize_trajectory, trig_expand_periodic  # noqa: F401
 from .msm import (  # noqa: F401

@@ -1,6 +1,9 @@
 """Chapman-Kolmogorov test on the device kernels.
 
 Mirrors
+* ``ck_its_selector.select_optimal_lag_ck_its`` ck_its_selector.py:462-599 (``_evaluate_single_lag`` :279-459,
+  ``LagEvaluationResult`` :23-37): per candidate lag the counts at tau and k*tau, coverage / median-count
+  guardrails, macro- or microstate CK error, reversible MLE timescales and the diagonal-mass guardrail;
 * ``ck_runner.run_ck(dtrajs, lag_time, output_dir, macro_k=4, min_trans=50, top_n_micro=50,
   factors=(2,3,4,5))`` ck_runner.py:293-332 with ``CKRunResult`` :32-48 and ``ck_rms_error`` :51-66;
 * ``CKMixin.compute_ck_test_micro`` _ck.py:61-110 and ``CKMixin.select_lag_time_ck`` _ck.py:159-175
@@ -46,7 +49,7 @@ logger = logging.getLogger("pmarlo")
 NUMERIC_MAX_RATE = 0.999999   # pmarlo/constants.py
 
 __all__ = ["CKRunResult", "CKTestResult", "ck_rms_error", "run_ck", "compute_ck_test_micro",
-           "select_lag_time_ck", "LabelShard"]
+           "select_lag_time_ck", "LabelShard", "LagEvaluationResult", "select_optimal_lag_ck_its"]
 
 
 @dataclass
@@ -390,3 +393,193 @@ def select_lag_time_ck(dtrajs, n_states: int, tau_candidates: Sequence[int], fac
             for t, m in zip(taus, mses):
                 w.writerow([int(t), float(m)])
     return int(selected), taus, mses, its
+
+
+# ----------------------------------------------------------------------------- ck_its_selector.py
+@dataclass
+class LagEvaluationResult:
+    """ck_its_selector.py:23-37."""
+
+    lag: int
+    ck_error: float
+    coverage_fraction: float
+    median_count: int
+    n_macrostates: int
+    n_microstates: int
+    passed_sanity: bool
+    failure_reason: Optional[str] = None
+    timescales: Optional[np.ndarray] = None
+    eigenvalue_gap: Optional[float] = None
+    diag_mass: Optional[float] = None
+
+
+def _coverage_and_median(C: np.ndarray) -> tuple[float, int]:
+    """ck_its_selector.py:86-114 on the K x K count matrix (host: graph bookkeeping, a K-sized median)."""
+    if C.size == 0:
+        return 0.0, 0
+    n, labels = connected_components(((C + C.T) > 0).astype(int), directed=False, return_labels=True)
+    cov = 0.0 if n == 0 else float(int(np.max(np.bincount(labels)))) / float(C.shape[0])
+    sc = C.sum(axis=0) + C.sum(axis=1)
+    med = int(np.median(sc[sc > 0])) if np.any(sc > 0) else 0
+    return cov, med
+
+
+def _auto_determine_macrostates(evals_desc: np.ndarray, n: int, min_macro: int, max_macro: int) -> int:
+    """ck_its_selector.py:117-155 given the sorted real parts of the spectrum of T."""
+    if n < min_macro or len(evals_desc) < min_macro + 1:
+        return min_macro
+    max_gap, best = 0.0, min_macro
+    for m in range(min_macro, min(max_macro + 1, len(evals_desc))):
+        gap = float(evals_desc[m - 1] - evals_desc[m])
+        if gap > max_gap:
+            max_gap, best = gap, m
+    return best
+
+
+def _l1_error(T_pred: torch.Tensor, T_obs: torch.Tensor) -> float:
+    """ck_its_selector.py:211-226."""
+    l1_obs = float(T_obs.abs().sum().item())
+    if l1_obs < NUMERIC_MIN_POSITIVE:
+        return float("inf")
+    return float((T_pred - T_obs).abs().sum().item()) / l1_obs
+
+
+def _stationary_device(T: torch.Tensor) -> torch.Tensor:
+    """Left Perron vector of a row-stochastic matrix (``_stationary_from_T``, _msm_utils.py:78-88): one
+    K x K linear solve on the device, the redundant balance equation replaced by sum(pi) = 1."""
+    n = int(T.shape[0])
+    A = T.t() - torch.eye(n, dtype=T.dtype, device=T.device)
+    A[n - 1, :] = 1.0
+    b = torch.zeros((n,), dtype=T.dtype, device=T.device)
+    b[n - 1] = 1.0
+    pi = torch.linalg.solve(A, b).abs()
+    return pi / pi.sum()
+
+
+def _reversible_summary(shard: LabelShard, n_states: int, lag: int, n_timescales: int):
+    """What ck_its_selector.py:397-404 takes from ``MaximumLikelihoodMSM(lagtime, reversible=True).fit(dtrajs)``:
+    sliding counts (K7) -> largest strongly connected set (host graph bookkeeping) -> reversible MLE (K8) ->
+    leading timescales (K9) and trace(T) / n over the active set."""
+    from .msm import largest_connected_set
+
+    C = kernels.count_lagged(shard.labels, shard.offsets, int(n_states), int(lag))
+    lcs = largest_connected_set(C.cpu().numpy())
+    act = torch.zeros((int(n_states),), dtype=torch.uint8, device=C.device)
+    act[torch.from_numpy(lcs).to(C.device)] = 1
+    T, pi, info = kernels.mle_rev(C.to(torch.float64), act, alpha=0.0)
+    if int(info[1].item()) < 0:
+        raise ValueError("reversible MLE failed: a state of the active set has no outgoing counts")
+    idx = torch.from_numpy(lcs).to(C.device)
+    diag_mass = float(T.diagonal()[idx].sum().item()) / float(lcs.size) if lcs.size else float("nan")
+    k = int(min(int(n_timescales) + 1, lcs.size))
+    ev, _ = kernels.eig_rev_topk(T, pi, k)
+    ev = ev.cpu().numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ts = -float(lag) / np.log(np.abs(ev[1:]))
+    return ts, diag_mass
+
+
+def _evaluate_single_lag(shard: LabelShard, lag: int, horizons: Sequence[int], n_states: int,
+                         coverage_threshold: float, min_median_count: int, diag_mass_threshold: float,
+                         macro_lumper, n_timescales: int) -> LagEvaluationResult:
+    """ck_its_selector.py:279-459."""
+    logger.info("[CK-ITS] Evaluating lag=%d", lag)
+    try:
+        C_tau = shard.counts(n_states, lag)
+        cov, med = _coverage_and_median(C_tau.cpu().numpy())
+        reason = None
+        if cov < coverage_threshold:
+            reason = f"Coverage {cov:.2%} < {coverage_threshold:.2%}"
+        elif med < min_median_count:
+            reason = f"Median count {med} < {min_median_count}"
+        if reason is not None:
+            logger.warning("[CK-ITS] Lag %d failed sanity: %s", lag, reason)
+            return LagEvaluationResult(lag, float("inf"), cov, med, 0, n_states, False, reason)
+        T_tau = _row_normalize_strict(C_tau)
+        evals = _eigvals_desc(T_tau)
+        n_cand = _auto_determine_macrostates(evals, int(T_tau.shape[0]), 2, 6)
+        labels = None
+        if macro_lumper is not None:
+            try:
+                labels = macro_lumper(T_tau.cpu().numpy(), n_cand)
+            except Exception as exc:                                      # ck_its_selector.py:335-338
+                logger.warning("[CK-ITS] PCCA+ exception for lag %d: %s", lag, exc)
+        n_macro, gap, err = 0, None, 0.0
+        if labels is not None:
+            labels = np.asarray(labels, dtype=np.int64)
+            n_macro = n_cand
+            pi = _stationary_device(T_tau)
+            chi = torch.zeros((int(T_tau.shape[0]), n_macro), dtype=torch.float64, device=T_tau.device)
+            chi[torch.arange(int(T_tau.shape[0]), device=T_tau.device), torch.from_numpy(labels).to(T_tau.device)] = 1.0
+            cp = chi.t() * pi[None, :]                                    # chi^T diag(pi)
+            den = cp @ chi + torch.eye(n_macro, dtype=torch.float64, device=T_tau.device) * NUMERIC_MIN_POSITIVE
+            macro = shard.relabel(labels.astype(np.int32))
+            for k in horizons:
+                T_pred = cp @ torch.linalg.matrix_power(T_tau, int(k)) @ chi @ torch.linalg.inv(den)
+                T_obs = _row_normalize_strict(macro.counts(n_macro, lag * int(k)))
+                err = max(err, _l1_error(T_pred, T_obs))
+            if len(evals) > n_macro:
+                gap = float(evals[n_macro - 1] - evals[n_macro])
+        else:
+            if macro_lumper is not None:
+                logger.warning("[CK-ITS] PCCA+ failed for lag %d, using microstate CK test fallback", lag)
+            for k in horizons:
+                T_obs = _row_normalize_strict(shard.counts(n_states, lag * int(k)))
+                err = max(err, _l1_error(torch.linalg.matrix_power(T_tau, int(k)), T_obs))
+        diag_mass, ts = float("nan"), None
+        try:
+            ts, diag_mass = _reversible_summary(shard, n_states, lag, n_timescales)
+        except Exception as exc:
+            logger.warning("[CK-ITS] Failed to compute timescales for lag %d: %s", lag, exc)
+            ts = None
+        reason = None
+        if not (np.isfinite(diag_mass) and diag_mass >= diag_mass_threshold):
+            reason = (f"Diagonal mass {diag_mass:.3f} < threshold {diag_mass_threshold:.3f}"
+                      if np.isfinite(diag_mass) else "Diagonal mass undefined")
+            logger.warning("[CK-ITS] Lag %d failed diagonal-mass guardrail: %s", lag, reason)
+        return LagEvaluationResult(lag, err, cov, med, n_macro, n_states, reason is None, reason, ts, gap, diag_mass)
+    except Exception as e:
+        logger.error("[CK-ITS] Failed to evaluate lag %d: %s", lag, e)
+        return LagEvaluationResult(lag, float("inf"), 0.0, 0, 0, n_states, False, f"Exception: {str(e)}")
+
+
+def select_optimal_lag_ck_its(dtrajs: Sequence[np.ndarray], tau_candidates: Optional[List[int]] = None,
+                              horizons: Optional[List[int]] = None, ck_threshold: float = 0.15,
+                              coverage_threshold: float = 0.98, min_median_count: int = 100,
+                              diag_mass_threshold: float = 0.6, *, macro_lumper=None,
+                              n_timescales: int = 10):
+    """``ck_its_selector.select_optimal_lag_ck_its`` (ck_its_selector.py:462-599): the smallest lag whose CK
+    error is below the threshold among those that pass the coverage, median-count and diagonal-mass
+    guardrails; fallbacks as in the reference.  Returns (selected_lag, [LagEvaluationResult]).
+
+    Differences, both documented in INTEGRATION.md: PCCA+ is the injected ``macro_lumper(T, n_macro)`` (None:
+    microstate CK test, the reference's fallback); ``LagEvaluationResult.timescales`` holds the leading
+    ``n_timescales`` values (the reference stores all n - 1; they do not enter the selection)."""
+    if dtrajs is None or len(dtrajs) == 0:
+        raise ValueError("No discrete trajectories provided")
+    usable = [np.asarray(t) for t in dtrajs if t is not None and np.asarray(t).size > 0]
+    if not usable:
+        raise ValueError("Discrete trajectories contain no frames for CK analysis; "
+                         "provide trajectories with at least two time steps.")
+    tau_candidates = [25, 50, 75, 100] if tau_candidates is None else list(tau_candidates)
+    horizons = [1, 2, 3, 4, 5] if horizons is None else list(horizons)
+    max_lag = max(0, max(int(t.size) for t in usable) - 1)                # ck_its_selector.py:40-67
+    valid = [int(t) for t in tau_candidates if t <= max_lag]
+    ignored = [int(t) for t in tau_candidates if t > max_lag]
+    if ignored:
+        logger.warning("[CK-ITS] Ignoring %d tau candidates that exceed available length (max supported lag=%d): %s",
+                       len(ignored), max_lag, ignored)
+    if not valid:
+        raise ValueError(f"All tau candidates exceed the available trajectory length (max supported lag {max_lag}). "
+                         "Provide smaller lag values or shorter horizons.")
+    n_states = int(max(int(np.max(t)) for t in usable)) + 1
+    shard = LabelShard.from_dtrajs(usable)
+    evaluations = [_evaluate_single_lag(shard, lag, horizons, n_states, coverage_threshold, min_median_count,
+                                        diag_mass_threshold, macro_lumper, n_timescales) for lag in sorted(valid)]
+    for r in sorted(evaluations, key=lambda r: r.lag):
+        if r.passed_sanity and r.ck_error <= ck_threshold:
+            return r.lag, evaluations
+    passing = [r for r in evaluations if r.passed_sanity]
+    if passing:
+        return min(passing, key=lambda r: r.ck_error).lag, evaluations
+    return min(tau_candidates), evaluations

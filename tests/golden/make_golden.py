@@ -20,6 +20,7 @@ It imports the reference functions that run without deeptime/mdtraj
                      (discretize.py:406-514; sklearn KMeans.predict labels)
 * ck.npz          -- markov_state_model.ck_runner.run_ck (ck_runner.py:293-332) and
                      CKMixin.compute_ck_test_micro / select_lag_time_ck (_ck.py:61-228)
+* ck_selector.npz -- markov_state_model.ck_its_selector.select_optimal_lag_ck_its (ck_its_selector.py:279-599)
 * topologies.npz  -- atom names / residue ids / coordinates (nm) parsed from
                      data/alanine-dipeptide.pdb and data/chignolin.pdb (model 1)
 """
@@ -356,7 +357,110 @@ def make_ck():
     np.savez_compressed(OUT / "ck.npz", **out)
 
 
+def _load_reference_selector():
+    """ck_its_selector.py imports deeptime's TransitionCountEstimator / MaximumLikelihoodMSM and three helpers
+    of _msm_utils (deeptime again).  It is loaded from the reference tree with
+    * ``MaximumLikelihoodMSM`` replaced by a minimal estimator built on the ORACLE's restatement of
+      deeptime (sliding counts, largest connected set, reversible MLE, timescales) -- so this fixture pins the
+      reference's control flow, thresholds, CK errors, coverage / median-count / diagonal-mass logic and the
+      selection rule, NOT deeptime's MLE arithmetic (that part stays "parity unpinned", DESIGN.md section 5);
+    * ``_row_normalize`` as in _load_reference_ck, ``_stationary_from_T`` by the Perron vector (numpy),
+      ``pcca_like_macrostates`` by a switchable stand-in (None, or contiguous blocks of states)."""
+    import importlib.util
+    from unittest import mock
+
+    sys.path.insert(0, str(OUT.parent.parent))
+    import oracle.ck as ock
+    import oracle.msm as omsm
+
+    mods = _load_reference_ck()          # installs the _refmsm package and its _msm_utils stub
+    utils = sys.modules["_refmsm._msm_utils"]
+    utils._stationary_from_T = lambda T: omsm.stationary_distribution(np.asarray(T, dtype=float))
+    state = {"blocks": False}
+
+    def pcca(T, n_macrostates=4, random_state=42):
+        if not state["blocks"]:
+            return None
+        n = T.shape[0]
+        return (np.arange(n) * int(n_macrostates)) // n
+    utils.pcca_like_macrostates = pcca
+
+    class _Model:
+        def __init__(self, ts, T):
+            self._ts, self.transition_matrix = ts, T
+
+        def timescales(self):
+            return self._ts
+
+    class MaximumLikelihoodMSM:
+        def __init__(self, lagtime, reversible=True):
+            self.lag = int(lagtime)
+
+        def fit(self, dtrajs):
+            self._m = _Model(*ock.rev_msm_summary(dtrajs, self.lag, None))
+            return self
+
+        def fetch_model(self):
+            return self._m
+
+    dt = types.ModuleType("deeptime"); dtm = types.ModuleType("deeptime.markov"); dtmm = types.ModuleType("deeptime.markov.msm")
+    dtm.TransitionCountEstimator = mock.MagicMock()
+    dtmm.MaximumLikelihoodMSM = MaximumLikelihoodMSM
+    sys.modules.update({"deeptime": dt, "deeptime.markov": dtm, "deeptime.markov.msm": dtmm})
+    spec = importlib.util.spec_from_file_location("_refmsm.ck_its_selector",
+                                                  str(REF / "src/pmarlo/markov_state_model/ck_its_selector.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["_refmsm.ck_its_selector"] = m
+    spec.loader.exec_module(m)
+    return m, state
+
+
+def make_ck_selector():
+    """ck_its_selector.select_optimal_lag_ck_its (ck_its_selector.py:462-599) with _evaluate_single_lag :279-459."""
+    import logging
+    logging.disable(logging.CRITICAL)
+    sel_mod, state = _load_reference_selector()
+    rng = np.random.default_rng(20260520)
+    base = _markov_dtrajs(rng, 12, [6000, 5000, 30], stay=0.9)
+    split = [np.concatenate([t % 6, 6 + (t[::-1] % 6)]) for t in _markov_dtrajs(rng, 12, [4000], stay=0.8)]
+    split = [split[0][:4000], split[0][4000:]]            # two disconnected halves of the state space
+    sparse = _markov_dtrajs(rng, 40, [900, 700], stay=0.5)
+    tail = [np.concatenate([t, [12]]) for t in _markov_dtrajs(rng, 12, [3000], stay=0.8)]   # state 12: empty row
+    meta = _markov_dtrajs(rng, 12, [8000, 8000], stay=0.95)
+    cases = {
+        "base": (base, dict(tau_candidates=[1, 2, 5, 10, 20000], min_median_count=50), False),
+        "strict": (base, dict(tau_candidates=[2, 5, 10], min_median_count=50, ck_threshold=0.01), False),
+        "split": (split, dict(tau_candidates=[1, 3], min_median_count=10), False),
+        "sparse": (sparse, dict(tau_candidates=[1, 2, 4], horizons=[1, 2]), False),
+        "tail": (tail, dict(tau_candidates=[1, 2], min_median_count=10, coverage_threshold=0.9), False),
+        "lowdiag": (base, dict(tau_candidates=[10, 20], min_median_count=50, diag_mass_threshold=0.9), False),
+        "macro": (meta, dict(tau_candidates=[2, 4, 8], min_median_count=50, horizons=[1, 2, 3]), True),
+    }
+    out = {"case_names": np.array(sorted(cases))}
+    for name, (dtrajs, kw, blocks) in cases.items():
+        state["blocks"] = blocks
+        sel, evs = sel_mod.select_optimal_lag_ck_its([np.asarray(t) for t in dtrajs], **kw)
+        out[f"{name}_lens"] = np.array([len(t) for t in dtrajs])
+        out[f"{name}_labels"] = np.concatenate(dtrajs).astype(np.int32)
+        out[f"{name}_kw"] = np.array(repr(kw))
+        out[f"{name}_blocks"] = np.array(blocks)
+        out[f"{name}_selected"] = np.array(sel)
+        out[f"{name}_lags"] = np.array([e.lag for e in evs])
+        out[f"{name}_ck_error"] = np.array([e.ck_error for e in evs], dtype=float)
+        out[f"{name}_coverage"] = np.array([e.coverage_fraction for e in evs], dtype=float)
+        out[f"{name}_median"] = np.array([e.median_count for e in evs])
+        out[f"{name}_n_macro"] = np.array([e.n_macrostates for e in evs])
+        out[f"{name}_passed"] = np.array([e.passed_sanity for e in evs])
+        out[f"{name}_reason"] = np.array(["" if e.failure_reason is None else e.failure_reason for e in evs])
+        out[f"{name}_diag_mass"] = np.array([np.nan if e.diag_mass is None else e.diag_mass for e in evs], dtype=float)
+        out[f"{name}_gap"] = np.array([np.nan if e.eigenvalue_gap is None else e.eigenvalue_gap for e in evs], dtype=float)
+        out[f"{name}_ts3"] = np.array([[np.nan] * 3 if e.timescales is None else list(e.timescales[:3]) for e in evs], dtype=float)
+        print("selector", name, "->", sel, [(e.lag, float(f"{e.ck_error:.4g}"), e.passed_sanity, e.n_macrostates, e.failure_reason) for e in evs])
+    np.savez_compressed(OUT / "ck_selector.npz", **out)
+
+
 if __name__ == "__main__":
+    make_ck_selector()
     make_ck()
     make_discretize()
     make_topologies()

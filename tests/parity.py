@@ -216,3 +216,38 @@ def check_ck_case(z, name, dtrajs, kw, run_ck, micro, select, rtol=1e-9):
         assert sel == int(z[f"{name}_sel"]), name
         np.testing.assert_allclose(mses, z[f"{name}_sel_mses"], rtol=rtol, atol=1e-15)
         np.testing.assert_allclose(its, z[f"{name}_sel_its"], rtol=1e-8)
+
+
+def block_lumper(T, n_macro):
+    """Stand-in for PCCA+ used by the golden generator: contiguous blocks of states."""
+    n = T.shape[0]
+    return (np.arange(n) * int(n_macro)) // n
+
+
+def selector_cases(z):
+    """Yield (name, dtrajs, kwargs, lumper) from tests/golden/ck_selector.npz."""
+    for name in [str(s) for s in z["case_names"]]:
+        lens = [int(v) for v in z[f"{name}_lens"]]
+        flat = z[f"{name}_labels"].astype(np.int64)
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        dtrajs = [flat[offs[i]:offs[i + 1]] for i in range(len(lens))]
+        kw = eval(str(z[f"{name}_kw"]), {"__builtins__": {}}, {"dict": dict})
+        yield name, dtrajs, kw, (block_lumper if bool(z[f"{name}_blocks"]) else None)
+
+
+def check_selector_case(z, name, dtrajs, kw, lumper, select, mle_rtol=1e-6):
+    sel, evs = select(dtrajs, macro_lumper=lumper, **kw)
+    assert sel == int(z[f"{name}_selected"]), name
+    assert [e.lag for e in evs] == [int(v) for v in z[f"{name}_lags"]], name
+    np.testing.assert_allclose([e.ck_error for e in evs], z[f"{name}_ck_error"], rtol=1e-8, err_msg=name)
+    np.testing.assert_allclose([e.coverage_fraction for e in evs], z[f"{name}_coverage"], rtol=1e-12, err_msg=name)
+    assert [e.median_count for e in evs] == [int(v) for v in z[f"{name}_median"]], name
+    assert [e.n_macrostates for e in evs] == [int(v) for v in z[f"{name}_n_macro"]], name
+    assert [bool(e.passed_sanity) for e in evs] == [bool(v) for v in z[f"{name}_passed"]], name
+    assert ["" if e.failure_reason is None else e.failure_reason for e in evs] == [str(v) for v in z[f"{name}_reason"]], name
+    dm = np.array([np.nan if e.diag_mass is None else e.diag_mass for e in evs], dtype=float)
+    np.testing.assert_allclose(dm, z[f"{name}_diag_mass"], rtol=mle_rtol, equal_nan=True, err_msg=name)
+    gap = np.array([np.nan if e.eigenvalue_gap is None else e.eigenvalue_gap for e in evs], dtype=float)
+    np.testing.assert_allclose(gap, z[f"{name}_gap"], rtol=1e-8, atol=1e-12, equal_nan=True, err_msg=name)
+    ts = np.array([[np.nan] * 3 if e.timescales is None else list(np.asarray(e.timescales)[:3]) for e in evs], dtype=float)
+    np.testing.assert_allclose(ts, z[f"{name}_ts3"], rtol=mle_rtol, equal_nan=True, err_msg=name)

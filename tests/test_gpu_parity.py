@@ -898,3 +898,13 @@ def test_ck_at_scale_against_oracle():
     shard = ck.LabelShard.from_dtrajs(dtrajs)
     again = ck.run_ck(shard, output_dir=None, **kw)
     assert again.mse == got.mse
+
+
+def test_ck_lag_selector_matches_reference_golden(golden):
+    """select_optimal_lag_ck_its on the device kernels against the vectors produced by the reference's
+    ck_its_selector.py (reversible-MLE quantities to 1e-6, everything else to rounding)."""
+    from pmarlo_b200 import ck
+
+    z = golden("ck_selector")
+    for name, dtrajs, kw, lumper in parity.selector_cases(z):
+        parity.check_selector_case(z, name, dtrajs, kw, lumper, ck.select_optimal_lag_ck_its, mle_rtol=1e-6)

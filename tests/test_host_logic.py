@@ -262,3 +262,25 @@ def test_ck_host_bookkeeping_on_the_kernel_contracts(monkeypatch, golden, tmp_pa
     ref = oracle.ck.run_ck([s], 5, macro_k=3, min_trans=20, macro_lumper=lambda T, k: blocks)
     assert got.mode == ref.mode == "macro"
     np.testing.assert_allclose([got.mse[k] for k in (2, 3, 4, 5)], [ref.mse[k] for k in (2, 3, 4, 5)], rtol=1e-9)
+
+
+def test_ck_lag_selector_host_logic_on_the_kernel_contracts(monkeypatch, golden):
+    """pmarlo_b200.ck.select_optimal_lag_ck_its against the reference's golden vectors with the device
+    kernels replaced by numpy statements of their contracts (guardrails, macro / micro CK error, diagonal
+    mass, selection rule and its fallbacks, error messages)."""
+    import torch
+
+    from pmarlo_b200 import ck, kernels
+    from tests import fake_kernels, parity
+
+    fake_kernels.install(monkeypatch)
+    monkeypatch.setattr(kernels, "require_cuda", lambda: torch.device("cpu"))
+    z = golden("ck_selector")
+    for name, dtrajs, kw, lumper in parity.selector_cases(z):
+        parity.check_selector_case(z, name, dtrajs, kw, lumper, ck.select_optimal_lag_ck_its, mle_rtol=1e-9)
+    with pytest.raises(ValueError, match="No discrete trajectories"):
+        ck.select_optimal_lag_ck_its([])
+    with pytest.raises(ValueError, match="contain no frames"):
+        ck.select_optimal_lag_ck_its([np.array([], dtype=int)])
+    with pytest.raises(ValueError, match="exceed the available trajectory length"):
+        ck.select_optimal_lag_ck_its([np.array([0, 1, 0, 1])], tau_candidates=[10])

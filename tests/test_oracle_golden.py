@@ -288,3 +288,21 @@ def test_ck_oracle_reference_test_cases():
                                           else rng.integers(0, 6))
     r = ock.run_ck([s], lag_time=5, macro_k=3, min_trans=20, macro_lumper=lambda T, k: blocks)
     assert r.mode == "macro" and sorted(r.mse) == [2, 3, 4, 5]
+
+
+def test_ck_selector_oracle_matches_reference(golden):
+    """oracle.ck.select_optimal_lag_ck_its against the reference's ck_its_selector.py (control flow, CK errors,
+    coverage / median-count / diagonal-mass guardrails, selection rule; see make_golden._load_reference_selector)."""
+    from oracle import ck as ock
+    from tests import parity
+
+    z = golden("ck_selector")
+    n = 0
+    for name, dtrajs, kw, lumper in parity.selector_cases(z):
+        parity.check_selector_case(z, name, dtrajs, kw, lumper, ock.select_optimal_lag_ck_its, mle_rtol=1e-12)
+        n += 1
+    assert n == 7
+    with pytest.raises(ValueError, match="No discrete trajectories"):
+        ock.select_optimal_lag_ck_its([])
+    with pytest.raises(ValueError, match="exceed the available trajectory length"):
+        ock.select_optimal_lag_ck_its([np.array([0, 1, 0, 1])], tau_candidates=[10])
