@@ -395,18 +395,6 @@ def tica_debug_counters():
     return list(buf)
 
 
-def tica_debug_trace():
-    import ctypes
-
-    from pmarlo_b200 import _lib
-
-    buf = (ctypes.c_int64 * 80)()
-    _lib.check(_lib.lib().pmb_debug_trace_tica(ctypes.cast(buf, ctypes.c_void_p)), "pmb_debug_trace_tica")
-    v = list(buf)
-    sweeps = [(v[16 + 2 * i], v[17 + 2 * i]) for i in range(32) if v[16 + 2 * i] > 0]
-    return {"smid_of_cta_0_15": v[:16], "sweep_ghz": [round(c / max(t, 1), 2) for c, t in sweeps]}
-
-
 def kmeans_debug_counters():
     import ctypes
 

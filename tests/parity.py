@@ -9,6 +9,8 @@ centroids; covariances, TICA eigenvalues, T, pi, eigenvalues and timescales with
 
 from __future__ import annotations
 
+import ast
+
 import numpy as np
 import torch
 
@@ -194,7 +196,7 @@ def ck_cases(z):
         flat = z[f"{name}_labels"].astype(np.int64)
         offs = np.concatenate([[0], np.cumsum(lens)])
         dtrajs = [flat[offs[i]:offs[i + 1]] for i in range(len(lens))]
-        kw = eval(str(z[f"{name}_kw"]), {"__builtins__": {}}, {"dict": dict})  # repr of a plain dict
+        kw = ast.literal_eval(str(z[f"{name}_kw"]))  # repr of a plain dict
         yield name, dtrajs, kw
 
 
@@ -231,7 +233,7 @@ def selector_cases(z):
         flat = z[f"{name}_labels"].astype(np.int64)
         offs = np.concatenate([[0], np.cumsum(lens)])
         dtrajs = [flat[offs[i]:offs[i + 1]] for i in range(len(lens))]
-        kw = eval(str(z[f"{name}_kw"]), {"__builtins__": {}}, {"dict": dict})
+        kw = ast.literal_eval(str(z[f"{name}_kw"]))
         yield name, dtrajs, kw, (block_lumper if bool(z[f"{name}_blocks"]) else None)
 
 
