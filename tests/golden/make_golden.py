@@ -21,6 +21,7 @@ It imports the reference functions that run without deeptime/mdtraj
 * ck.npz          -- markov_state_model.ck_runner.run_ck (ck_runner.py:293-332) and
                      CKMixin.compute_ck_test_micro / select_lag_time_ck (_ck.py:61-228)
 * ck_selector.npz -- markov_state_model.ck_its_selector.select_optimal_lag_ck_its (ck_its_selector.py:279-599)
+* macro.npz       -- _msm_utils.compute_macro_populations / lump_micro_to_macro_T / compute_macro_mfpt
 * topologies.npz  -- atom names / residue ids / coordinates (nm) parsed from
                      data/alanine-dipeptide.pdb and data/chignolin.pdb (model 1)
 """
@@ -459,7 +460,37 @@ def make_ck_selector():
     np.savez_compressed(OUT / "ck_selector.npz", **out)
 
 
+def make_macro():
+    """_msm_utils.compute_macro_populations / lump_micro_to_macro_T / compute_macro_mfpt (_msm_utils.py:103-162):
+    pure numpy functions of a module that imports deeptime at the top, loaded with deeptime mocked."""
+    import importlib.util
+    from unittest import mock
+
+    for name in ("deeptime", "deeptime.markov", "deeptime.markov.msm", "deeptime.markov.tools",
+                 "deeptime.markov.tools.analysis", "deeptime.markov.tools.estimation",
+                 "deeptime.markov.tools.estimation.dense", "deeptime.markov.tools.estimation.dense.transition_matrix"):
+        sys.modules[name] = mock.MagicMock(name=name)
+    spec = importlib.util.spec_from_file_location("_ref_msm_utils_real",
+                                                  str(REF / "src/pmarlo/markov_state_model/_msm_utils.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rng = np.random.default_rng(77)
+    K, n_macro = 60, 5
+    T = rng.random((K, K)) ** 4 + 1e-4
+    T /= T.sum(axis=1, keepdims=True)
+    w, v = np.linalg.eig(T.T)
+    pi = np.abs(np.real(v[:, np.argmax(np.real(w))])); pi /= pi.sum()
+    lab = rng.integers(0, n_macro, size=K)
+    lab[:n_macro] = np.arange(n_macro)
+    pops = m.compute_macro_populations(pi, lab)
+    Tm = m.lump_micro_to_macro_T(T, pi, lab)
+    mf = m.compute_macro_mfpt(Tm)
+    np.savez_compressed(OUT / "macro.npz", T=T, pi=pi, lab=lab, pops=pops, Tm=Tm, mfpt=mf)
+    print("macro:", pops.round(3), Tm.shape, float(mf.max()))
+
+
 if __name__ == "__main__":
+    make_macro()
     make_ck_selector()
     make_ck()
     make_discretize()

@@ -908,3 +908,10 @@ def test_ck_lag_selector_matches_reference_golden(golden):
     z = golden("ck_selector")
     for name, dtrajs, kw, lumper in parity.selector_cases(z):
         parity.check_selector_case(z, name, dtrajs, kw, lumper, ck.select_optimal_lag_ck_its, mle_rtol=1e-6)
+
+
+def test_macro_helpers_on_device(golden):
+    from pmarlo_b200 import macro
+
+    z = golden("macro")
+    np.testing.assert_allclose(macro.lump_micro_to_macro_T(z["T"], z["pi"], z["lab"]), z["Tm"], rtol=1e-12)

@@ -284,3 +284,20 @@ def test_ck_lag_selector_host_logic_on_the_kernel_contracts(monkeypatch, golden)
         ck.select_optimal_lag_ck_its([np.array([], dtype=int)])
     with pytest.raises(ValueError, match="exceed the available trajectory length"):
         ck.select_optimal_lag_ck_its([np.array([0, 1, 0, 1])], tau_candidates=[10])
+
+
+def test_macro_helpers_match_reference_golden(monkeypatch, golden):
+    """pmarlo_b200.macro against the reference's own numpy functions (tests/golden/macro.npz); the flux
+    aggregation runs through torch, here on the CPU device."""
+    import torch
+
+    from pmarlo_b200 import kernels, macro
+
+    monkeypatch.setattr(kernels, "require_cuda", lambda: torch.device("cpu"))
+    z = golden("macro")
+    np.testing.assert_allclose(macro.compute_macro_populations(z["pi"], z["lab"]), z["pops"], rtol=1e-13)
+    Tm = macro.lump_micro_to_macro_T(z["T"], z["pi"], z["lab"])
+    np.testing.assert_allclose(Tm, z["Tm"], rtol=1e-12)
+    np.testing.assert_allclose(macro.compute_macro_mfpt(Tm), z["mfpt"], rtol=1e-10)
+    assert macro.compute_macro_populations(np.zeros(0), np.zeros(0, dtype=int)).shape == (0,)
+    assert macro.lump_micro_to_macro_T(np.zeros((0, 0)), np.zeros(0), np.zeros(0, dtype=int)).shape == (0, 0)
