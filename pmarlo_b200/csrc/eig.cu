@@ -21,6 +21,7 @@ namespace cg = cooperative_groups;
 namespace pmb {
 
 constexpr int kEigJacobiMaxK = 256;
+constexpr int kLanPeriod = 8;   // re-orthogonalisation period (see lanczos_kernel)
 constexpr int kLanThreads = 256;
 
 int sym_eigvals_launch(double* A, int n, int batch, double* evals, double* scratch, int* order,
@@ -95,7 +96,8 @@ struct LanParams {
   long long* info;     // 2
   double* V;           // (m+1) x K
   double* w;           // K
-  double* z;           // K
+  double* z;           // K (second w buffer)
+  double* rs;          // 2 x K: 1/sqrt(pi), sqrt(pi)
   double* h;           // 2 x (m+1)
   double* alpha;       // m
   double* beta;        // m
@@ -132,11 +134,19 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
     }
   };
 
+  // Buffers: w is double buffered (p.w, p.z); rs = 1/sqrt(pi), sq = sqrt(pi) on the active states (0 elsewhere).
+  double* w_cur = p.w;
+  double* w_new = p.z;
+  double* rs = p.rs;
+  double* sq = p.rs + K;
   // v0: deterministic, supported on the active states
   double acc = 0.0;
   for (int e = gtid; e < K; e += gthreads) {
-    const double v = (p.pi[e] > 0.0) ? 1.0 + 0.5 * sin(0.7548776662466927 * (double)(e + 1)) : 0.0;
-    p.w[e] = v;
+    const double pe = p.pi[e];
+    const double v = (pe > 0.0) ? 1.0 + 0.5 * sin(0.7548776662466927 * (double)(e + 1)) : 0.0;
+    w_cur[e] = v;
+    rs[e] = pe > 0.0 ? 1.0 / sqrt(pe) : 0.0;
+    sq[e] = pe > 0.0 ? sqrt(pe) : 0.0;
     acc = fma(v, v, acc);
   }
   block_partial(acc);
@@ -147,63 +157,74 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
     for (int t = gtid; t < p.k; t += gthreads) p.evals[t] = 0.0;
     return;
   }
-  for (int e = gtid; e < K; e += gthreads) {
-    const double v = __ldcg(p.w + e) / nrm;
-    p.V[e] = v;
-    const double pe = p.pi[e];
-    p.z[e] = pe > 0.0 ? v / sqrt(pe) : 0.0;
-  }
-  grid.sync();
+  // The Lanczos vector v_j is never materialised on its own pass: w_cur holds the un-normalised vector and
+  // `binv` its scale, and phase A of step j both stores V[j] = binv w_cur and applies the operator to it.
+  double binv = 1.0 / nrm;
 
+  // Re-orthogonalisation schedule (periodic, Grcar / Simon): two consecutive steps out of every kLanPeriod
+  // orthogonalise w against ALL previous vectors, twice (CGS2, "twice is enough"); the steps in between only
+  // against v_{j-1} and v_j (the three-term recurrence).  Orthogonality lost to a converged Ritz vector grows
+  // by a bounded factor per step, so it stays far below sqrt(eps) over the 6 local steps and is reset to eps
+  // by the pair of full steps; the Ritz values of T_m keep full accuracy (semi-orthogonality suffices).
+  // A full step costs 5 grid barriers, a local one 3 (it was 6 for every step).
   int m_eff = 0;
   for (int j = 0; j < p.m; ++j) {
-    // A: w = D^{1/2} T z
+    const double* wc = w_cur;
+    double* wn = w_new;
+    // A: V[j] = binv w_cur;  w_new = D^{1/2} T D^{-1/2} V[j]
+    {
+      double* vj = p.V + (size_t)j * K;
+      for (int e = gtid; e < K; e += gthreads) vj[e] = __ldcg(wc + e) * binv;
+    }
     for (int i = gwarp; i < K; i += nwarps) {
-      const double pe = p.pi[i];
+      const double sqi = sq[i];
       double s = 0.0;
-      if (pe > 0.0) {
+      if (sqi > 0.0) {
         const double* Trow = p.T + (size_t)i * K;
         // four independent accumulators: four L2 round trips in flight instead of one
         double s1 = 0.0, s2 = 0.0, s3 = 0.0;
         int c = lane;
         for (; c + 96 < K; c += 128) {
-          s = fma(Trow[c], __ldcg(p.z + c), s);
-          s1 = fma(Trow[c + 32], __ldcg(p.z + c + 32), s1);
-          s2 = fma(Trow[c + 64], __ldcg(p.z + c + 64), s2);
-          s3 = fma(Trow[c + 96], __ldcg(p.z + c + 96), s3);
+          s = fma(Trow[c], __ldcg(wc + c) * rs[c], s);
+          s1 = fma(Trow[c + 32], __ldcg(wc + c + 32) * rs[c + 32], s1);
+          s2 = fma(Trow[c + 64], __ldcg(wc + c + 64) * rs[c + 64], s2);
+          s3 = fma(Trow[c + 96], __ldcg(wc + c + 96) * rs[c + 96], s3);
         }
-        for (; c < K; c += 32) s = fma(Trow[c], __ldcg(p.z + c), s);
-        s = warp_sum((s + s1) + (s2 + s3)) * sqrt(pe);
+        for (; c < K; c += 32) s = fma(Trow[c], __ldcg(wc + c) * rs[c], s);
+        s = warp_sum((s + s1) + (s2 + s3)) * sqi * binv;
       }
-      if (lane == 0) p.w[i] = s;
+      if (lane == 0) wn[i] = s;
     }
     grid.sync();
+    const bool full = (j < 2) || (j % kLanPeriod) >= kLanPeriod - 2;
+    const int i_lo = full ? 0 : (j > 0 ? j - 1 : 0);
+    const int npass = full ? 2 : 1;
     double a_j = 0.0;
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < npass; ++pass) {
       double* h = p.h + (size_t)pass * (p.m + 1);
       // B: h_i = v_i . w
-      for (int i = gwarp; i <= j; i += nwarps) {
+      for (int i = i_lo + gwarp; i <= j; i += nwarps) {
         const double* vi = p.V + (size_t)i * K;
         double s = 0.0;
         double s1 = 0.0, s2 = 0.0, s3 = 0.0;
         int c = lane;
         for (; c + 96 < K; c += 128) {
-          s = fma(__ldcg(vi + c), __ldcg(p.w + c), s);
-          s1 = fma(__ldcg(vi + c + 32), __ldcg(p.w + c + 32), s1);
-          s2 = fma(__ldcg(vi + c + 64), __ldcg(p.w + c + 64), s2);
-          s3 = fma(__ldcg(vi + c + 96), __ldcg(p.w + c + 96), s3);
+          s = fma(__ldcg(vi + c), __ldcg(wn + c), s);
+          s1 = fma(__ldcg(vi + c + 32), __ldcg(wn + c + 32), s1);
+          s2 = fma(__ldcg(vi + c + 64), __ldcg(wn + c + 64), s2);
+          s3 = fma(__ldcg(vi + c + 96), __ldcg(wn + c + 96), s3);
         }
-        for (; c < K; c += 32) s = fma(__ldcg(vi + c), __ldcg(p.w + c), s);
+        for (; c < K; c += 32) s = fma(__ldcg(vi + c), __ldcg(wn + c), s);
         s = warp_sum((s + s1) + (s2 + s3));
         if (lane == 0) h[i] = s;
       }
       grid.sync();
-      // C: w -= sum_i h_i v_i  (+ partial |w|^2 on the second pass)
+      // C: w -= sum_i h_i v_i  (+ partial |w|^2 on the last pass)
       double nn = 0.0;
       for (int e = gtid; e < K; e += gthreads) {
-        double v = __ldcg(p.w + e);
+        double v = __ldcg(wn + e);
         double v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        int i = 0;
+        int i = i_lo;
         for (; i + 3 <= j; i += 4) {
           v = fma(-__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), v);
           v1 = fma(-__ldcg(h + i + 1), __ldcg(p.V + (size_t)(i + 1) * K + e), v1);
@@ -212,25 +233,19 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
         }
         for (; i <= j; ++i) v = fma(-__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), v);
         v += (v1 + v2) + v3;
-        p.w[e] = v;
+        wn[e] = v;
         nn = fma(v, v, nn);
       }
       a_j += __ldcg(h + j);
-      if (pass == 1) block_partial(nn);
+      if (pass == npass - 1) block_partial(nn);
       grid.sync();
     }
     const double b_j = sqrt(grid_sum_partials(p.part, gridDim.x));
     if (gtid == 0) { p.alpha[j] = a_j; p.beta[j] = b_j; }
     m_eff = j + 1;
     if (!(b_j > 1e-13) || j + 1 == p.m) break;  // invariant subspace / done (uniform across the grid)
-    double* vn = p.V + (size_t)(j + 1) * K;
-    for (int e = gtid; e < K; e += gthreads) {
-      const double v = __ldcg(p.w + e) / b_j;
-      vn[e] = v;
-      const double pe = p.pi[e];
-      p.z[e] = pe > 0.0 ? v / sqrt(pe) : 0.0;
-    }
-    grid.sync();
+    binv = 1.0 / b_j;
+    { double* t = w_cur; w_cur = w_new; w_new = t; }
   }
   grid.sync();
   if (blockIdx.x != 0) return;
@@ -287,7 +302,7 @@ extern "C" size_t pmb_eig_rev_topk_ws_bytes(int K, int k, int batch, int max_ste
   if (K <= kEigJacobiMaxK)
     return ((size_t)batch * K * K + 2 * (size_t)batch * K) * sizeof(double) + (size_t)batch * K * sizeof(int) + 64;
   const int m = lanczos_steps(K, k, max_steps);
-  return ((size_t)(m + 1) * K + 2 * (size_t)K + 2 * (size_t)(m + 1) + 4 * (size_t)m + 1024) * sizeof(double);
+  return ((size_t)(m + 1) * K + 4 * (size_t)K + 2 * (size_t)(m + 1) + 4 * (size_t)m + 1024) * sizeof(double);
 }
 
 extern "C" int pmb_eig_rev_topk(const double* T, const double* pi, int K, int k, int batch, int max_steps,
@@ -334,7 +349,8 @@ extern "C" int pmb_eig_rev_topk(const double* T, const double* pi, int K, int k,
     p.V = base;
     p.w = p.V + (size_t)(m + 1) * K;
     p.z = p.w + K;
-    p.h = p.z + K;
+    p.rs = p.z + K;
+    p.h = p.rs + 2 * (size_t)K;
     p.alpha = p.h + 2 * (size_t)(m + 1);
     p.beta = p.alpha + m;
     p.ritz = p.beta + m;
