@@ -322,11 +322,29 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
   auto apply_row = [&](int i, double qi, float qfi) -> double {
     double a0 = 0.0, a1 = 0.0;
     if constexpr (REG) {
+      // No per-element branch: entries beyond K have sreg = 0 and read a clamped (valid, positive) q, so they
+      // add exactly 0.  With `if (j < K)` around every element ptxas emitted a branch per element and the 32
+      // reciprocal chains of a lane ran one after the other (measured: 4 266 cycles per row, 133 per
+      // element = the length of one LDS -> MUFU -> Newton -> FMA chain).  Batches of four independent chains;
+      // the accumulation order (even entries -> a0, odd -> a1) is unchanged, so the result is bit-identical.
 #pragma unroll
-      for (int t = 0; t < 32; t += 2) {
-        const int j0 = lane + 32 * t, j1 = j0 + 32;
-        if (j0 < K) a0 = fma(sreg[t], rcp_newton1(qi + q[j0], qfi + qf[j0]), a0);
-        if (j1 < K) a1 = fma(sreg[t + 1], rcp_newton1(qi + q[j1], qfi + qf[j1]), a1);
+      for (int t = 0; t < 32; t += 4) {
+        double den[4];
+        float denf[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          int j = lane + 32 * (t + u);
+          j = j < K ? j : K - 1;
+          den[u] = qi + q[j];
+          denf[u] = qfi + qf[j];
+        }
+        double r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = rcp_newton1(den[u], denf[u]);
+        a0 = fma(sreg[t], r[0], a0);
+        a1 = fma(sreg[t + 1], r[1], a1);
+        a0 = fma(sreg[t + 2], r[2], a0);
+        a1 = fma(sreg[t + 3], r[3], a1);
       }
     } else {
       const double* __restrict__ Srow = p.S + (size_t)i * K;
@@ -387,12 +405,21 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
   long long it = 0;
   int notconv = 1;
   long long cyc[4] = {0, 0, 0, 0};
+#ifdef PMB_MLE_PROF
+  long long prof_apply = 0;
+#endif
   while (it < p.maxiter && notconv) {
     const long long t0 = clock64();
     ++gen;
+#ifdef PMB_MLE_PROF
+    long long t0a = t0;
+#endif
     for (int i = gwarp; i < K; i += nwarps) {
       double r = 0.0;
       if (x[i] > 0.0) r = apply_row(i, q[i], qf[i]);
+#ifdef PMB_MLE_PROF
+      t0a = clock64();
+#endif
       if (lane == 0) exchange_store(gen, i, r);
     }
     const long long t1 = clock64();
@@ -401,6 +428,10 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     part = 0.0;
     for (int i = tid; i < K; i += blockDim.x) part += us[i];
     const double norm = cta_sum(part, s_red);      // includes the barrier that orders us[] writes
+#ifdef PMB_MLE_PROF
+    cyc[3] += clock64() - t2;      // own entries gathered -> every thread of the CTA has its entries (stragglers)
+    prof_apply += t0a - t0;        // the row product alone
+#endif
     double rnorm = rcp_newton1(norm, (float)norm);  // two Newton steps: full fp64 accuracy
     rnorm = fma(rnorm, fma(-norm, rnorm, 1.0), rnorm);
     int flag = 0;
@@ -420,8 +451,11 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2;
   }
   if (blockIdx.x == 0 && tid == 0) {
-    g_dbg[0] = it; g_dbg[1] = cyc[0]; g_dbg[2] = cyc[1]; g_dbg[3] = cyc[2]; g_dbg[4] = 0;
+    g_dbg[0] = it; g_dbg[1] = cyc[0]; g_dbg[2] = cyc[1]; g_dbg[3] = cyc[2]; g_dbg[4] = cyc[3];
     g_dbg[5] = gridDim.x; g_dbg[6] = REG ? 1 : 0; g_dbg[7] = 0;
+#ifdef PMB_MLE_PROF
+    g_dbg[7] = prof_apply;
+#endif
   }
   // final application with the last x: T rows and pi
   ++gen;
