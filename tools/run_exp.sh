@@ -1,8 +1,7 @@
-timeout 300 python -m pytest tests -m gpu -x -q -k "msm or its or pipeline_small" > gpurun_out/t72.log 2>&1; echo "pytest_exit=$?"; tail -n 3 gpurun_out/t72.log
-python bench.py --frames-per-gpu 1250000 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench72.log 2> gpurun_out/bench72.err; echo "bench=$?"
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/tests_gpu.log 2>&1; echo "pytest_exit=$?"; tail -n 3 gpurun_out/tests_gpu.log
+python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err; echo "bench=$?"
 python - <<'PY'
 import json
-d=json.loads([l for l in open("gpurun_out/bench72.log") if l.startswith("{")][-1])
-c=d["mle_phase_cycles"]; it=c[0]
-print("iters", it, "per iteration: compute+store", c[1]/it, "(row product", c[7]/it, ") gather own", c[2]/it, "rest", c[3]/it, "(wait all + norm", c[4]/it, ") mle ms", d["stages_ms"]["mle"], d["timescales"][:3])
+d=json.loads([l for l in open("gpurun_out/bench_default.log") if l.startswith("{")][-1])
+print(round(d["value"]/1e6,2), round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"]/1e6,2), d["mle_iters"], {k: round(v,2) for k,v in d["stages_ms"].items()})
 PY
