@@ -301,3 +301,77 @@ def test_macro_helpers_match_reference_golden(monkeypatch, golden):
     np.testing.assert_allclose(macro.compute_macro_mfpt(Tm), z["mfpt"], rtol=1e-10)
     assert macro.compute_macro_populations(np.zeros(0), np.zeros(0, dtype=int)).shape == (0,)
     assert macro.lump_micro_to_macro_T(np.zeros((0, 0)), np.zeros(0), np.zeros(0, dtype=int)).shape == (0, 0)
+
+
+def test_ck_host_logic_fuzz_against_oracle(monkeypatch):
+    """Seeded random label trajectories (rare states, unassigned frames, unused ids, short shards) through
+    run_ck, compute_ck_test_micro, select_lag_time_ck and select_optimal_lag_ck_its: the device-side host
+    logic (kernels replaced by their numpy contracts) must agree with the oracle restatement of the
+    reference, outcome by outcome (mode, factors, errors raised, selected lags)."""
+    import torch
+
+    from oracle import ck as ock
+    from pmarlo_b200 import ck, kernels
+    from tests import fake_kernels
+
+    fake_kernels.install(monkeypatch)
+    monkeypatch.setattr(kernels, "require_cuda", lambda: torch.device("cpu"))
+    rng = np.random.default_rng(321)
+
+    def chain(K, n, stay, rare):
+        P = rng.random((K, K)) ** 3 + 1e-3
+        P[:, rare] *= 0.01
+        P /= P.sum(1, keepdims=True)
+        cum = np.cumsum(stay * np.eye(K) + (1 - stay) * P, 1)
+        s = np.empty(n, dtype=np.int64)
+        s[0] = rng.integers(0, K)
+        u = rng.random(n)
+        for t in range(1, n):
+            s[t] = min(int(np.searchsorted(cum[s[t - 1]], u[t])), K - 1)
+        return s
+
+    def outcome(fn):
+        try:
+            return ("ok", fn())
+        except Exception as e:      # the reference raises (deeptime row normalisation, eigenvalue count): compare the type
+            return ("err", type(e).__name__)
+
+    for trial in range(24):
+        K = int(rng.integers(3, 20))
+        rare = list(rng.choice(K, size=int(rng.integers(0, 3)), replace=False))
+        dtr = [chain(K, int(rng.integers(20, 1200)), float(rng.uniform(0.3, 0.9)), rare)
+               for _ in range(int(rng.integers(1, 4)))]
+        if trial % 3 == 0:
+            dtr[0] = dtr[0].copy()
+            dtr[0][rng.random(dtr[0].size) < 0.05] = -1
+        if trial % 4 == 1:
+            dtr = [d + 2 for d in dtr]
+        lag = int(rng.integers(1, 5))
+        kw = dict(min_trans=int(rng.integers(1, 30)), top_n_micro=int(rng.integers(2, 25)), macro_k=int(rng.integers(2, 5)))
+        a = outcome(lambda: ock.run_ck(dtr, lag, **kw))
+        b = outcome(lambda: ck.run_ck(dtr, lag, None, **kw))
+        assert a[0] == b[0], (trial, a, b)
+        if a[0] == "ok":
+            ra, rb = a[1], b[1]
+            assert (ra.mode, sorted(ra.mse), list(ra.insufficient_k)) == (rb.mode, sorted(rb.mse), list(rb.insufficient_k)), trial
+            np.testing.assert_allclose([rb.mse[k] for k in sorted(rb.mse)], [ra.mse[k] for k in sorted(ra.mse)], rtol=1e-9, atol=1e-15)
+        else:
+            assert a[1] == b[1], (trial, a, b)
+        n_states = int(max(int(d.max()) for d in dtr)) + 1
+        ma = ock.compute_ck_test_micro(dtr, n_states, lag, max_states=kw["top_n_micro"])
+        mb = ck.compute_ck_test_micro(dtr, n_states, lag, max_states=kw["top_n_micro"])
+        assert (ma.insufficient_data, sorted(ma.mse)) == (mb.insufficient_data, sorted(mb.mse)), trial
+        np.testing.assert_allclose([mb.mse[k] for k in sorted(mb.mse)], [ma.mse[k] for k in sorted(ma.mse)], rtol=1e-9, atol=1e-15)
+        sa = outcome(lambda: ock.select_lag_time_ck(dtr, n_states, [1, 2, 3])[0])
+        sb = outcome(lambda: ck.select_lag_time_ck(dtr, n_states, [1, 2, 3])[0])
+        assert sa == sb, (trial, sa, sb)
+        if all(int(d.min()) >= 0 for d in dtr):
+            oa = ock.select_optimal_lag_ck_its(dtr, [1, 2, 4], min_median_count=5, coverage_threshold=0.7, n_timescales=3)
+            ob = ck.select_optimal_lag_ck_its(dtr, [1, 2, 4], min_median_count=5, coverage_threshold=0.7, n_timescales=3)
+            assert oa[0] == ob[0], trial
+            for ea, eb in zip(oa[1], ob[1]):
+                assert (ea.lag, ea.passed_sanity, ea.median_count, ea.n_macrostates) == \
+                       (eb.lag, eb.passed_sanity, eb.median_count, eb.n_macrostates), trial
+                assert (ea.failure_reason or "")[:9] == (eb.failure_reason or "")[:9], (trial, ea.failure_reason, eb.failure_reason)
+                if np.isfinite(ea.ck_error):
+                    np.testing.assert_allclose(eb.ck_error, ea.ck_error, rtol=1e-8)
