@@ -375,3 +375,60 @@ def test_ck_host_logic_fuzz_against_oracle(monkeypatch):
                 assert (ea.failure_reason or "")[:9] == (eb.failure_reason or "")[:9], (trial, ea.failure_reason, eb.failure_reason)
                 if np.isfinite(ea.ck_error):
                     np.testing.assert_allclose(eb.ck_error, ea.ck_error, rtol=1e-8)
+
+
+def test_numpy_models_of_two_kernel_algorithms():
+    """CPU models of two algorithmic choices made inside kernels, so that the claims in DESIGN.md are checked
+    without a GPU:
+    (1) eig.cu: Lanczos with periodic re-orthogonalisation (2 full CGS2 steps out of 8, three-term recurrence
+        in between, the schedule of lanczos_kernel) gives the Ritz values of full re-orthogonalisation on a
+        clustered spectrum; without any re-orthogonalisation a ghost copy of the top eigenvalue appears;
+    (2) tica_grid.cu: the division-free Jacobi rotation c^2 = (1 + |alpha|/r)/2, s = sign(alpha) g / (2 r c)
+        orthogonalises two rows, and the carried squared norms follow a' = a - t g, b' = b + t g."""
+    rng = np.random.default_rng(0)
+    K = 400
+    lam = np.concatenate([[1.0, 0.98994, 0.97752, 0.97577, 0.97517, 0.97441], np.sort(rng.uniform(-0.3, 0.95, K - 6))[::-1]])
+    Q, _ = np.linalg.qr(rng.standard_normal((K, K)))
+    S = (Q * lam) @ Q.T
+    S = 0.5 * (S + S.T)
+
+    def lanczos(m, period, all_full=False):
+        V = np.zeros((m + 1, K))
+        w = 1.0 + 0.5 * np.sin(0.7548776662466927 * np.arange(1, K + 1))
+        binv = 1.0 / np.linalg.norm(w)
+        alpha, beta = np.zeros(m), np.zeros(m)
+        for j in range(m):
+            V[j] = w * binv
+            wn = S @ V[j]
+            full = all_full or j < 2 or (j % period) >= period - 2
+            lo = 0 if full else max(0, j - 1)
+            a = 0.0
+            for _ in range(2 if full else 1):
+                h = V[lo:j + 1] @ wn
+                wn = wn - h @ V[lo:j + 1]
+                a += h[-1]
+            alpha[j], beta[j] = a, np.linalg.norm(wn)
+            w, binv = wn, 1.0 / beta[j]
+        Tm = np.diag(alpha) + np.diag(beta[:-1], 1) + np.diag(beta[:-1], -1)
+        ev = np.linalg.eigvalsh(Tm)
+        return ev[np.argsort(-np.abs(ev))], np.abs(V[:m] @ V[:m].T - np.eye(m)).max()
+
+    ev_full, orth_full = lanczos(150, 8, all_full=True)
+    ev_per, orth_per = lanczos(150, 8)
+    ev_none, orth_none = lanczos(150, 10 ** 6)
+    np.testing.assert_allclose(ev_per[:6], ev_full[:6], rtol=0, atol=1e-13)
+    assert orth_full < 1e-13 and orth_per < 1e-12
+    assert orth_none > 1e-3 and abs(ev_none[1] - 1.0) < 1e-6       # ghost of the Perron eigenvalue
+
+    for _ in range(200):
+        x, y = rng.standard_normal(64) * 10 ** rng.uniform(-3, 3), rng.standard_normal(64) * 10 ** rng.uniform(-3, 3)
+        a, b, g = x @ x, y @ y, x @ y
+        alpha = 0.5 * (b - a)
+        r = np.hypot(alpha, g)
+        c = np.sqrt(0.5 * (1.0 + abs(alpha) / r))
+        s = (1.0 if alpha >= 0 else -1.0) * g / (2.0 * r * c)
+        t = s / c
+        xn, yn = c * x - s * y, s * x + c * y
+        assert abs(xn @ yn) <= 1e-12 * np.sqrt(a * b)
+        assert abs(c * c + s * s - 1.0) < 1e-15
+        np.testing.assert_allclose([xn @ xn, yn @ yn], [a - t * g, b + t * g], rtol=1e-9)
