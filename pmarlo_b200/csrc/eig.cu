@@ -6,9 +6,11 @@
 //  * K <= kEigJacobiMaxK: A is formed explicitly and handed to the batched
 //    one-sided Jacobi solver of tica.cu (one CTA per matrix) -- the ITS sweep
 //    path, one CTA per lag time;
-//  * larger K: Lanczos with full (two-pass classical Gram-Schmidt)
-//    re-orthogonalisation in ONE cooperative kernel: the mat-vec streams T once
-//    per step (8 K^2 bytes, HBM/L2-bound), the Ritz values of the m x m
+//  * larger K: Lanczos with periodic re-orthogonalisation (two consecutive full
+//    two-pass Gram-Schmidt steps out of eight, the three-term recurrence in
+//    between) in ONE cooperative kernel: the mat-vec streams T once per step
+//    (8 K^2 bytes, L2-resident for K = 1000), a step costs 3-5 grid barriers and
+//    is latency-bound; the Ritz values of the m x m
 //    tridiagonal matrix come from Sturm-sequence bisection (one thread per
 //    eigenvalue).  Convergence flag: the k leading Ritz values of T_m and of
 //    T_{m - m/8} agree to 1e-10.

@@ -1,10 +1,11 @@
 // tica_grid.cu -- K4 on several SMs: the same algorithm as tica_solve_kernel (tica.cu) as ONE
 // cooperative kernel.  A d = 256 Jacobi eigen-solve is latency-bound (about 3e9 fp64 operations, but
 // thousands of dependent rounds): the single-CTA kernel needs 171 ms, a grid-wide cyclic ordering
-// with one grid barrier per round 56 ms (measured on B200).  Here the rows are processed as BLOCK
-// pairs: a CTA orthogonalises the 2 x 16 rows of its block pair completely in shared memory before
-// the next grid barrier, so a sweep has 15 grid barriers instead of 255.  Data that other CTAs wrote
-// is always read with ld.global.cg (L2), never through L1.
+// with one grid barrier per round 56 ms, the kernel below 7.8 ms (measured on B200).  The rows are
+// processed in BLOCKS of 8: a CTA orthogonalises the rows of its block pair against each other
+// completely in shared memory / registers before the next grid barrier, so a sweep has d / 8 grid
+// barriers instead of d - 1 (see jacobi_grid).  Data that other CTAs wrote is always read with
+// ld.global.cg (L2), never through L1.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -13,7 +14,7 @@ namespace cg = cooperative_groups;
 
 namespace pmb {
 
-constexpr int kTgThreads = 512;   // 16 warps: one local row pair each
+constexpr int kTgThreads = 512;   // 16 warps: one local row pair each (b of them busy in a block round)
 constexpr int kTgMaxSweeps = 40;
 constexpr double kTgTol = 4.5e-16;  // x sqrt(n), as in tica.cu
 
