@@ -77,9 +77,10 @@ def bench_config(n_states=N_STATES, kmeans_iters=KMEANS_ITERS, gram_impl=0):
                           gram_impl=gram_impl, seed=4)
 
 
-def synth_xyz_device(n_traj, frames_per_traj, device, seed, rho=0.9995, sigma=0.03, chunk=2048):
-    """AR(1) internal motion (rho) around a random-coil 33-residue backbone, generated on the
-    device chunk by chunk: x_t = rho^t (x_0 + sum_{s<=t} rho^-s e_s) inside a chunk."""
+def synth_xyz_device(n_traj, frames_per_traj, device, seed, rho=0.9995, sigma=0.03, chunk=2048, base=None):
+    """AR(1) internal motion (rho) around a random-coil 33-residue backbone (or the mean structure
+    ``base`` (A,3) nm), generated on the device chunk by chunk: x_t = rho^t (x_0 + sum_{s<=t} rho^-s e_s)
+    inside a chunk."""
     import torch
 
     # the molecule (mean structure) is the same on every rank; only the dynamics are seeded per rank
@@ -87,10 +88,14 @@ def synth_xyz_device(n_traj, frames_per_traj, device, seed, rho=0.9995, sigma=0.
     g0.manual_seed(4)
     g = torch.Generator(device=device)
     g.manual_seed(int(seed))
-    A = 3 * N_RES
-    steps = torch.randn((A, 3), generator=g0, device=device, dtype=torch.float64)
-    steps /= steps.norm(dim=1, keepdim=True)
-    base = torch.cumsum(0.15 * steps, dim=0).to(torch.float32)
+    if base is None:
+        A = 3 * N_RES
+        steps = torch.randn((A, 3), generator=g0, device=device, dtype=torch.float64)
+        steps /= steps.norm(dim=1, keepdim=True)
+        base = torch.cumsum(0.15 * steps, dim=0).to(torch.float32)
+    else:
+        base = base.to(device=device, dtype=torch.float32)
+        A = int(base.shape[0])
     out = torch.empty((n_traj, frames_per_traj, A, 3), dtype=torch.float32, device=device)
     state = sigma * torch.randn((n_traj, 1, A, 3), generator=g, device=device, dtype=torch.float32)
     amp = sigma * (1 - rho * rho) ** 0.5

@@ -94,3 +94,58 @@ def run(trajs_xyz, phi_q, psi_q, pairs, *, tica_lag, tica_dim, n_states, kmeans_
     st["eig"] = time.perf_counter() - t0
     st["mle_iters"] = float(mle_iters)
     return CpuResult(ts, ev, st, int(sum(lengths)))
+
+
+@dataclass
+class ChainResult:
+    """Every intermediate of the chain, for the chained parity tests of the BASELINE configs."""
+    tica: object | None
+    Y: np.ndarray            # fp64 view of the fp32 projected coordinates the reference would cluster
+    centers: np.ndarray
+    labels: np.ndarray
+    kmeans_iters: int
+    counts: np.ndarray
+    T: np.ndarray
+    pi: np.ndarray
+    eigenvalues: np.ndarray
+    timescales: np.ndarray
+
+
+def run_chain(feats, *, preprocess="standard", tica_lag=10, tica_dim=2, n_states=100, init_rows=None,
+              kmeans_iters=20, kmeans_tolerance=None, msm_lag=10, n_timescales=5, alpha=1e-3,
+              mle_maxerr=1e-8, mle_maxiter=1_000_000) -> ChainResult:
+    """features (list of per-trajectory fp32 arrays) -> z-score -> TICA -> exact fp64 Lloyd from the centres
+    at frames ``init_rows`` -> sliding counts -> +alpha -> reversible MLE -> eigenvalues -> timescales
+    (src/pmarlo/api/conformations.py:192-200 with reduce_features / cluster_microstates(initial_centers=) /
+    build_msm_from_labels).  ``tica_dim <= 0`` clusters the features directly (config C2).
+    ``kmeans_tolerance=None`` runs exactly ``kmeans_iters`` Lloyd updates (the benchmark's fixed-iteration mode)."""
+    lengths = [int(f.shape[0]) for f in feats]
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    flat = np.concatenate([np.asarray(f, dtype=np.float64) for f in feats], axis=0)
+    model = None
+    if tica_dim > 0:
+        Z = flat if preprocess is None else tica.preprocess(flat, scale=(preprocess == "standard"))
+        prepped = [Z[off[i]:off[i + 1]] for i in range(len(lengths))]
+        model = tica.tica_fit(prepped, tica_lag)
+        Y = tica.tica_transform(model, Z, tica_dim).astype(np.float32).astype(np.float64)
+    else:
+        Y = flat.astype(np.float32).astype(np.float64)
+    c = Y[np.asarray(init_rows, dtype=np.int64)].copy()
+    if kmeans_tolerance is None:
+        for _ in range(kmeans_iters):
+            lab, _ = kmeans.assign(Y, c)
+            c, _ = kmeans._update(Y, lab, c)
+        n_it = kmeans_iters
+    else:
+        c, n_it, _, _ = kmeans.lloyd(Y, c, kmeans_iters, kmeans_tolerance)
+    labels, _ = kmeans.assign(Y, c)
+    dtrajs = [labels[off[i]:off[i + 1]] for i in range(len(lengths))]
+    C = counts.count_lagged(dtrajs, n_states, msm_lag)
+    Ca, active = msm.ensure_connected_counts(C.astype(float), alpha=alpha)
+    from . import cext
+
+    mle = cext.mle_rev if cext.available() else msm.mle_rev   # same algorithm, compiled (pinned to each other)
+    Ta, pia, _ = mle(Ca, maxerr=mle_maxerr, maxiter=mle_maxiter)
+    T, pi = msm.expand_results(n_states, active, Ta, pia)
+    ev = msm.eigenvalues_rev(Ta, pia, min(n_timescales + 1, Ta.shape[0]))
+    return ChainResult(model, Y, c, labels, n_it, C, T, pi, ev, msm.safe_timescales(msm_lag, ev[1:]))

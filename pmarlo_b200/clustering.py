@@ -58,10 +58,12 @@ class LloydResult:
 
 
 class _Accum:
-    """Per-iteration partials: [sums K*D | inertia 1] fp64 and counts K int64."""
+    """Per-iteration partials: [sums K*D | inertia 1 | counts K (fp64 copy)] fp64 and counts K int64.
+    The fp64 copy of the counts (exact below 2^53) lets one all-reduce carry everything
+    ("one fused allreduce per iteration")."""
 
     def __init__(self, K: int, D: int, device):
-        self.f = torch.zeros((K * D + 1,), dtype=torch.float64, device=device)
+        self.f = torch.zeros((K * D + 1 + K,), dtype=torch.float64, device=device)
         self.counts = torch.zeros((K,), dtype=torch.int64, device=device)
         self.K, self.D = K, D
 
@@ -71,7 +73,15 @@ class _Accum:
 
     @property
     def inertia(self):
-        return self.f[self.K * self.D:]
+        return self.f[self.K * self.D: self.K * self.D + 1]
+
+    def allreduce(self, comm: Comm) -> None:
+        if comm.size == 1:
+            return
+        cf = self.f[self.K * self.D + 1:]
+        cf.copy_(self.counts)
+        comm.allreduce_sum(self.f)
+        self.counts.copy_(cf)
 
     def zero_(self):
         self.f.zero_()
@@ -104,7 +114,7 @@ def lloyd_device(Y: torch.Tensor, initial_centers: torch.Tensor, max_iter: int =
             kernels.kmeans_assign(Y, centers, labels=labels, sums=acc.sums, counts=acc.counts,
                                   inertia=acc.inertia, hints=hints)
         hints = labels
-        comm.allreduce_sum(acc.f, acc.counts)
+        acc.allreduce(comm)
         if pending and tolerance is not None:
             cost = float(acc.inertia.item())   # cost of the centres produced by iteration `it`
             rel = abs(cost - prev_cost) / cost if cost != 0.0 else 0.0

@@ -546,8 +546,10 @@ __global__ void __launch_bounds__(256) kmeans_recheck_kernel(KmTcParams p) {
   const int D = p.D, K = p.K;
   for (int e = gw; e < count; e += nw) {
     const int64_t row = p.recheck_list[e];
+    // bk starts at 0 like the SIMT kernel and np.argmin: a NaN / Inf row (every comparison false) is
+    // labelled 0 instead of indexing the accumulators out of bounds
     double bd = 1.7976931348623157e308;
-    int bk = 0x7fffffff;
+    int bk = 0;
     for (int k = lane; k < K; k += 32) {
       double acc = 0.0;
       const double* c = p.centers + (size_t)k * D;

@@ -17,12 +17,14 @@ __all__ = ["Comm"]
 class Comm:
     """Thin view of the default process group (no-op when not initialised)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, solo: bool = False):
         import torch.distributed as dist
 
         self._dist = dist
         self.group = group
-        self.active = dist.is_available() and dist.is_initialized()
+        # solo: behave as a single rank even inside an initialised process group (the 1-rank reference run
+        # of bench.py's multi-rank parity check)
+        self.active = (not solo) and dist.is_available() and dist.is_initialized()
         self.size = dist.get_world_size(group) if self.active else 1
         self.rank = dist.get_rank(group) if self.active else 0
 

@@ -36,6 +36,19 @@ def _dev(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
+def _flat(t, dtype, name: str, numel: int | None = None, shape: tuple | None = None) -> torch.Tensor:
+    """A contiguous device tensor of the stated dtype (and size): the C ABI sees raw pointers, so a
+    strided view or a short output would read or write the wrong memory instead of failing."""
+    _dev(t, dtype, name)
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if numel is not None and int(t.numel()) != int(numel):
+        raise ValueError(f"{name} must have {numel} elements, got {t.numel()}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -212,6 +225,15 @@ def kmeans_assign(Y: torch.Tensor, centers: torch.Tensor, labels: torch.Tensor |
         raise ValueError("centers and Y disagree on the feature dimension")
     if labels is None:
         labels = torch.empty((n,), dtype=torch.int32, device=Y.device)
+    _flat(labels, torch.int32, "labels", numel=n)
+    if sums is not None:
+        _flat(sums, torch.float64, "sums", numel=K * D)
+    if counts is not None:
+        _flat(counts, torch.int64, "counts", numel=K)
+    if inertia is not None:
+        _flat(inertia, torch.float64, "inertia", numel=1)
+    if n_rechecked is not None:
+        _flat(n_rechecked, torch.int64, "n_rechecked", numel=1)
     if hints is not None:
         _dev(hints, torch.int32, "hints")
         if hints.numel() != n or not hints.is_contiguous():
@@ -258,10 +280,11 @@ def kmeans_update(centers: torch.Tensor, sums: torch.Tensor, counts: torch.Tenso
 def count_lagged(labels: torch.Tensor, seg_offsets: torch.Tensor, K: int, lag: int, step: int = 1,
                  out: torch.Tensor | None = None) -> torch.Tensor:
     """K7.  Accumulates into ``out`` (K,K) int64 (zero-initialised when None)."""
-    _dev(labels, torch.int32, "labels")
-    _dev(seg_offsets, torch.int64, "seg_offsets")
+    _flat(labels, torch.int32, "labels")
+    _flat(seg_offsets, torch.int64, "seg_offsets")
     if out is None:
         out = torch.zeros((K, K), dtype=torch.int64, device=labels.device)
+    _flat(out, torch.int64, "out", shape=(K, K))
     check(_lib.lib().pmb_count_lagged(ptr(labels), int(labels.numel()), ptr(seg_offsets),
                                       int(seg_offsets.numel()) - 1, int(K), int(lag), int(step),
                                       ptr(out), stream_handle(labels.device)), "pmb_count_lagged")
@@ -269,11 +292,12 @@ def count_lagged(labels: torch.Tensor, seg_offsets: torch.Tensor, K: int, lag: i
 
 
 def count_lagged_weighted(labels, weights, seg_offsets, K: int, lag: int, step: int = 1, out=None):
-    _dev(labels, torch.int32, "labels")
-    _dev(weights, torch.float64, "weights")
-    _dev(seg_offsets, torch.int64, "seg_offsets")
+    _flat(labels, torch.int32, "labels")
+    _flat(weights, torch.float64, "weights", numel=labels.numel())
+    _flat(seg_offsets, torch.int64, "seg_offsets")
     if out is None:
         out = torch.zeros((K, K), dtype=torch.float64, device=labels.device)
+    _flat(out, torch.float64, "out", shape=(K, K))
     check(_lib.lib().pmb_count_lagged_weighted(ptr(labels), ptr(weights), int(labels.numel()),
                                                ptr(seg_offsets), int(seg_offsets.numel()) - 1, int(K),
                                                int(lag), int(step), ptr(out),
@@ -284,9 +308,9 @@ def count_lagged_weighted(labels, weights, seg_offsets, K: int, lag: int, step: 
 def relabel_compact(labels: torch.Tensor, seg_offsets: torch.Tensor, lut: torch.Tensor):
     """``[lut[s] for s in traj if lut[s] >= 0]`` for every shard (ck_runner.py:150-153): returns the
     shortened label shard (int32, device) and its offsets (int64, device, length n_seg + 1)."""
-    _dev(labels, torch.int32, "labels")
-    _dev(seg_offsets, torch.int64, "seg_offsets")
-    _dev(lut, torch.int32, "lut")
+    _flat(labels, torch.int32, "labels")
+    _flat(seg_offsets, torch.int64, "seg_offsets")
+    _flat(lut, torch.int32, "lut")
     n, n_seg = int(labels.numel()), int(seg_offsets.numel()) - 1
     out = torch.empty((max(n, 1),), dtype=torch.int32, device=labels.device)
     new_off = torch.empty((n_seg + 1,), dtype=torch.int64, device=labels.device)

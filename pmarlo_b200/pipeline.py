@@ -83,12 +83,15 @@ def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | N
                  comm: Comm | None = None, features: torch.Tensor | None = None,
                  initial_centers: torch.Tensor | None = None, timer: StageTimer | None = None,
                  read_back: bool = True, buffers: dict | None = None,
-                 tica_model: TicaModel | None = None) -> PipelineResult:
+                 tica_model: TicaModel | None = None,
+                 initial_center_rows: np.ndarray | None = None) -> PipelineResult:
     """Run the whole path on this rank's shard.  Either ``xyz`` (+ ``plan``) or
     precomputed ``features`` (N,d) float32 must be given; with ``cfg.tica_dim <= 0``
     the features are clustered directly (config C2: 2-D Mueller-Brown data).
     ``buffers``: a dict that keeps the large per-frame tensors (features, Y, labels) alive between
-    calls so that repeated runs on same-sized shards do not go through the allocator."""
+    calls so that repeated runs on same-sized shards do not go through the allocator.
+    ``initial_center_rows``: frame indices into RANK 0's shard whose projected coordinates seed Lloyd
+    (``initial_centers=`` given as frames, so that runs with different rank counts can share them)."""
     comm = comm if comm is not None else Comm()
     timer = timer if timer is not None else NULL_TIMER
     dev = (xyz if xyz is not None else features).device
@@ -121,6 +124,12 @@ def run_pipeline(xyz: torch.Tensor | None, segs: Segments, plan: FeaturePlan | N
         Y = X
 
     with timer.stage("kmeans"):
+        if initial_centers is None and initial_center_rows is not None:
+            initial_centers = torch.empty((cfg.n_states, int(Y.shape[1])), dtype=torch.float64, device=dev)
+            if comm.rank == 0:
+                idx = torch.from_numpy(np.asarray(initial_center_rows, dtype=np.int64)).to(dev)
+                initial_centers.copy_(Y.index_select(0, idx).to(torch.float64))
+            comm.broadcast(initial_centers, src=0)
         if initial_centers is None:
             initial_centers = seeded_initial_centers(Y, cfg.n_states, cfg.seed, comm)
         labels = _buf("labels", (int(Y.shape[0]),), torch.int32)
