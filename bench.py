@@ -41,10 +41,11 @@ N_DIST = 128
 FRAMES_PER_TRAJ = 125_000
 TICA_LAG, TICA_DIM, N_STATES, KMEANS_ITERS, MSM_LAG, N_TIMESCALES = 20, 10, 1000, 20, 20, 5
 METRIC = "frames/sec end-to-end MSM pipeline"
-# CPU arm: the reversible-MLE fixed point costs ~3 ms per iteration on the host (K^2 = 10^6 cells) whatever the
-# number of frames, and a small sample's sparse count matrix needs > 50 000 iterations.  The full C4 count
-# matrix (10 M frames) converges in ~10^3 iterations (bench.py prints mle_iters), so the CPU sample is capped there.
-CPU_MLE_ITER_CAP = 1000
+# CPU arm: the reversible-MLE fixed point costs K^2 = 10^6 cells per iteration on the host whatever the number
+# of frames, and a small sample's sparse count matrix needs > 50 000 iterations.  The full C4 count matrix
+# (10 M frames) converges in ~1.3 x 10^3 iterations (bench.py prints mle_iters), so the CPU sample is capped there.
+CPU_MLE_ITER_CAP = 1324
+CPU_SAMPLE_FRAMES = 250_000     # ~10 s of host work per step: K^2-sized stages stay below 15 % of the CPU step
 UNIT = "frames/s"
 
 
@@ -189,7 +190,7 @@ def run_cpu_pipeline(trajs, n_states=N_STATES, kmeans_iters=KMEANS_ITERS):
     pairs = ofeat.ca_pairs_all(ofeat.ca_indices(top.names))[:N_DIST]
     return opipe.run(trajs, phi, psi, pairs, tica_lag=TICA_LAG, tica_dim=TICA_DIM, n_states=n_states,
                      kmeans_iters=kmeans_iters, msm_lag=MSM_LAG, n_timescales=N_TIMESCALES, seed=4,
-                     mle_maxiter=CPU_MLE_ITER_CAP)
+                     mle_maxiter=CPU_MLE_ITER_CAP, threads=cpu_threads())
 
 
 def cpu_threads() -> int:
@@ -210,6 +211,19 @@ def time_cpu(sample_traj, sample_frames, repeats=1):
     return res.n_frames / best, best, res
 
 
+CPU_IMPL_NOTE = ("numpy/scipy BLAS + scikit-learn Lloyd + plain-C (pthread) reversible MLE port of the algorithm; "
+                 "NOT deeptime's C++/OpenMP nor mdtraj's C (absent from the image)")
+
+
+def cpu_cost_split(stage_seconds, n_frames):
+    """Per-frame and fixed (K^2-sized, frame-independent) parts of the CPU step, so that the extrapolation
+    to the GPU arm's frame count is explicit: t(n) ~ fixed_s + n * per_frame_us."""
+    fixed = sum(float(stage_seconds.get(k, 0.0)) for k in ("mle", "eig"))
+    per_frame = sum(float(stage_seconds.get(k, 0.0)) for k in ("featurize", "tica_fit", "project", "kmeans", "count"))
+    return {"per_frame_us": 1e6 * per_frame / max(1, n_frames), "fixed_s": fixed,
+            "asymptotic_frames_per_s": max(1, n_frames) / per_frame if per_frame > 0 else None}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -226,15 +240,18 @@ def reference_arm(args):
     value = res.n_frames / dt
     sample = (f"{n_traj} trajectories x {n_frames} frames of the C4 workload per step (same shapes, K={N_STATES}, "
               f"{KMEANS_ITERS} Lloyd iterations, reversible MLE capped at {CPU_MLE_ITER_CAP} iterations = what the full "
-              f"10 M-frame count matrix needs), numpy/scipy BLAS + sklearn Lloyd on {cores} threads")
+              f"10 M-frame count matrix needs) on {cores} threads; {CPU_IMPL_NOTE}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, n_traj * n_frames, cpu=True),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         **cpu_cost_split(res.stage_seconds, res.n_frames)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "stages_s": res.stage_seconds,
+        "fixed_share_of_step": (float(res.stage_seconds.get("mle", 0.0)) + float(res.stage_seconds.get("eig", 0.0))) / dt,
+        "parity": PARITY_NOTE,
     }
     print(json.dumps(line))
     return 0
@@ -250,6 +267,147 @@ def workload_config(args, frames_per_gpu, cpu=False):
         "msm_lag": MSM_LAG, "parallelism": f"frame shards x{args.gpus}, allreduce of partial sums",
         "l2_policy": "inputs (1188 B of coordinates per frame, >= 1.4 GB per step) larger than the 126 MB L2",
     }
+
+
+# ----------------------------------------------------------------------------- extra measurements
+def h2d_ceiling(host, dst, comm, device, repeats=3):
+    """Pinned host -> device copy rate with every rank copying AT THE SAME TIME and no kernels running:
+    the platform ceiling the e2e number (11.9 GB of coordinates per step and GPU) is bounded by."""
+    import torch
+
+    n = min(int(host.shape[0]), int(dst.shape[0]))
+    nbytes = n * int(host[0].numel()) * 4
+    best = None
+    for _ in range(repeats + 1):
+        torch.cuda.synchronize(device)
+        comm.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dst[:n].copy_(host[:n], non_blocking=True)
+        b.record()
+        torch.cuda.synchronize(device)
+        ms = a.elapsed_time(b)
+        best = ms if best is None else min(best, ms)
+    t = torch.tensor([best], dtype=torch.float64, device=device)
+    comm.allreduce_max(t)                      # slowest rank: all ranks copy concurrently
+    gbs = nbytes / (float(t.item()) * 1e-3) / 1e9
+    return {"per_gpu_gbs": gbs, "aggregate_gbs": gbs * comm.size, "bytes": nbytes, "concurrent_ranks": comm.size}
+
+
+def strong_scaling_record(args, comm, device, rank, world, cfg):
+    """The north-star configuration itself: C4's 10 M frames IN TOTAL dealt over the ranks (80 trajectories,
+    80 / N per GPU), device resident, same pipeline.  Reported next to the weak-scaling `value`."""
+    import torch
+
+    from pmarlo_b200.pipeline import StageTimer, run_pipeline
+
+    total_traj = 80
+    per = total_traj // world
+    wl = make_workload(per, FRAMES_PER_TRAJ, device, seed=4000 + rank)
+    bufs: dict = {}
+    res = None
+    for _ in range(max(3, min(args.warmup, 5))):
+        res = run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, read_back=True, buffers=bufs)
+    torch.cuda.synchronize(device)
+    comm.barrier()
+    torch.cuda.synchronize(device)
+    steps = max(3, min(args.steps, 10))
+    timer = StageTimer(True)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        res = run_pipeline(wl.xyz, wl.segs, wl.plan, cfg, comm, timer=timer, read_back=True, buffers=bufs)
+    b.record()
+    torch.cuda.synchronize(device)
+    comm.barrier()
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+    comm.allreduce_max(ms)
+    ms_step = float(ms.item()) / steps
+    frames_total = per * world * FRAMES_PER_TRAJ
+    return {"frames_total": frames_total, "frames_per_gpu": per * FRAMES_PER_TRAJ, "steps": steps,
+            "ms_per_step": ms_step, "value": frames_total / (ms_step * 1e-3), "unit": UNIT,
+            "stages_ms": {k: v / steps for k, v in timer.totals_ms().items() if k in TOP_LEVEL_STAGES},
+            "mle_iters": int(res.mle_info[0].item())}
+
+
+def multi_rank_parity(comm, device, rank, world, plan):
+    """N-rank results against a 1-rank run of the same pipeline over the concatenated shards (rank 0 runs
+    it with a solo communicator).  Counts given identical labels must be bit-exact for any N (integer
+    sums); along the whole chain the fp64 partial sums are added in a different order, so covariances agree
+    to ~1e-15 and a frame sitting on a Voronoi boundary may change its label."""
+    import torch
+    import torch.distributed as dist
+
+    from pmarlo_b200 import kernels
+    from pmarlo_b200.distributed import Comm
+    from pmarlo_b200.pipeline import PipelineConfig, run_pipeline
+    from pmarlo_b200.shards import Segments
+
+    n_traj, fpt, K = 2, 20_000, 200
+    xyz = synth_xyz_device(n_traj, fpt, device, seed=9000 + rank, rho=0.995)
+    segs = Segments.from_lengths([fpt] * n_traj)
+    cfg = PipelineConfig(tica_lag=TICA_LAG, tica_dim=TICA_DIM, preprocess="standard", n_states=K, kmeans_max_iter=5,
+                         kmeans_tolerance=None, msm_lag=MSM_LAG, n_timescales=N_TIMESCALES, seed=4)
+    rows = np.sort(np.random.default_rng(12).choice(n_traj * fpt, size=K, replace=False))
+    res = run_pipeline(xyz, segs, plan, cfg, comm, initial_center_rows=rows)
+    all_xyz = [torch.empty_like(xyz) for _ in range(world)]
+    all_lab = [torch.empty_like(res.labels) for _ in range(world)]
+    dist.all_gather(all_xyz, xyz.contiguous())
+    dist.all_gather(all_lab, res.labels.contiguous())
+    rec = None
+    if rank == 0:
+        solo = Comm(solo=True)
+        X1 = torch.cat(all_xyz, dim=0)
+        segs1 = Segments.from_lengths([fpt] * (n_traj * world))
+        one = run_pipeline(X1, segs1, plan, cfg, solo, initial_center_rows=rows)
+        labN = torch.cat(all_lab, dim=0)
+        C_given = kernels.count_lagged(labN, segs1.device(device), K, cfg.msm_lag)
+
+        def rel(a, b):
+            a, b = a.double(), b.double()
+            return float((a - b).abs().max().item() / max(float(b.abs().max().item()), 1e-300))
+
+        rec = {
+            "ranks": world, "frames": int(X1.shape[0]), "n_states": K,
+            "counts_equal_given_labels": bool(torch.equal(C_given, res.counts)),
+            "labels_mismatch": int((labN != one.labels).sum().item()),
+            "counts_equal": bool(torch.equal(one.counts, res.counts)),
+            "C00_rel": rel(res.tica.C00, one.tica.C00), "C0t_rel": rel(res.tica.C0t, one.tica.C0t),
+            "T_rel": rel(res.T, one.T), "pi_rel": rel(res.pi, one.pi),
+            "eig_rel": rel(res.eigenvalues, one.eigenvalues),
+        }
+    comm.barrier()
+    return rec
+
+
+def end_to_end_roofline(stages, frames, cfg, peaks, world):
+    """T_min = sum over stages of max(bytes / HBM peak, flops / tensor-or-fp32 peak)
+    for this rank's frames (dense-equivalent algorithmic work, no 3xTF32 split factor) + all-reduce volume /
+    NVLink rate; `frac` = T_min / measured step."""
+    hbm = float(peaks.get("hbm_gbs", 6650.0)) * 1e9
+    tf32 = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0 * 1e12
+    d, m, K = 256, cfg.tica_dim, cfg.n_states
+    per_frame = {
+        "featurize": (12 * 3 * N_RES + 4 * d, 0.0),
+        "col_moments": (4 * d, 0.0),
+        "gram": (2 * 4 * d, 2 * 2 * d * d),                                   # two launches
+        "project": (4 * d + 4 * m, 2 * d * m),
+        "kmeans": ((4 * m + 4) * (cfg.kmeans_max_iter + 1), 2 * m * K * (cfg.kmeans_max_iter + 1)),
+        "count": (4, 0.0),
+    }
+    t_min = 0.0
+    parts = {}
+    for name, (b, f) in per_frame.items():
+        t = max(b * frames / hbm, f * frames / tf32)
+        parts[name] = t * 1e3
+        t_min += t
+    nv = 770e9
+    allreduce_bytes = (2 * d * d * 8 + 6 * d * 8 + (K * m + K + 1) * 8 * (cfg.kmeans_max_iter + 1) + K * K * 8) if world > 1 else 0
+    t_min += 2.0 * allreduce_bytes / nv
+    measured = sum(v for k, v in stages.items() if k in TOP_LEVEL_STAGES)
+    return {"t_min_ms": t_min * 1e3, "measured_ms": measured, "frac": (t_min * 1e3) / measured if measured else None,
+            "parts_ms": parts, "note": "dense-equivalent algorithmic work per SURVEY 8(d); the latency-bound d x d and "
+                                       "K x K solves (K4, K8, K9) have no roofline term and count fully against the fraction"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -338,6 +496,20 @@ def gpu_arm(args):
     e2e_value = frames * world / (e2e_ms * 1e-3)
     h2d = int(host.numel() * 4)
     d2h = int(out["d2h_bytes"])
+    ceiling = h2d_ceiling(host, bufs["xyz"], comm, device)
+    del host
+    bufs.clear()
+    torch.cuda.empty_cache()
+
+    strong = verify = None
+    if world == 1 and frames == 10_000_000:
+        strong = {"frames_total": frames, "frames_per_gpu": frames, "steps": args.steps, "ms_per_step": ms_per_step,
+                  "value": value, "unit": UNIT, "stages_ms": {k: v for k, v in stages.items() if k in TOP_LEVEL_STAGES},
+                  "mle_iters": int(res.mle_info[0].item())}
+    if world > 1 and not args.no_extras:
+        strong = strong_scaling_record(args, comm, device, rank, world, cfg)
+        torch.cuda.empty_cache()
+        verify = multi_rank_parity(comm, device, rank, world, wl.plan)
 
     if rank != 0:
         if world > 1:
@@ -356,9 +528,9 @@ def gpu_arm(args):
         cpu = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
                "sample": f"2 trajectories x {args.cpu_sample_frames // 2} frames of the same workload "
                          f"(K={N_STATES}, {KMEANS_ITERS} Lloyd iterations, reversible MLE capped at {CPU_MLE_ITER_CAP} "
-                         f"iterations), {secs:.1f} s of oracle work on {cpu_threads()} threads; the K^2-sized "
-                         "MLE/eigen stages do not shrink with the sample",
-               "stages_s": {k: round(v2, 3) for k, v2 in cres.stage_seconds.items()}}
+                         f"iterations), {secs:.1f} s of oracle work on {cpu_threads()} threads; {CPU_IMPL_NOTE}",
+               "stages_s": {k: round(v2, 3) for k, v2 in cres.stage_seconds.items()},
+               **cpu_cost_split(cres.stage_seconds, cres.n_frames)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -366,7 +538,11 @@ def gpu_arm(args):
         "vs_baseline": None, "dtype": "f32 features / 3xTF32-or-fp32 Gram with fp64 flush / f64 MSM",
         "data": "synthetic", "config": workload_config(args, frames),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms},
+                "ms_per_step": e2e_ms, "h2d_ceiling_gbs": ceiling,
+                "h2d_bound_ms": h2d / (ceiling["per_gpu_gbs"] * 1e9) * 1e3,
+                "returns": "labels, T, pi, eigenvalues, timescales, MLE info (numpy)"},
+        "e2e_roofline": end_to_end_roofline(stages, frames, cfg, peaks, world),
+        "strong": strong, "multi_rank_parity": verify, "parity": PARITY_NOTE,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "stages_ms": stages, "kmeans_iters_run": int(res.kmeans_iters),
         "tica_rank_sweeps": [int(v) for v in res.tica.rank_dev.tolist()],
@@ -469,6 +645,10 @@ def roofline(stages, counts, frames, cfg, peaks, args):
 
 TOP_LEVEL_STAGES = ("featurize", "tica_fit", "project", "kmeans", "count", "mle", "eig")
 
+PARITY_NOTE = ("partial: integer stages (labels given centres, counts) bit-exact against reference-generated goldens; "
+               "floating stages (dihedrals, TICA, reversible MLE, eigenvalues) within 1e-6 of the oracle restatement, "
+               "which is unpinned against deeptime/mdtraj binaries (absent from the image)")
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -480,8 +660,10 @@ def main():
                     help="frames of this rank's shard (default: the whole of C4, 10 M frames = 80 trajectories "
                          "x 125 000, on every GPU; weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample-frames", type=int, default=40_000)
+    ap.add_argument("--cpu-sample-frames", type=int, default=CPU_SAMPLE_FRAMES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the strong-scaling record and the multi-rank parity check (N > 1)")
     ap.add_argument("--gram-impl", type=int, default=0)
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")

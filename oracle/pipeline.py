@@ -42,7 +42,8 @@ def block_features(xyz: np.ndarray, phi_q: np.ndarray, psi_q: np.ndarray, pairs:
 
 
 def run(trajs_xyz, phi_q, psi_q, pairs, *, tica_lag, tica_dim, n_states, kmeans_iters, msm_lag,
-        n_timescales, seed=0, mle_maxerr=1e-8, mle_maxiter=1_000_000, exact=False, chunk=20000) -> CpuResult:
+        n_timescales, seed=0, mle_maxerr=1e-8, mle_maxiter=1_000_000, exact=False, chunk=20000,
+        threads=1) -> CpuResult:
     st = {}
     t0 = time.perf_counter()
     feats = []
@@ -86,7 +87,12 @@ def run(trajs_xyz, phi_q, psi_q, pairs, *, tica_lag, tica_dim, n_states, kmeans_
     st["count"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     Ca, active = msm.ensure_connected_counts(C)
-    T, pi, mle_iters = msm.mle_rev(Ca, maxerr=mle_maxerr, maxiter=mle_maxiter)
+    from . import cext
+
+    if cext.available():   # same fixed point, compiled and row-parallel (pinned to msm.mle_rev in tests/test_oracle_c.py)
+        T, pi, mle_iters = cext.mle_rev(Ca, maxerr=mle_maxerr, maxiter=mle_maxiter, threads=threads)
+    else:
+        T, pi, mle_iters = msm.mle_rev(Ca, maxerr=mle_maxerr, maxiter=mle_maxiter)
     st["mle"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     ev = msm.eigenvalues_rev(T, pi, min(n_timescales + 1, T.shape[0]))

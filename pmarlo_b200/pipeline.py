@@ -221,9 +221,24 @@ def estimate_msm_from_host(xyz_host, lengths, plan: FeaturePlan, cfg: PipelineCo
             acc.add(X[a:b], Segments(offs[lo:hi + 1] - a))
     model = acc.finish() if acc is not None else None
     res = run_pipeline(None, segs, plan, cfg, comm, features=X, read_back=False, buffers=buffers, tica_model=model)
-    ev = res.eigenvalues.cpu().numpy()
-    pi = res.pi.cpu().numpy()
-    info = res.mle_info.cpu().numpy()
+    # what the reference's API hands back: labels (cluster_microstates), T and pi (build_msm_from_labels),
+    # eigenvalues / timescales; read into pinned host buffers kept between calls
+    def _pinned(name, t):
+        h = bufs.get(name)
+        if h is None or tuple(h.shape) != tuple(t.shape) or h.dtype != t.dtype:
+            h = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+            bufs[name] = h
+        h.copy_(t, non_blocking=True)
+        return h
+
+    h_lab = _pinned("h_labels", res.labels)
+    h_T = _pinned("h_T", res.T)
+    h_pi = _pinned("h_pi", res.pi)
+    h_ev = _pinned("h_ev", res.eigenvalues)
+    h_info = _pinned("h_info", res.mle_info)
+    torch.cuda.current_stream(device).synchronize()
+    ev = h_ev.numpy()
     ts = safe_timescales(cfg.msm_lag, ev[1:])
-    return {"timescales": ts, "eigenvalues": ev, "stationary_distribution": pi, "mle_info": info,
-            "d2h_bytes": int(ev.nbytes + pi.nbytes + info.nbytes)}
+    return {"timescales": ts, "eigenvalues": ev, "stationary_distribution": h_pi.numpy(), "mle_info": h_info.numpy(),
+            "labels": h_lab.numpy(), "transition_matrix": h_T.numpy(),
+            "d2h_bytes": int(sum(h.numel() * h.element_size() for h in (h_lab, h_T, h_pi, h_ev, h_info)))}

@@ -3,8 +3,13 @@
 from __future__ import annotations
 
 import contextlib
+import os
 
 import torch
+
+# NVTX ranges per stage (tracing): on when PMB_NVTX=1, so that an nsys / ncu --nvtx
+# timeline shows the stage names; off by default (a push/pop pair per stage costs ~1 us of host time).
+_NVTX = os.environ.get("PMB_NVTX", "0") not in ("", "0")
 
 __all__ = ["StageTimer", "NULL_TIMER"]
 
@@ -19,8 +24,14 @@ class StageTimer:
 
     @contextlib.contextmanager
     def stage(self, name: str):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(f"pmb200:{name}")
         if not self.enabled:
-            yield
+            try:
+                yield
+            finally:
+                if _NVTX:
+                    torch.cuda.nvtx.range_pop()
             return
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -29,6 +40,8 @@ class StageTimer:
         finally:
             b.record()
             self.records.append((name, a, b))
+            if _NVTX:
+                torch.cuda.nvtx.range_pop()
 
     def totals_ms(self) -> dict[str, float]:
         out: dict[str, float] = {}
