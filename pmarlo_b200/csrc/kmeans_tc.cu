@@ -1,28 +1,40 @@
-// kmeans_tc.cu -- K6 (tensor-core path): nearest-centre assignment as a tcgen05 TF32 GEMM with the
-// argmin fused into the TMEM epilogue, labels bit-exact against the fp64 oracle.
+// kmeans_tc.cu -- K6 (tensor-core path): nearest-centre assignment as a tcgen05 score GEMM with the argmin
+// fused into the TMEM epilogue, labels bit-exact against the fp64 oracle.
 //
-//   score(t,k) - |y_t|^2 = |c_k|^2 - 2 y_t.c_k            (one 128 x 256 x KS MMA tile per chunk)
+//   score(t,k) - |y_t|^2 = |c_k|^2 - 2 y_t.c_k          (one 128 x 128 x KS MMA tile per 128-centre chunk)
 //
-// The product is made fp32-accurate on TF32 tensor cores by splitting along the MMA K dimension
-// ("3xTF32 in K"): every coordinate d contributes three K slots
-//      A (frame side):  y_hi  y_lo  y_hi        B (centre side):  c'_hi  c'_hi  c'_lo     (c' = -2 c)
-// and |c|^2 rides in two more slots (two TF32 pieces against 1.0), so the accumulator that leaves TMEM
-// is the squared distance minus |y|^2, which does not change the argmin.  Slot order: 0-1 |c|^2 pieces
-// (A side 1.0), then 2 + 3 d + {0,1,2}; KS = 3 D + 2 rounded up to 8 (D = 10: 32 slots, four MMAs).
+// Operands are FP16 (kind::f16, K = 16 per instruction: twice the K rate of kind::tf32 for the same 11-bit
+// significands), made fp32-accurate by splitting along the MMA K dimension.  Everything is pre-scaled by a
+// power of two s (centre coordinates land in [2^9, 2^10)), so that hi/lo pieces stay in fp16's normal range;
+// scores scale by s^2, which no comparison below notices.  Every coordinate d contributes three K slots
+//      A (frame side):  y_hi  y_lo  y_hi        B (centre side):  c'_hi  c'_hi  c'_lo     (c' = -2 c s)
+// and |c|^2 s^2 rides in two more slots (two fp16 pieces of |c|^2 s^2 / 2^13 against the constant 2^13), so the
+// accumulator that leaves TMEM is the squared distance minus |y|^2, which does not change the argmin.
+// Slot order: 0-1 |c|^2 pieces, then 2 + 3 d + {0,1,2}; KS = 3 D + 2 rounded up to 16 (D = 10: 32 slots =
+// two MMAs per chunk).  Products of two fp16 values are exact in the fp32 accumulator, like TF32 x TF32.
 //
-// Pipeline (one persistent CTA per SM, 25 warps, warp-specialised, mbarrier hand-offs):
-//   warps 17-20  producers : build the A tile (128 frames x KS slots, K-major core-matrix layout) and
-//                            the per-row screening threshold from the hinted centre (rows prefetched)
-//   warps 21-24  finalisers: merge the column groups, certainty test, labels, fused Lloyd accumulation
-//   warp  16     MMA issuer: per 256-centre chunk KS/8 tcgen05.mma into one of two TMEM buffers
-//   warps 0-15   epilogue  : tcgen05.ld 64 columns per warp and chunk, running (best, second) as
-//                            packed integer keys (score bits with the column in the low 5 bits)
-// The centre operand B (Kpad x KS) is staged once per CTA and stays resident in shared memory.
+// The centre operand is laid out once per call by kmeans_tc_prep_kernel in global memory, chunk by chunk in
+// the shared-memory image the MMA reads; CTAs bulk-copy (cp.async.bulk) chunks into a ring of shared-memory
+// slots.  When all chunks fit (C4: 8 x 8 KB) they are loaded once and stay resident; otherwise (C5: D = 64,
+// K = 5000, 40 x 52 KB) they stream through the ring once per frame tile, fed from L2.
+//
+// Pipeline (one persistent CTA per SM, 26 warps, warp-specialised, mbarrier hand-offs):
+//   warps 0-15   epilogue  : four groups of four warps (one per TMEM lane quarter).  Group g owns TMEM ring
+//                            slot g: tcgen05.ld 4 x 32 columns, 3-input-min tree, screening against the
+//                            row's threshold, running (best, second) as packed integer keys
+//   warp  16     MMA issuer: per chunk KS/16 tcgen05.mma (M 128, N 128) into the next of FOUR TMEM buffers
+//   warp  17     loader    : bulk copies of centre chunks into the shared-memory ring
+//   warps 18-21  producers : build the A tile (128 frames x KS slots, K-major core-matrix layout) and the
+//                            per-row screening threshold from the hinted centre (rows prefetched)
+//   warps 22-25  finalisers: merge the groups, certainty test, labels, fused Lloyd accumulation
 //
 // Exactness: a frame whose best and second-best scores are closer than a bound on the arithmetic
 // error (operand rounding, dropped lo.lo terms, tensor-core accumulation, key truncation) is NOT
 // labelled here: it goes to a list, and kmeans_recheck_kernel re-evaluates it against all centres
 // in fp64 with the oracle's operation order (oracle/kmeans.py::sqdist_direct), one warp per frame.
+// So do frames whose scaled coordinates leave fp16's range (|y_d| > 64 max|c|) and non-finite frames.
+#include <cuda_fp16.h>
+
 #include "tc05.cuh"
 
 namespace pmb {
@@ -43,16 +55,23 @@ __device__ long long g_km_dbg[16];
 #endif
 
 constexpr int kTcTile = 128;     // frames per tile  (MMA M)
-constexpr int kTcChunk = 256;    // centres per MMA  (MMA N)
+constexpr int kTcChunk = 128;    // centres per MMA  (MMA N) = columns of one TMEM buffer
+constexpr int kTcRing = 4;       // TMEM buffers (4 x 128 columns = all 512)
+constexpr int kTcKpadTo = 256;   // K is padded to a multiple of this (contract of pmb_kmeans_tc_scores)
 constexpr int kTcEpiWarps = 16;
 constexpr int kTcProdWarps = 4;
 constexpr int kTcFinWarps = 4;
 constexpr int kTcMmaWarp = kTcEpiWarps;
-constexpr int kTcThreads = (kTcEpiWarps + 1 + kTcProdWarps + kTcFinWarps) * 32;   // 800
+constexpr int kTcLoadWarp = kTcEpiWarps + 1;
+constexpr int kTcProdWarp0 = kTcEpiWarps + 2;
+constexpr int kTcFinWarp0 = kTcProdWarp0 + kTcProdWarps;
+constexpr int kTcThreads = (kTcEpiWarps + 2 + kTcProdWarps + kTcFinWarps) * 32;   // 832
 constexpr int kTcDReg = 16;      // coordinates of a frame held in registers (larger D: re-read from L1/L2)
-constexpr int kTcColsPerWarp = kTcChunk / (kTcEpiWarps / 4);        // 64
+constexpr int kTcMaxSlots = 16;  // upper bound of the shared-memory ring of centre chunks
 constexpr float kTcErrScale = 1.9073486e-6f;   // 2^-19: envelope of the score error in units of (|y| + |c|max)^2
 constexpr float kTcKeyTrunc = 1.0f + 7.6293945e-6f;  // 1 + 2^-17 (5 key bits of a 23-bit mantissa dropped)
+constexpr float kTcNormUnit = 8192.0f;         // 2^13: the A-side constant the |c|^2 pieces are multiplied with
+constexpr float kTcHalfMax = 6.0e4f;           // |scaled coordinate| above this does not fit fp16
 
 struct KmTcParams {
   const float* Y;
@@ -61,8 +80,9 @@ struct KmTcParams {
   int64_t ld;
   const double* centers;
   int K;
-  int Kpad;   // K rounded up to a multiple of 256 (dummy centres score 2^126)
-  int KS;     // K slots per row, multiple of 8
+  int Kpad;   // K rounded up to a multiple of 256; padding rows copy centre K-1 with a large penalty
+  int KS;     // K slots per row, multiple of 16
+  int nslots; // shared-memory ring slots for centre chunks; resident when nslots == Kpad / 128
   int32_t* labels;
   const int32_t* hints;   // previous labels (may alias labels) or nullptr: only used to skip work
   double* sums;
@@ -76,26 +96,115 @@ struct KmTcParams {
   unsigned long long* lcounts;   // K
   int accumulate;       // sums / counts / inertia requested
   float* dbg_scores;    // n x Kpad (tests only) or nullptr
+  // written by kmeans_tc_prep_kernel
+  unsigned char* Bg;    // Kpad / 128 chunks of 128 x KS fp16 in the K-major core-matrix image
+  float* cs32;          // K x D: (float)c * s
+  float* meta;          // [0] s, [1] max |c| s * 1.0001, [2] 1 / s^2
 };
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// byte offset of (row, slot) in a K-major fp16 operand tile: 8-row x 16-byte core matrices (8 slots wide),
+// adjacent in K 128 B apart, adjacent in M/N `sbo` apart
+__device__ __forceinline__ uint32_t off_kmajor_h(int row, int slot, uint32_t sbo) {
+  return (uint32_t)(row >> 3) * sbo + (uint32_t)(slot >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(slot & 7) * 2u;
+}
+
+// Instruction descriptor for kind::f16 with F16 operands and F32 accumulation (same fields as idesc_tf32 with
+// A/B format 0 = F16).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Centre operand: scale, split, |c|^2 pieces, laid out chunk by chunk in the shared-memory image.
+__global__ void __launch_bounds__(1024) kmeans_tc_prep_kernel(KmTcParams p) {
+  __shared__ float s_red[32];
+  __shared__ float s_scale;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = p.D, K = p.K, KS = p.KS;
+  float amax = 0.f;
+  for (int i = tid; i < K * D; i += blockDim.x) amax = fmaxf(amax, fabsf((float)p.centers[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0) s_red[warp] = amax;
+  __syncthreads();
+  if (tid == 0) {
+    float m = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_red[w]);
+    int e = 0;
+    if (m > 0.f && m < 3.0e38f) e = 9 - ilogbf(m);     // m * 2^e in [2^9, 2^10)
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    s_scale = ldexpf(1.0f, e);
+  }
+  __syncthreads();
+  const float sc = s_scale;
+  const uint32_t sbo = (uint32_t)(KS / 8) * 128u;
+  const size_t chunk_bytes = (size_t)kTcChunk * KS * 2;
+  float cmax2 = 0.f;
+  for (int k = tid; k < p.Kpad; k += blockDim.x) {
+    unsigned char* base = p.Bg + (size_t)(k / kTcChunk) * chunk_bytes;
+    const int r = k % kTcChunk;
+    auto put = [&](int slot, float v) {
+      *reinterpret_cast<__half*>(base + off_kmajor_h(r, slot, sbo)) = __float2half_rn(v);
+    };
+    const int src = k < K ? k : K - 1;
+    double n2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const float c32 = (float)p.centers[(size_t)src * D + d];
+      n2 = fma((double)c32, (double)c32, n2);
+      const float cs = c32 * sc;
+      if (k < K) p.cs32[(size_t)k * D + d] = cs;
+      const float cm = -2.0f * cs;
+      const float hi = __half2float(__float2half_rn(cm));
+      put(2 + 3 * d + 0, hi);
+      put(2 + 3 * d + 1, hi);
+      put(2 + 3 * d + 2, cm - hi);
+    }
+    for (int sl = 3 * D + 2; sl < KS; ++sl) put(sl, 0.f);
+    const double n2s = n2 * (double)sc * (double)sc;
+    const double q = n2s / (double)kTcNormUnit;
+    const float p1 = __half2float(__float2half_rn((float)q));
+    put(0, p1);
+    // padding rows: centre K-1 again with a penalty of 2^13 * 30000 in score units, so they never win
+    put(1, k < K ? (float)(q - (double)p1) : 30000.0f);
+    if (k < K) cmax2 = fmaxf(cmax2, (float)n2s * 1.0001f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cmax2 = fmaxf(cmax2, __shfl_xor_sync(0xffffffffu, cmax2, o));
+  __syncthreads();
+  if (lane == 0) s_red[warp] = cmax2;
+  __syncthreads();
+  if (tid == 0) {
+    float m = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_red[w]);
+    p.meta[0] = sc;
+    p.meta[1] = sqrtf(m) * 1.0001f;
+    p.meta[2] = 1.0f / (sc * sc);
+  }
 }
 
 struct TcSmem {
-  uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], r_full[2], r_empty[2], thr_ready[4];
+  uint64_t a_full[2], a_empty[2], t_full[kTcRing], t_empty[kTcRing], r_full[2], r_empty[2], thr_ready[4];
+  uint64_t b_full[kTcMaxSlots], b_empty[kTcMaxSlots];
   uint32_t tmem_slot;
-  float cmax;
-  float red[32];
   float thr[4][kTcTile];   // per-row screening threshold of tile it (slot it & 3), minus |y|^2
-  float xn2[4][kTcTile];   // |y|^2 of the row
+  float xn2[4][kTcTile];   // |y|^2 of the row (scaled)
   int res_best[2][4][kTcTile];
   int res_second[2][4][kTcTile];
-  int res_chunk[2][4][kTcTile];
+  int res_block[2][4][kTcTile];
   float res_thr[2][kTcTile];
-  float stage[kTcFinWarps][32][kTcDReg + 1];   // finalisers: transposed warp reduction of the coordinates
+  float res_xn2[2][kTcTile];
 };
 
 // DBG: also write the raw scores (tests).  INREG: D <= kTcDReg, a frame's coordinates live in registers.
@@ -104,79 +213,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KS = p.KS, D = p.D, K = p.K, Kpad = p.Kpad;
-  const uint32_t lbo = 128u, sbo = (uint32_t)(KS / 4) * 128u;
-  unsigned char* sB = smem_raw;                                   // Kpad x KS floats
-  unsigned char* sA = sB + (size_t)Kpad * KS * 4;                 // 2 x 128 x KS floats
-  TcSmem* S = reinterpret_cast<TcSmem*>(sA + (size_t)2 * kTcTile * KS * 4);
+  const uint32_t lbo = 128u, sbo = (uint32_t)(KS / 8) * 128u;
+  const uint32_t chunk_bytes = (uint32_t)kTcChunk * (uint32_t)KS * 2u;   // also the bytes of one A tile
+  const int nslots = p.nslots;
+  unsigned char* sB = smem_raw;                                   // nslots x 128 x KS fp16
+  unsigned char* sA = sB + (size_t)nslots * chunk_bytes;          // 2 x 128 x KS fp16
+  TcSmem* S = reinterpret_cast<TcSmem*>(sA + (size_t)2 * chunk_bytes);
+  float* stage = reinterpret_cast<float*>(S + 1);                 // INREG finalisers: [4][32][kTcDReg + 1]
   const int n_chunks = Kpad / kTcChunk;
+  const bool resident = nslots >= n_chunks;
   const int64_t n_tiles = (p.n + kTcTile - 1) / kTcTile;
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&S->a_full[b], kTcProdWarps * 32);
       mbar_init(&S->a_empty[b], 1);
-      mbar_init(&S->t_full[b], 1);
-      mbar_init(&S->t_empty[b], kTcEpiWarps);
       mbar_init(&S->r_full[b], kTcEpiWarps * 32);
       mbar_init(&S->r_empty[b], kTcFinWarps * 32);
     }
+    for (int b = 0; b < kTcRing; ++b) {
+      mbar_init(&S->t_full[b], 1);
+      mbar_init(&S->t_empty[b], 4);
+    }
     for (int b = 0; b < 4; ++b) mbar_init(&S->thr_ready[b], 1);
+    for (int b = 0; b < kTcMaxSlots; ++b) {
+      mbar_init(&S->b_full[b], 1);
+      mbar_init(&S->b_empty[b], 1);
+    }
     fence_barrier_init();
   }
   if (warp == kTcMmaWarp) tc::tmem_alloc(&S->tmem_slot, 512);
-
-  // ---- stage the centre operand: row k = n2 pieces (2) | [c'_hi c'_hi c'_lo]_d | 0...
-  float cmax2 = 0.f;
-  for (int k = tid; k < Kpad; k += kTcThreads) {
-    auto put = [&](int slot, float v) {
-      *reinterpret_cast<float*>(sB + tc::off_kmajor(k, slot, lbo, sbo)) = v;
-    };
-    for (int s = 0; s < KS; ++s) put(s, 0.f);
-    if (k < K) {
-      double n2 = 0.0;
-      for (int d = 0; d < D; ++d) {
-        const float c32 = (float)p.centers[(size_t)k * D + d];
-        n2 = fma((double)c32, (double)c32, n2);
-        const float cm = -2.0f * c32;
-        const float hi = tf32_rna(cm);
-        const float lo = tf32_rna(cm - hi);
-        put(2 + 3 * d + 0, hi);
-        put(2 + 3 * d + 1, hi);
-        put(2 + 3 * d + 2, lo);
-      }
-      const float p1 = tf32_rna((float)n2);
-      put(0, p1);
-      put(1, tf32_rna((float)(n2 - (double)p1)));
-      cmax2 = fmaxf(cmax2, (float)n2 * 1.0001f);
-    } else {
-      put(0, 8.507059e37f);   // 2^126: a dummy centre never wins
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cmax2 = fmaxf(cmax2, __shfl_xor_sync(0xffffffffu, cmax2, o));
-  if (lane == 0) S->red[warp] = cmax2;
-  fence_proxy_async_smem();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  if (tid == 0) {
-    float m = 0.f;
-    for (int w = 0; w < kTcThreads / 32; ++w) m = fmaxf(m, S->red[w]);
-    S->cmax = sqrtf(m) * 1.0001f;
-  }
-  __syncthreads();
   const uint32_t tmem = S->tmem_slot;
-  const float cmax = S->cmax;
+  const float scale = p.meta[0], cmax = p.meta[1];
 
   if (warp < kTcEpiWarps) {
     // =========================================================== epilogue warps
     const int quarter = warp & 3, grp = warp >> 2;
     const int row = quarter * 32 + lane;
-    uint32_t j = 0;   // chunk counter across tiles
+    const float inv_s2 = p.meta[2];
     uint32_t it = 0;
+    uint32_t uses = 0;   // how many times this group's TMEM buffer has been filled
     KM_DECL;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      int best = 0x7fffffff, second = 0x7fffffff, bchunk = 0;
+      int best = 0x7fffffff, second = 0x7fffffff, bblock = 0;
       // screening threshold of this row (written by the producers, handed over by the MMA warp)
       KM_T(e0);
       mbar_wait(&S->thr_ready[it & 3u], (it >> 2) & 1u);
@@ -184,22 +266,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       KM_ACC(0, e0, e1);
       const float thr = S->thr[it & 3u][row];
       const float xn2 = S->xn2[it & 3u][row];
-      for (int c = 0; c < n_chunks; ++c, ++j) {
-        const uint32_t tb = j & 1u;
+      // buffer j = it * n_chunks + c goes to ring slot j % 4: this group sees the chunks with j % 4 == grp
+      const uint32_t j0 = it * (uint32_t)n_chunks;
+      for (int c = (int)((grp - j0) & 3u); c < n_chunks; c += kTcRing, ++uses) {
         KM_T(e2);
-        mbar_wait(&S->t_full[tb], (j >> 1) & 1u);
+        mbar_wait(&S->t_full[grp], uses & 1u);
         KM_T(e3);
         KM_ACC(1, e2, e3);
         tc::fence_after_sync();
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(grp * kTcChunk);
 #pragma unroll
-        for (int h = 0; h < kTcColsPerWarp / 32; ++h) {
-          const int col0 = grp * kTcColsPerWarp + h * 32;
+        for (int h = 0; h < kTcChunk / 32; ++h) {
           float v[32];
-          tc::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTcChunk + (uint32_t)col0, v);
+          tc::tmem_ld32(tbase + (uint32_t)(h * 32), v);
           if constexpr (DBG) {
             const int64_t grow = tile * kTcTile + row;
             if (grow < p.n)
-              for (int q = 0; q < 32; ++q) p.dbg_scores[grow * Kpad + c * kTcChunk + col0 + q] = v[q] + xn2;
+              for (int q = 0; q < 32; ++q)
+                p.dbg_scores[grow * Kpad + c * kTcChunk + h * 32 + q] = (v[q] + xn2) * inv_s2;
           }
           // screen: a block whose minimum is above the row's threshold cannot hold the best centre nor
           // one within the certainty margin of it (the finaliser caps `second` at the threshold)
@@ -225,11 +309,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
             second = min(min(second, hi), t);
             best = min(best, lo);
           }
-          if (best != blk_before) bchunk = (c << 1) | h;   // low 5 key bits refer to this block
+          if (best != blk_before) bblock = c * (kTcChunk / 32) + h;   // low 5 key bits refer to this block
         }
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&S->t_empty[tb]);
+        if (lane == 0) tc::mbar_arrive(&S->t_empty[grp]);
         KM_T(e4);
         KM_ACC(2, e3, e4);
       }
@@ -240,15 +324,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       KM_ACC(3, e5, e6);
       S->res_best[rb][grp][row] = best;
       S->res_second[rb][grp][row] = second;
-      S->res_chunk[rb][grp][row] = bchunk;
-      if (grp == 0) S->res_thr[rb][row] = thr + xn2;   // back in score space, like the keys
+      S->res_block[rb][grp][row] = bblock;
+      if (grp == 0) {
+        S->res_thr[rb][row] = thr + xn2;   // back in score space, like the keys
+        S->res_xn2[rb][row] = xn2;
+      }
       tc::mbar_arrive(&S->r_full[rb]);
     }
     if (warp == 0) { KM_FLUSH(0, 4); }
   } else if (warp == kTcMmaWarp) {
-    // =========================================================== MMA issuer (lane 0 issues, the warp stays converged)
-    const uint32_t idesc = tc::idesc_tf32(kTcTile, kTcChunk, 0, 0);
+    // =========================================================== MMA issuer (one elected lane issues, the warp stays converged)
+    const uint32_t idesc = idesc_f16(kTcTile, kTcChunk);
     const uint32_t aB = smem_u32(sB), aA = smem_u32(sA);
+    const int nks = KS / 16;
     uint32_t j = 0, it = 0;
     KM_DECL;
     KM_T(m_begin);
@@ -260,26 +348,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       KM_ACC(0, m0, m1);
       tc::fence_after_sync();
       if (lane == 0) tc::mbar_arrive(&S->thr_ready[it & 3u]);   // producers' thr[] -> epilogue warps
-      const uint32_t a_base = aA + ab * (uint32_t)(kTcTile * KS * 4);
+      const uint32_t a_base = aA + ab * chunk_bytes;
       for (int c = 0; c < n_chunks; ++c, ++j) {
-        const uint32_t tb = j & 1u;
+        const uint32_t tb = j & (kTcRing - 1);
+        // the chunk's shared-memory slot: resident chunks are waited for once, streamed ones every time
+        const uint32_t bs = resident ? (uint32_t)c : (j % (uint32_t)nslots);
+        if (!resident || it == 0) {
+          const uint32_t fill = resident ? 0u : (j / (uint32_t)nslots);
+          mbar_wait(&S->b_full[bs], fill & 1u);
+        }
         KM_T(m2);
-        mbar_wait(&S->t_empty[tb], ((j >> 1) & 1u) ^ 1u);
+        mbar_wait(&S->t_empty[tb], ((j >> 2) & 1u) ^ 1u);
         KM_T(m3);
         KM_ACC(1, m2, m3);
         tc::fence_after_sync();
         {
           // descriptor of k-step s = base descriptor + (s * 2 * lbo >> 4) in the 14-bit address field
           const uint64_t da0 = tc::smem_desc(a_base, lbo, sbo, tc::kLayoutNone);
-          const uint64_t db0 = tc::smem_desc(aB + (uint32_t)c * (kTcChunk / 8) * sbo, lbo, sbo, tc::kLayoutNone);
+          const uint64_t db0 = tc::smem_desc(aB + bs * chunk_bytes, lbo, sbo, tc::kLayoutNone);
           const uint32_t d_tmem = tmem + tb * kTcChunk;
-          const int nks = KS / 8;
 #pragma unroll 1
           for (int s = 0; s < nks; ++s) {
             const uint64_t step = (uint64_t)((uint32_t)s * ((2u * lbo) >> 4));
-            tc::mma_tf32_elect(d_tmem, da0 + step, db0 + step, idesc, s > 0 ? 1u : 0u);
+            mma_f16_elect(d_tmem, da0 + step, db0 + step, idesc, s > 0 ? 1u : 0u);
           }
           tc::mma_commit_elect(&S->t_full[tb]);
+          if (!resident) tc::mma_commit_elect(&S->b_empty[bs]);
         }
       }
       tc::mma_commit_elect(&S->a_empty[ab]);
@@ -290,11 +384,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     km_prof[3] = (long long)it;
 #endif
     KM_FLUSH(4, 4);
-  } else if (warp < kTcMmaWarp + 1 + kTcProdWarps) {
+  } else if (warp == kTcLoadWarp) {
+    // =========================================================== loader: centre chunks -> shared-memory ring
+    if (lane == 0) {
+      if (resident) {
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_expect_tx(&S->b_full[c], chunk_bytes);
+          bulk_g2s(sB + (size_t)c * chunk_bytes, p.Bg + (size_t)c * chunk_bytes, chunk_bytes, &S->b_full[c]);
+        }
+      } else {
+        uint32_t j = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          for (int c = 0; c < n_chunks; ++c, ++j) {
+            const uint32_t bs = j % (uint32_t)nslots, fill = j / (uint32_t)nslots;
+            mbar_wait(&S->b_empty[bs], (fill & 1u) ^ 1u);
+            mbar_expect_tx(&S->b_full[bs], chunk_bytes);
+            bulk_g2s(sB + (size_t)bs * chunk_bytes, p.Bg + (size_t)c * chunk_bytes, chunk_bytes, &S->b_full[bs]);
+          }
+        }
+      }
+    }
+  } else if (warp < kTcFinWarp0) {
     // =========================================================== producers: A tile + screening threshold
-    const int pt = tid - (kTcMmaWarp + 1) * 32;   // 0..127: row of the tile
+    const int pt = tid - kTcProdWarp0 * 32;   // 0..127: row of the tile
     constexpr bool in_regs = INREG;
-    float yn[kTcDReg];   // coordinates of this thread's row of the NEXT tile (prefetched)
+    float yn[kTcDReg];   // SCALED coordinates of this thread's row of the NEXT tile (prefetched)
     int hint_n = -1;
     auto prefetch = [&](int64_t tile) {
       const int64_t row = tile * kTcTile + pt;
@@ -303,7 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
         if (p.hints != nullptr) hint_n = p.hints[row];
         if constexpr (in_regs) {
 #pragma unroll
-          for (int d = 0; d < kTcDReg; ++d) yn[d] = (d < D) ? p.Y[row * p.ld + d] : 0.f;
+          for (int d = 0; d < kTcDReg; ++d) yn[d] = (d < D) ? p.Y[row * p.ld + d] * scale : 0.f;
         }
       } else {
 #pragma unroll
@@ -312,6 +426,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     };
     uint32_t it = 0;
     double ysq_acc = 0.0;
+    const double inv_s2d = (double)p.meta[2];
     KM_DECL;
     if ((int64_t)blockIdx.x < n_tiles) prefetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -323,27 +438,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       for (int d = 0; d < kTcDReg; ++d) y[d] = yn[d];
       const int hint = hint_n;
       if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
-      // distance to the hinted centre from the resident centre operand: c32 = -(c'_hi + c'_lo) / 2 exactly
+      // fp32 distance to the hinted centre (scaled centres written by the prep kernel)
       float u = __int_as_float(0x7f800000);
       if (valid && hint >= 0 && hint < K) {
         u = 0.f;
-        auto cget = [&](int d) {
-          const float hi = *reinterpret_cast<const float*>(sB + tc::off_kmajor(hint, 2 + 3 * d, lbo, sbo));
-          const float lo = *reinterpret_cast<const float*>(sB + tc::off_kmajor(hint, 2 + 3 * d + 2, lbo, sbo));
-          return -0.5f * (hi + lo);
-        };
+        const float* ch = p.cs32 + (size_t)hint * D;
         if constexpr (in_regs) {
 #pragma unroll
           for (int d = 0; d < kTcDReg; ++d) {
             if (d < D) {
-              const float t = y[d] - cget(d);
+              const float t = y[d] - ch[d];
               u = fmaf(t, t, u);
             }
           }
         } else {
 #pragma unroll 4
           for (int d = 0; d < D; ++d) {
-            const float t = p.Y[row * p.ld + d] - cget(d);
+            const float t = p.Y[row * p.ld + d] * scale - ch[d];
             u = fmaf(t, t, u);
           }
         }
@@ -352,51 +463,78 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       mbar_wait(&S->a_empty[ab], ((it >> 1) & 1u) ^ 1u);
       KM_T(p1);
       KM_ACC(0, p0, p1);
-      unsigned char* A = sA + (size_t)ab * kTcTile * KS * 4;
+      unsigned char* A = sA + (size_t)ab * chunk_bytes;
       float xn2 = 0.f;
+      bool fits = true;   // every scaled coordinate is finite and inside fp16's range
       if constexpr (in_regs) {
+        double rowsq = 0.0;   // |y s|^2 in fp64: the inertia identity cancels, fp32 would not do
 #pragma unroll
         for (int d = 0; d < kTcDReg; ++d) {
           const float v = y[d];          // zero beyond D and for rows past the end
           xn2 = fmaf(v, v, xn2);
-          ysq_acc = fma((double)v, (double)v, ysq_acc);
+          rowsq = fma((double)v, (double)v, rowsq);
+          fits = fits && (fabsf(v) < kTcHalfMax);
         }
-        const float one = valid ? 1.0f : 0.0f;
-        // slot s: 0-1 -> 1, 2 + 3 d + r -> (r == 1 ? y_lo[d] : y_hi[d]); 16-byte stores, 8 lanes
+        if (!fits) {
+#pragma unroll
+          for (int d = 0; d < kTcDReg; ++d) y[d] = 0.f;
+        }
+        const float one = valid ? kTcNormUnit : 0.0f;
+        // slot s: 0-1 -> 2^13, 2 + 3 d + r -> (r == 1 ? y_lo[d] : y_hi[d]); 16-byte stores (8 slots), 8 lanes
         // cover one 128-byte core-matrix row: conflict-free
         auto slot_val = [&](int sl) -> float {
           if (sl < 2) return one;
           const int d = (sl - 2) / 3, r = (sl - 2) % 3;
           if (d >= kTcDReg) return 0.f;
-          const float hi = tf32_rna(y[d]);   // recomputed per use: keeps the producer's register count low
-          return r == 1 ? tf32_rna(y[d] - hi) : hi;
+          const float hi = __half2float(__float2half_rn(y[d]));   // recomputed per use: keeps the register count low
+          return r == 1 ? (y[d] - hi) : hi;
         };
         unsigned char* arow = A + (uint32_t)(pt >> 3) * sbo + (uint32_t)(pt & 7) * 16u;
 #pragma unroll
-        for (int j = 0; j < (3 * kTcDReg + 2 + 7) / 8 * 2; ++j) {
-          if (4 * j < KS)
-            *reinterpret_cast<float4*>(arow + (uint32_t)j * lbo) =
-                make_float4(slot_val(4 * j), slot_val(4 * j + 1), slot_val(4 * j + 2), slot_val(4 * j + 3));
+        for (int j = 0; j < (3 * kTcDReg + 2 + 15) / 16 * 2; ++j) {
+          if (8 * j < KS) {
+            __half2 h0 = __floats2half2_rn(slot_val(8 * j), slot_val(8 * j + 1));
+            __half2 h1 = __floats2half2_rn(slot_val(8 * j + 2), slot_val(8 * j + 3));
+            __half2 h2 = __floats2half2_rn(slot_val(8 * j + 4), slot_val(8 * j + 5));
+            __half2 h3 = __floats2half2_rn(slot_val(8 * j + 6), slot_val(8 * j + 7));
+            uint4 w;
+            w.x = *reinterpret_cast<uint32_t*>(&h0);
+            w.y = *reinterpret_cast<uint32_t*>(&h1);
+            w.z = *reinterpret_cast<uint32_t*>(&h2);
+            w.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(arow + (uint32_t)j * lbo) = w;
+          }
         }
+        if (valid && fits) ysq_acc = fma(rowsq, inv_s2d, ysq_acc);   // s is a power of two: exact
       } else {
         auto put = [&](int slot, float v) {
-          *reinterpret_cast<float*>(A + tc::off_kmajor(pt, slot, lbo, sbo)) = v;
+          *reinterpret_cast<__half*>(A + off_kmajor_h(pt, slot, sbo)) = __float2half_rn(v);
         };
 #pragma unroll 4
         for (int d = 0; d < D; ++d) {
-          const float v = valid ? p.Y[row * p.ld + d] : 0.f;
+          const float v = valid ? p.Y[row * p.ld + d] * scale : 0.f;
           xn2 = fmaf(v, v, xn2);
-          ysq_acc = fma((double)v, (double)v, ysq_acc);
-          const float hi = tf32_rna(v);
+          fits = fits && (fabsf(v) < kTcHalfMax);
+        }
+        double acc = 0.0;
+#pragma unroll 4
+        for (int d = 0; d < D; ++d) {
+          const float raw = valid ? p.Y[row * p.ld + d] : 0.f;
+          acc = fma((double)raw, (double)raw, acc);
+          const float v = fits ? raw * scale : 0.f;
+          const float hi = __half2float(__float2half_rn(v));
           put(2 + 3 * d + 0, hi);
-          put(2 + 3 * d + 1, tf32_rna(v - hi));
+          put(2 + 3 * d + 1, v - hi);
           put(2 + 3 * d + 2, hi);
         }
-        const float one = valid ? 1.0f : 0.0f;
+        if (valid && fits) ysq_acc += acc;
+        const float one = valid ? kTcNormUnit : 0.0f;
         put(0, one);
         put(1, one);
         for (int sl = 3 * D + 2; sl < KS; ++sl) put(sl, 0.f);
       }
+      // A frame that does not fit is decided by the fp64 re-check: NaN |y|^2 fails every certainty test.
+      if (!fits) xn2 = __int_as_float(0x7fc00000);
       // screening threshold: the fp32 distance to the hinted centre bounds the best score from above
       // (up to the envelope E); the margin keeps the certainty test decidable.  TMEM holds score - |y|^2, so the
       // epilogue compares against thr - |y|^2 and adds |y|^2 back only on the rare slow path
@@ -408,7 +546,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       KM_T(p2);
       KM_ACC(1, p1, p2);
     }
-    if (warp == kTcMmaWarp + 1) { KM_FLUSH(8, 2); }
+    if (warp == kTcProdWarp0) { KM_FLUSH(8, 2); }
     if (p.accumulate) {
       ysq_acc = warp_sum(ysq_acc);
       if (lane == 0 && ysq_acc != 0.0) atomicAdd(p.ysq, ysq_acc);
@@ -416,17 +554,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
   } else {
     // =========================================================== finalisers: merge, certainty test, labels,
     // fused Lloyd accumulation
-    const int pt = tid - (kTcMmaWarp + 1 + kTcProdWarps) * 32;
+    const int pt = tid - kTcFinWarp0 * 32;
     constexpr bool in_regs = INREG;
     int recheck_acc = 0;
     KM_DECL;
-    float yn[kTcDReg];
+    float yn[kTcDReg];   // UNSCALED coordinates (they feed the Lloyd sums)
     auto prefetch = [&](int64_t tile) {
       const int64_t row = tile * kTcTile + pt;
 #pragma unroll
       for (int d = 0; d < kTcDReg; ++d) yn[d] = (in_regs && d < D && row < p.n) ? p.Y[row * p.ld + d] : 0.f;
     };
     uint32_t it = 0;
+    double ysq_fix = 0.0;   // |y|^2 of the frames the producers left out of ysq (they did not fit fp16)
     if ((int64_t)blockIdx.x < n_tiles) prefetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       float y[kTcDReg];
@@ -438,40 +577,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       mbar_wait(&S->r_full[rb], (it >> 1) & 1u);
       KM_T(f1);
       KM_ACC(0, f0, f1);
-      int b = 0x7fffffff, s2 = 0x7fffffff, bc = 0;
+      int b = 0x7fffffff, s2 = 0x7fffffff, bb = 0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const int gb = S->res_best[rb][g][pt], gs = S->res_second[rb][g][pt], gc = S->res_chunk[rb][g][pt];
+        const int gb = S->res_best[rb][g][pt], gs = S->res_second[rb][g][pt], gk = S->res_block[rb][g][pt];
         const int t = max(b, gb);           // merge: new second = min(s2, gs, max(b, gb))
         s2 = min(min(s2, gs), t);
-        if (gb < b) { b = gb; bc = (gc << 2) | g; }
+        if (gb < b) { b = gb; bb = gk; }
       }
       const float thr = S->res_thr[rb][pt];
+      const float xn2s = S->res_xn2[rb][pt];   // NaN: the frame did not fit fp16
       tc::mbar_arrive(&S->r_empty[rb]);
       const int64_t row = tile * kTcTile + pt;
       const bool valid = row < p.n;
       int lab = -1;
       if (valid) {
-        // column = chunk * 256 + group * 64 + h * 32 + (key & 31);  bc = ((chunk << 1 | h) << 2) | group
-        const int g = bc & 3, h = (bc >> 2) & 1, ch = bc >> 3;
-        int k = ch * kTcChunk + g * kTcColsPerWarp + h * 32 + (b & 31);
-        if (k >= K) k = K - 1;   // cannot happen for finite data (dummy centres score 2^126)
+        int k = bb * 32 + (b & 31);
+        const bool in_range = k < K;   // a padding row can only win when no real centre was scored (b == INT_MAX)
+        if (!in_range) k = K - 1;
         const float s1f = __uint_as_float((uint32_t)b & 0xFFFFFFE0u);
         const float s2f = fminf(__uint_as_float((uint32_t)s2 & 0xFFFFFFE0u), thr);
-        float xn2 = 0.f;
-        if constexpr (in_regs) {
-#pragma unroll
-          for (int d = 0; d < kTcDReg; ++d) xn2 = fmaf(y[d], y[d], xn2);
-        } else {
-#pragma unroll 4
-          for (int d = 0; d < D; ++d) {
-            const float v = p.Y[row * p.ld + d];
-            xn2 = fmaf(v, v, xn2);
-          }
-        }
-        const float rr = sqrtf(xn2) * 1.0001f + cmax;
+        const float rr = sqrtf(xn2s) * 1.0001f + cmax;
         const float E = kTcErrScale * rr * rr;
-        const bool certain = (b >= 0) && (b != 0x7fffffff) && (K == 1 || (s1f * kTcKeyTrunc + E < s2f - E));
+        const bool certain = in_range && (b >= 0) && (b != 0x7fffffff) && (K == 1 || (s1f * kTcKeyTrunc + E < s2f - E));
         p.labels[row] = k;
         if (certain) {
           lab = k;
@@ -479,6 +607,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
           ++recheck_acc;
           const int pos = atomicAdd(p.recheck_count, 1);
           p.recheck_list[pos] = (int)row;
+        }
+        if (!(xn2s == xn2s) && p.accumulate) {
+          if constexpr (in_regs) {
+#pragma unroll
+            for (int d = 0; d < kTcDReg; ++d) ysq_fix = fma((double)y[d], (double)y[d], ysq_fix);
+          } else {
+            for (int d = 0; d < D; ++d) {
+              const double v = (double)p.Y[row * p.ld + d];
+              ysq_fix = fma(v, v, ysq_fix);
+            }
+          }
         }
       }
       // fused Lloyd accumulation into this call's private sums / counts.  32 consecutive frames of a
@@ -490,7 +629,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
           if (lab0 >= 0) {
             if constexpr (in_regs) {
               // transpose through shared memory: lane (d, half) adds 16 rows of coordinate d in fp64
-              float* stg = &S->stage[warp - (kTcMmaWarp + 1 + kTcProdWarps)][0][0];
+              float* stg = stage + (size_t)(warp - kTcFinWarp0) * 32 * (kTcDReg + 1);
 #pragma unroll
               for (int d = 0; d < kTcDReg; ++d) stg[lane * (kTcDReg + 1) + d] = y[d];
               __syncwarp();
@@ -523,7 +662,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       KM_T(f2);
       KM_ACC(1, f1, f2);
     }
-    if (warp == kTcMmaWarp + 1 + kTcProdWarps) { KM_FLUSH(10, 2); }
+    if (warp == kTcFinWarp0) { KM_FLUSH(10, 2); }
+    if (p.accumulate) {
+      ysq_fix = warp_sum(ysq_fix);
+      if (lane == 0 && ysq_fix != 0.0) atomicAdd(p.ysq, ysq_fix);
+    }
     if (p.n_rechecked != nullptr) {
       int r = recheck_acc;
 #pragma unroll
@@ -613,19 +756,35 @@ int kmeans_tc_debug_counters(int64_t* out16) {
   return PMB_OK;
 }
 
-static inline int tc_slots(int D) { return ((3 * D + 2) + 7) / 8 * 8; }
-static inline int tc_kpad(int K) { return (K + kTcChunk - 1) / kTcChunk * kTcChunk; }
-static inline size_t tc_smem_bytes(int D, int K) {
-  return (size_t)tc_kpad(K) * tc_slots(D) * 4 + (size_t)2 * kTcTile * tc_slots(D) * 4 + sizeof(TcSmem) + 16;
+static inline int tc_slots(int D) { return ((3 * D + 2) + 15) / 16 * 16; }
+static inline int tc_kpad(int K) { return (K + kTcKpadTo - 1) / kTcKpadTo * kTcKpadTo; }
+static inline size_t tc_chunk_bytes(int D) { return (size_t)kTcChunk * tc_slots(D) * 2; }
+static inline size_t tc_fixed_smem(int D) {
+  // two A tiles + bookkeeping + the finalisers' transpose buffer (register path only)
+  return 2 * tc_chunk_bytes(D) + sizeof(TcSmem) + (D <= kTcDReg ? (size_t)kTcFinWarps * 32 * (kTcDReg + 1) * 4 : 0) + 16;
+}
+// ring slots for centre chunks: all of them when they fit (resident), else as many as fit (streamed, >= 2)
+static inline int tc_ring_slots(int D, int K) {
+  const size_t budget = 227 * 1024, fixed = tc_fixed_smem(D);
+  if (fixed >= budget) return 0;
+  const int n_chunks = tc_kpad(K) / kTcChunk;
+  int fit = (int)((budget - fixed) / tc_chunk_bytes(D));
+  if (fit > kTcMaxSlots) fit = kTcMaxSlots;
+  if (n_chunks <= fit) return n_chunks;
+  return fit >= 2 ? fit : 0;
 }
 
 bool kmeans_tc_supported(int D, int K) {
-  return D >= 1 && K >= 1 && tc_smem_bytes(D, K) <= 227 * 1024 && tc_kpad(K) / kTcChunk <= (1 << 20);
+  return D >= 1 && K >= 1 && tc_slots(D) * 2 / 16 < (1 << 14) && tc_ring_slots(D, K) > 0;
 }
 
+static inline size_t tc_align256(size_t x) { return (x + 255) / 256 * 256; }
+
 size_t kmeans_tc_ws_bytes(int64_t n, int D, int K) {
-  // [count | ysq | pad to 64 B][local sums K x D][local counts K][re-check list n]
-  return 64 + ((size_t)K * D + K) * sizeof(double) + (size_t)n * sizeof(int) + 64;
+  // [count | ysq | meta | pad to 256 B][local sums K x D][local counts K][scaled centres K x D fp32]
+  // [centre operand image Kpad x KS fp16][re-check list n]
+  return 256 + tc_align256(((size_t)K * D + K) * sizeof(double)) + tc_align256((size_t)K * D * sizeof(float)) +
+         tc_align256((size_t)tc_kpad(K) * tc_slots(D) * 2) + (size_t)n * sizeof(int) + 256;
 }
 
 int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double* centers, int K, int32_t* labels,
@@ -633,19 +792,30 @@ int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double*
                      float* dbg_scores, cudaStream_t st) {
   KmTcParams p;
   p.Y = Y; p.n = n; p.D = D; p.ld = ld; p.centers = centers; p.K = K;
-  p.Kpad = tc_kpad(K); p.KS = tc_slots(D);
+  p.Kpad = tc_kpad(K); p.KS = tc_slots(D); p.nslots = tc_ring_slots(D, K);
   p.labels = labels; p.hints = hints; p.sums = sums; p.counts = counts; p.inertia = inertia; p.n_rechecked = n_rechecked;
+  PMB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "pmb_kmeans_assign: workspace must be 256-byte aligned");
   unsigned char* w8 = static_cast<unsigned char*>(ws);
   p.recheck_count = reinterpret_cast<int*>(w8);
   p.ysq = reinterpret_cast<double*>(w8 + 16);
-  p.lsums = reinterpret_cast<double*>(w8 + 64);
+  p.meta = reinterpret_cast<float*>(w8 + 64);
+  size_t off = 256;
+  p.lsums = reinterpret_cast<double*>(w8 + off);
   p.lcounts = reinterpret_cast<unsigned long long*>(p.lsums + (size_t)K * D);
-  p.recheck_list = reinterpret_cast<int*>(p.lcounts + K);
+  off += tc_align256(((size_t)K * D + K) * sizeof(double));
+  p.cs32 = reinterpret_cast<float*>(w8 + off);
+  off += tc_align256((size_t)K * D * sizeof(float));
+  p.Bg = w8 + off;
+  off += tc_align256((size_t)p.Kpad * p.KS * 2);
+  p.recheck_list = reinterpret_cast<int*>(w8 + off);
   p.accumulate = (sums != nullptr || inertia != nullptr) ? 1 : 0;
   p.dbg_scores = dbg_scores;
   PMB_REQUIRE(n < (int64_t)0x7fffffff, "pmb_kmeans_assign: tensor path needs n < 2^31");
-  const size_t smem = tc_smem_bytes(D, K);
-  PMB_CUDA(cudaMemsetAsync(ws, 0, 64 + (p.accumulate ? ((size_t)K * D + K) * sizeof(double) : 0), st));
+  PMB_REQUIRE(p.nslots > 0, "pmb_kmeans_assign: D=%d does not fit the tensor path's shared memory", D);
+  const size_t smem = (size_t)p.nslots * tc_chunk_bytes(D) + tc_fixed_smem(D);
+  PMB_CUDA(cudaMemsetAsync(ws, 0, 256 + (p.accumulate ? ((size_t)K * D + K) * sizeof(double) : 0), st));
+  kmeans_tc_prep_kernel<<<1, 1024, 0, st>>>(p);
+  PMB_LAUNCH_CHECK();
   const int64_t n_tiles = (n + kTcTile - 1) / kTcTile;
   const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
   auto launch = [&](auto kern) -> int {
