@@ -230,6 +230,14 @@ PMB_API int pmb_counts_active(const int64_t* C, int K, double eps, double* Cf, u
  * B (Kdim x N) row-major (MN-major, 128 B swizzle with 32 B base: the Gram layout).  D: 128 x N fp32. */
 PMB_API int pmb_tc_selftest(const float* A, const float* B, int N, int Kdim, int mode, float* D,
                             pmb_stream_t stream);
+/* Same product from caller-built shared-memory operand images (a_bytes / b_bytes, copied verbatim to
+ * 1024-byte aligned shared memory) and explicit descriptor fields: leading / stride byte offsets, layout type
+ * (0 none, 1 128B swizzle with 32B base, 2 128B, 4 64B, 6 32B), descriptor address advance per K step for
+ * each operand, the 32-bit instruction descriptor, kind (0 tf32, 1 f16).  Test-only: validates the 16-bit
+ * operand layouts of K6 (fp16, K-major) and K3 (bf16, MN-major) in isolation. */
+PMB_API int pmb_tc_selftest_raw(const void* Aimg, uint32_t a_bytes, const void* Bimg, uint32_t b_bytes, int N,
+                                int nsteps, uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t step_a,
+                                uint32_t step_b, uint32_t idesc, int kind, float* D, pmb_stream_t stream);
 
 /* ---- K8 reversible maximum-likelihood MSM -----------------------------------------
  * Replaces deeptime MaximumLikelihoodMSM(reversible=True).fit(counts)

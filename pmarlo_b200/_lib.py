@@ -51,6 +51,8 @@ PROTOTYPES = {
     "pmb_relabel_compact_ws_bytes": (_sz, [_i64]),
     "pmb_relabel_compact": (_i32, [_p, _i64, _p, _i32, _p, _i32, _p, _p, _p, _sz, _p]),
     "pmb_tc_selftest": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p]),
+    "pmb_tc_selftest_raw": (_i32, [_p, C.c_uint32, _p, C.c_uint32, _i32, _i32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                   C.c_uint32, C.c_uint32, C.c_uint32, _i32, _p, _p]),
     "pmb_mle_rev_ws_bytes": (_sz, [_i32, _i32]),
     "pmb_mle_rev": (_i32, [_p, _p, _i32, _i32, _f64, _f64, _i64, _p, _p, _p, _p, _sz, _p]),
     "pmb_counts_active": (_i32, [_p, _i32, _f64, _p, _p, _p]),

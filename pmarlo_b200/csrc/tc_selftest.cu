@@ -84,7 +84,87 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
   if (warp == 0) tc::tmem_dealloc(tmem, cols);
 }
 
+// Raw variant: the host supplies the two shared-memory operand IMAGES byte for byte plus every descriptor
+// field, so that a layout hypothesis (16-bit operands, MN-major swizzles, ...) can be checked from Python
+// without recompiling.  kind: 0 = tf32, 1 = f16 (fp16 / bf16 operands, selected by the idesc format fields).
+__global__ void __launch_bounds__(128) tc_selftest_raw_kernel(const unsigned char* __restrict__ Aimg, uint32_t a_bytes,
+                                                              const unsigned char* __restrict__ Bimg, uint32_t b_bytes,
+                                                              int N, int nsteps, uint32_t lbo, uint32_t sbo, uint32_t layout,
+                                                              uint32_t step_a, uint32_t step_b, uint32_t idesc, int kind,
+                                                              float* __restrict__ D) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned char* sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  unsigned char* sB = sA + ((a_bytes + 1023u) & ~1023u);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)N) cols <<= 1;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, cols);
+  for (uint32_t i = tid; i < a_bytes; i += 128) sA[i] = Aimg[i];
+  for (uint32_t i = tid; i < b_bytes; i += 128) sB[i] = Bimg[i];
+  fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    for (int s = 0; s < nsteps; ++s) {
+      const uint64_t da = tc::smem_desc(smem_u32(sA) + (uint32_t)s * step_a, lbo, sbo, (uint64_t)layout);
+      const uint64_t db = tc::smem_desc(smem_u32(sB) + (uint32_t)s * step_b, lbo, sbo, (uint64_t)layout);
+      if (kind == 0) {
+        tc::mma_tf32(tmem, da, db, idesc, s > 0 ? 1u : 0u);
+      } else {
+        const uint32_t acc = s > 0 ? 1u : 0u;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem),
+            "l"(da), "l"(db), "r"(idesc), "r"(acc)
+            : "memory");
+      }
+    }
+    tc::mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc::fence_after_sync();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) D[(size_t)row * N + c0 + j] = v[j];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, cols);
+}
+
 }  // namespace pmb
+
+extern "C" int pmb_tc_selftest_raw(const void* Aimg, uint32_t a_bytes, const void* Bimg, uint32_t b_bytes, int N,
+                                   int nsteps, uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t step_a,
+                                   uint32_t step_b, uint32_t idesc, int kind, float* D, pmb_stream_t stream) {
+  using namespace pmb;
+  PMB_REQUIRE(Aimg && Bimg && D, "pmb_tc_selftest_raw: null pointer");
+  PMB_REQUIRE(N >= 32 && N <= 256 && N % 32 == 0, "pmb_tc_selftest_raw: N must be a multiple of 32 in [32,256]");
+  PMB_REQUIRE(nsteps >= 1 && nsteps <= 16 && (kind == 0 || kind == 1), "pmb_tc_selftest_raw: bad nsteps / kind");
+  const size_t smem = (size_t)((a_bytes + 1023u) & ~1023u) + b_bytes + 2048;
+  PMB_REQUIRE(smem <= 200 * 1024, "pmb_tc_selftest_raw: operand images too large");
+  PMB_CUDA(cudaFuncSetAttribute(tc_selftest_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_raw_kernel<<<1, 128, smem, as_stream(stream)>>>(static_cast<const unsigned char*>(Aimg), a_bytes,
+                                                              static_cast<const unsigned char*>(Bimg), b_bytes, N, nsteps,
+                                                              lbo, sbo, layout, step_a, step_b, idesc, kind, D);
+  PMB_LAUNCH_CHECK();
+  return PMB_OK;
+}
 
 extern "C" int pmb_tc_selftest(const float* A, const float* B, int N, int Kdim, int mode, float* D,
                                pmb_stream_t stream) {

@@ -404,5 +404,18 @@ def tc_selftest(A: torch.Tensor, B: torch.Tensor, mode: int) -> torch.Tensor:
     return D
 
 
+def tc_selftest_raw(a_img: torch.Tensor, b_img: torch.Tensor, n: int, nsteps: int, lbo: int, sbo: int, layout: int,
+                    step_a: int, step_b: int, idesc: int, kind: int) -> torch.Tensor:
+    """tcgen05 product from caller-built shared-memory operand images (uint8 tensors); see pmb200.h."""
+    _flat(a_img, torch.uint8, "a_img")
+    _flat(b_img, torch.uint8, "b_img")
+    D = torch.empty((128, int(n)), dtype=torch.float32, device=a_img.device)
+    check(_lib.lib().pmb_tc_selftest_raw(ptr(a_img), int(a_img.numel()), ptr(b_img), int(b_img.numel()), int(n),
+                                         int(nsteps), int(lbo), int(sbo), int(layout), int(step_a), int(step_b),
+                                         int(idesc), int(kind), ptr(D), stream_handle(a_img.device)),
+          "pmb_tc_selftest_raw")
+    return D
+
+
 def as_numpy(t: torch.Tensor) -> np.ndarray:
     return t.detach().cpu().numpy()
