@@ -19,9 +19,9 @@
 // K = 5000, 40 x 52 KB) they stream through the ring once per frame tile, fed from L2.
 //
 // Pipeline (one persistent CTA per SM, 26 warps, warp-specialised, mbarrier hand-offs):
-//   warps 0-15   epilogue  : four groups of four warps (one per TMEM lane quarter).  Group g owns TMEM ring
-//                            slot g: tcgen05.ld 4 x 32 columns, 3-input-min tree, screening against the
-//                            row's threshold, running (best, second) as packed integer keys
+//   warps 0-15   epilogue  : warp (g, q) reads columns 32 g .. 32 g + 31 of lane quarter q of EVERY buffer with
+//                            one tcgen05.ld, releases the buffer at once, then 3-input-min tree, screening
+//                            against the row's threshold, running (best, second) as packed integer keys
 //   warp  16     MMA issuer: per chunk KS/16 tcgen05.mma (M 128, N 128) into the next of FOUR TMEM buffers
 //   warp  17     loader    : bulk copies of centre chunks into the shared-memory ring
 //   warps 18-21  producers : build the A tile (128 frames x KS slots, K-major core-matrix layout) and the
@@ -54,6 +54,9 @@ __device__ long long g_km_dbg[16];
 #define KM_FLUSH(base, n)
 #endif
 
+#ifndef PMB_KM_EPI
+#define PMB_KM_EPI 1   // 0: every epilogue warp reads one block of every buffer; 1: one warp group per ring slot
+#endif
 constexpr int kTcTile = 128;     // frames per tile  (MMA M)
 constexpr int kTcChunk = 128;    // centres per MMA  (MMA N) = columns of one TMEM buffer
 constexpr int kTcRing = 4;       // TMEM buffers (4 x 128 columns = all 512)
@@ -227,13 +230,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&S->a_full[b], kTcProdWarps * 32);
-      mbar_init(&S->a_empty[b], 1);
+      mbar_init(&S->a_empty[b], resident ? 2 : 1);
       mbar_init(&S->r_full[b], kTcEpiWarps * 32);
       mbar_init(&S->r_empty[b], kTcFinWarps * 32);
     }
     for (int b = 0; b < kTcRing; ++b) {
       mbar_init(&S->t_full[b], 1);
-      mbar_init(&S->t_empty[b], 4);
+      mbar_init(&S->t_empty[b], PMB_KM_EPI == 0 ? kTcEpiWarps : 4);
     }
     for (int b = 0; b < 4; ++b) mbar_init(&S->thr_ready[b], 1);
     for (int b = 0; b < kTcMaxSlots; ++b) {
@@ -255,7 +258,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     const int row = quarter * 32 + lane;
     const float inv_s2 = p.meta[2];
     uint32_t it = 0;
-    uint32_t uses = 0;   // how many times this group's TMEM buffer has been filled
+    uint32_t uses = 0;   // group-per-buffer variant: how many times this group's TMEM buffer has been filled
+    (void)uses;
     KM_DECL;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       int best = 0x7fffffff, second = 0x7fffffff, bblock = 0;
@@ -266,24 +270,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       KM_ACC(0, e0, e1);
       const float thr = S->thr[it & 3u][row];
       const float xn2 = S->xn2[it & 3u][row];
-      // buffer j = it * n_chunks + c goes to ring slot j % 4: this group sees the chunks with j % 4 == grp
-      const uint32_t j0 = it * (uint32_t)n_chunks;
-      for (int c = (int)((grp - j0) & 3u); c < n_chunks; c += kTcRing, ++uses) {
+#if PMB_KM_EPI == 0
+      // Every epilogue warp visits every buffer (ring slot j % 4 for chunk j = it * n_chunks + c) and reads ONE
+      // 32-column block of it: the round trip MMA -> commit -> epilogue -> release -> next MMA of a slot costs
+      // ~1100 cycles of latency whatever the work (tools/ubench_mma.cu, mma_ring), so the time a buffer stays
+      // with the epilogue has to be as short as possible -- 16 warps x 1 block, not 4 warps x 4 blocks.
+      uint32_t j = it * (uint32_t)n_chunks;
+      for (int c = 0; c < n_chunks; ++c, ++j) {
+        const uint32_t tb = j & (kTcRing - 1);
         KM_T(e2);
-        mbar_wait(&S->t_full[grp], uses & 1u);
+        mbar_wait(&S->t_full[tb], (j >> 2) & 1u);
         KM_T(e3);
         KM_ACC(1, e2, e3);
         tc::fence_after_sync();
-        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(grp * kTcChunk);
-#pragma unroll
-        for (int h = 0; h < kTcChunk / 32; ++h) {
+        {
           float v[32];
-          tc::tmem_ld32(tbase + (uint32_t)(h * 32), v);
+          tc::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTcChunk + (uint32_t)(grp * 32), v);
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&S->t_empty[tb]);     // the values are in registers: release the buffer now
           if constexpr (DBG) {
             const int64_t grow = tile * kTcTile + row;
             if (grow < p.n)
               for (int q = 0; q < 32; ++q)
-                p.dbg_scores[grow * Kpad + c * kTcChunk + h * 32 + q] = (v[q] + xn2) * inv_s2;
+                p.dbg_scores[grow * Kpad + c * kTcChunk + grp * 32 + q] = (v[q] + xn2) * inv_s2;
           }
           // screen: a block whose minimum is above the row's threshold cannot hold the best centre nor
           // one within the certainty margin of it (the finaliser caps `second` at the threshold)
@@ -297,8 +307,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
 #pragma unroll
           for (int q = 0; q < 4; ++q) t4[q] = fminf(fminf(t12[3 * q], t12[3 * q + 1]), t12[3 * q + 2]);
           const float bmin = fminf(fminf(fminf(t4[0], t4[1]), t4[2]), t4[3]);
+          if (__any_sync(0xffffffffu, bmin <= thr)) {
+            // packed keys: score bits with the position inside this 32-column block in the low 5 bits
+            const int blk_before = best;
+#pragma unroll
+            for (int q = 0; q < 32; q += 2) {
+              const int k0 = (int)((__float_as_uint(fmaxf(v[q] + xn2, 0.f)) & 0xFFFFFFE0u) | (uint32_t)q);
+              const int k1 = (int)((__float_as_uint(fmaxf(v[q + 1] + xn2, 0.f)) & 0xFFFFFFE0u) | (uint32_t)(q + 1));
+              const int lo = min(k0, k1), hi = max(k0, k1);
+              const int t = max(best, lo);
+              second = min(min(second, hi), t);
+              best = min(best, lo);
+            }
+            if (best != blk_before) bblock = c * (kTcChunk / 32) + grp;   // low 5 key bits refer to this block
+          }
+        }
+        KM_T(e4);
+        KM_ACC(2, e3, e4);
+      }
+#else
+      // Group g owns ring slot g: chunk j = it * n_chunks + c lands in slot j % 4, so this group sees the chunks with
+      // j % 4 == grp and reads all four 32-column blocks of its lane quarter.
+      const uint32_t j0 = it * (uint32_t)n_chunks;
+      for (int c = (int)((grp - j0) & 3u); c < n_chunks; c += kTcRing, ++uses) {
+        KM_T(e2);
+        mbar_wait(&S->t_full[grp], uses & 1u);
+        KM_T(e3);
+        KM_ACC(1, e2, e3);
+        tc::fence_after_sync();
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(grp * kTcChunk);
+#pragma unroll
+        for (int h = 0; h < kTcChunk / 32; ++h) {
+          float v[32];
+          tc::tmem_ld32(tbase + (uint32_t)(h * 32), v);
+          if (h == kTcChunk / 32 - 1) {          // last block in registers: hand the buffer back before the arithmetic
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&S->t_empty[grp]);
+          }
+          if constexpr (DBG) {
+            const int64_t grow = tile * kTcTile + row;
+            if (grow < p.n)
+              for (int q = 0; q < 32; ++q)
+                p.dbg_scores[grow * Kpad + c * kTcChunk + h * 32 + q] = (v[q] + xn2) * inv_s2;
+          }
+          float t12[12];
+#pragma unroll
+          for (int q = 0; q < 10; ++q) t12[q] = fminf(fminf(v[3 * q], v[3 * q + 1]), v[3 * q + 2]);
+          t12[10] = v[30];
+          t12[11] = v[31];
+          float t4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) t4[q] = fminf(fminf(t12[3 * q], t12[3 * q + 1]), t12[3 * q + 2]);
+          const float bmin = fminf(fminf(fminf(t4[0], t4[1]), t4[2]), t4[3]);
           if (!__any_sync(0xffffffffu, bmin <= thr)) continue;
-          // packed keys: score bits with the position inside this 32-column block in the low 5 bits
           const int blk_before = best;
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
@@ -309,14 +371,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
             second = min(min(second, hi), t);
             best = min(best, lo);
           }
-          if (best != blk_before) bblock = c * (kTcChunk / 32) + h;   // low 5 key bits refer to this block
+          if (best != blk_before) bblock = c * (kTcChunk / 32) + h;
         }
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&S->t_empty[grp]);
         KM_T(e4);
         KM_ACC(2, e3, e4);
       }
+#endif
       const uint32_t rb = it & 1u;
       KM_T(e5);
       mbar_wait(&S->r_empty[rb], ((it >> 1) & 1u) ^ 1u);
@@ -332,74 +392,160 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       tc::mbar_arrive(&S->r_full[rb]);
     }
     if (warp == 0) { KM_FLUSH(0, 4); }
-  } else if (warp == kTcMmaWarp) {
-    // =========================================================== MMA issuer (one elected lane issues, the warp stays converged)
+  } else if (warp == kTcMmaWarp || (warp == kTcLoadWarp && resident)) {
+    // =========================================================== MMA issuer(s)
+    // This warp's own instruction stream is the pace-maker of the tensor pipe: a lone warp retires a dependent
+    // scalar instruction every ~5 cycles, so descriptor arithmetic, integer divisions or one elect per MMA in
+    // this loop cost more than the MMAs themselves (tools/ubench_mma.cu: 708 cycles per 2-MMA chunk with a
+    // naive loop, 175 with the loop below).  Everything is precomputed; one elect covers a chunk's MMAs and
+    // its commit.
     const uint32_t idesc = idesc_f16(kTcTile, kTcChunk);
     const uint32_t aB = smem_u32(sB), aA = smem_u32(sA);
     const int nks = KS / 16;
-    uint32_t j = 0, it = 0;
+    const uint64_t dA0 = tc::smem_desc(aA, lbo, sbo, tc::kLayoutNone);
+    const uint64_t dA_other = (uint64_t)(chunk_bytes >> 4);     // address-field distance between the two A tiles
+    const uint64_t dB0 = tc::smem_desc(aB, lbo, sbo, tc::kLayoutNone);
+    const uint64_t dB_slot = (uint64_t)(chunk_bytes >> 4);      // ... from one ring slot of the centre operand to the next
+    const uint64_t kstep = (uint64_t)((2u * lbo) >> 4);         // ... and from one K = 16 step to the next
+    const uint32_t t_full0 = smem_u32(&S->t_full[0]), t_empty0 = smem_u32(&S->t_empty[0]);
+    uint32_t it = 0;
     KM_DECL;
     KM_T(m_begin);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t ab = it & 1u;
-      KM_T(m0);
-      mbar_wait(&S->a_full[ab], (it >> 1) & 1u);
-      KM_T(m1);
-      KM_ACC(0, m0, m1);
-      tc::fence_after_sync();
-      if (lane == 0) tc::mbar_arrive(&S->thr_ready[it & 3u]);   // producers' thr[] -> epilogue warps
-      const uint32_t a_base = aA + ab * chunk_bytes;
-      for (int c = 0; c < n_chunks; ++c, ++j) {
-        const uint32_t tb = j & (kTcRing - 1);
-        // the chunk's shared-memory slot: resident chunks are waited for once, streamed ones every time
-        const uint32_t bs = resident ? (uint32_t)c : (j % (uint32_t)nslots);
-        if (!resident || it == 0) {
-          const uint32_t fill = resident ? 0u : (j / (uint32_t)nslots);
-          mbar_wait(&S->b_full[bs], fill & 1u);
-        }
-        KM_T(m2);
-        mbar_wait(&S->t_empty[tb], ((j >> 2) & 1u) ^ 1u);
-        KM_T(m3);
-        KM_ACC(1, m2, m3);
-        tc::fence_after_sync();
-        {
-          // descriptor of k-step s = base descriptor + (s * 2 * lbo >> 4) in the 14-bit address field
-          const uint64_t da0 = tc::smem_desc(a_base, lbo, sbo, tc::kLayoutNone);
-          const uint64_t db0 = tc::smem_desc(aB + bs * chunk_bytes, lbo, sbo, tc::kLayoutNone);
-          const uint32_t d_tmem = tmem + tb * kTcChunk;
+    // one chunk: nks MMAs into TMEM buffer tb and the commit that hands the buffer to the epilogue
+    auto issue_chunk = [&](uint64_t da, uint64_t db, uint32_t tb) {
+      const uint32_t d_tmem = tmem + tb * kTcChunk;
+      const uint32_t bar = t_full0 + tb * 8u;
+      if (nks == 2) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %5, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %4, %5, 1;\n\t"
+            "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(da), "l"(db), "l"(da + kstep), "l"(db + kstep), "r"(idesc), "r"(bar)
+            : "memory");
+      } else if (nks == 1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 0;\n\t"
+            "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(da), "l"(db), "r"(idesc), "r"(bar)
+            : "memory");
+      } else {
+        uint64_t a = da, b = db;
 #pragma unroll 1
-          for (int s = 0; s < nks; ++s) {
-            const uint64_t step = (uint64_t)((uint32_t)s * ((2u * lbo) >> 4));
-            mma_f16_elect(d_tmem, da0 + step, db0 + step, idesc, s > 0 ? 1u : 0u);
-          }
-          tc::mma_commit_elect(&S->t_full[tb]);
-          if (!resident) tc::mma_commit_elect(&S->b_empty[bs]);
+        for (int s = 0; s < nks; ++s, a += kstep, b += kstep) mma_f16_elect(d_tmem, a, b, idesc, s > 0 ? 1u : 0u);
+        tc::mma_commit_elect(&S->t_full[tb]);
+      }
+    };
+    // wait until the epilogue has released ring slot tb (phase parity par)
+    auto wait_slot = [&](uint32_t tb, uint32_t par) {
+      const uint32_t addr = t_empty0 + tb * 8u;
+#pragma unroll 1
+      for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(addr), "r"(par)
+            : "memory");
+        if (ok) return;
+      }
+      __trap();
+    };
+    if (resident) {
+      // TWO issuing warps (this one and the otherwise idle loader warp): the pace of a lone issuer is its own
+      // serial instruction stream (~350 cycles per chunk with the waits), twice what the epilogue needs.  Warp m
+      // issues the chunks c = m (mod 2); the number of chunks per tile is even, so they live in ring slots
+      // m and m + 2.  The second warp first launches the one-time bulk copies of the centre chunks.
+      const uint32_t m = (uint32_t)(warp - kTcMmaWarp);
+      if (m == 1u && lane == 0) {
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_expect_tx(&S->b_full[c], chunk_bytes);
+          bulk_g2s(sB + (size_t)c * chunk_bytes, p.Bg + (size_t)c * chunk_bytes, chunk_bytes, &S->b_full[c]);
         }
       }
-      tc::mma_commit_elect(&S->a_empty[ab]);
+      __syncwarp();
+      for (int c = 0; c < n_chunks; ++c) mbar_wait(&S->b_full[c], 0u);
+      uint32_t tb = m, par = 1u;   // ring slot and the parity its t_empty barrier is waited with
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ab = it & 1u;
+        KM_T(m0);
+        mbar_wait(&S->a_full[ab], (it >> 1) & 1u);
+        KM_T(m1);
+        KM_ACC(0, m0, m1);
+        tc::fence_after_sync();
+        if (m == 0u && lane == 0) tc::mbar_arrive(&S->thr_ready[it & 3u]);   // producers' thr[] -> epilogue warps
+        const uint64_t da = dA0 + (ab ? dA_other : 0ull);
+        uint64_t db = dB0 + (uint64_t)m * dB_slot;
+#pragma unroll 1
+        for (int c = (int)m; c < n_chunks; c += 2, db += 2 * dB_slot) {
+          KM_T(m2);
+          wait_slot(tb, par);
+          KM_T(m3);
+          KM_ACC(1, m2, m3);
+          tc::fence_after_sync();
+          issue_chunk(da, db, tb);
+          tb ^= 2u;
+          par ^= (tb == m) ? 1u : 0u;
+        }
+        tc::mma_commit_elect(&S->a_empty[ab]);      // one arrival per issuing warp
+      }
+    } else {
+      uint32_t tb = 0, par = 1u;
+      uint32_t bs = 0, bfill = 0;   // streamed centre chunks: shared-memory ring slot and fill parity
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ab = it & 1u;
+        KM_T(m0);
+        mbar_wait(&S->a_full[ab], (it >> 1) & 1u);
+        KM_T(m1);
+        KM_ACC(0, m0, m1);
+        tc::fence_after_sync();
+        if (lane == 0) tc::mbar_arrive(&S->thr_ready[it & 3u]);
+        const uint64_t da = dA0 + (ab ? dA_other : 0ull);
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(&S->b_full[bs], bfill);
+          KM_T(m2);
+          wait_slot(tb, par);
+          KM_T(m3);
+          KM_ACC(1, m2, m3);
+          tc::fence_after_sync();
+          issue_chunk(da, dB0 + (uint64_t)bs * dB_slot, tb);
+          tc::mma_commit_elect(&S->b_empty[bs]);
+          if (++bs == (uint32_t)nslots) { bs = 0; bfill ^= 1u; }
+          tb = (tb + 1u) & (kTcRing - 1);
+          par ^= (tb == 0u) ? 1u : 0u;
+        }
+        tc::mma_commit_elect(&S->a_empty[ab]);
+      }
     }
     KM_T(m_end);
     KM_ACC(2, m_begin, m_end);
 #ifdef PMB_KM_PROF
     km_prof[3] = (long long)it;
 #endif
-    KM_FLUSH(4, 4);
+    if (warp == kTcMmaWarp) { KM_FLUSH(4, 4); }
   } else if (warp == kTcLoadWarp) {
-    // =========================================================== loader: centre chunks -> shared-memory ring
+    // =========================================================== loader (streamed centre chunks only) -> shared-memory ring
     if (lane == 0) {
-      if (resident) {
-        for (int c = 0; c < n_chunks; ++c) {
-          mbar_expect_tx(&S->b_full[c], chunk_bytes);
-          bulk_g2s(sB + (size_t)c * chunk_bytes, p.Bg + (size_t)c * chunk_bytes, chunk_bytes, &S->b_full[c]);
-        }
-      } else {
-        uint32_t j = 0;
+      {
+        uint32_t bs = 0, bfill = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-          for (int c = 0; c < n_chunks; ++c, ++j) {
-            const uint32_t bs = j % (uint32_t)nslots, fill = j / (uint32_t)nslots;
-            mbar_wait(&S->b_empty[bs], (fill & 1u) ^ 1u);
+          for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(&S->b_empty[bs], bfill ^ 1u);
             mbar_expect_tx(&S->b_full[bs], chunk_bytes);
             bulk_g2s(sB + (size_t)bs * chunk_bytes, p.Bg + (size_t)c * chunk_bytes, chunk_bytes, &S->b_full[bs]);
+            if (++bs == (uint32_t)nslots) { bs = 0; bfill ^= 1u; }
           }
         }
       }

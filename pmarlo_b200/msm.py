@@ -303,3 +303,83 @@ def implied_timescales(dtrajs: Sequence[np.ndarray], lag_times: Sequence[int], n
         out_ts[b, : ts.size] = ts
         iters[b] = infoh[row, 0]
     return ITSResult(np.asarray(lags), out_ts, out_ev, iters, sizes)
+
+
+# ----------------------------------------------------------------------------- lag ladders / deterministic ITS
+_LAG_LADDER = (1, 2, 3, 5, 8, 10, 15, 20, 30, 40, 50, 75, 80, 100, 150, 160, 200, 300, 320, 500, 640, 750, 1000,
+               1280, 1500, 2000)
+
+
+def candidate_lag_ladder(min_lag: int = 1, max_lag: int = 200, n_candidates: int | None = None) -> list[int]:
+    """``pmarlo.utils.msm_utils.candidate_lag_ladder`` (utils/msm_utils.py:21-105): the curated ladder of
+    "nice" lags inside [min_lag, max_lag], optionally thinned to ``n_candidates`` roughly evenly spaced
+    entries with both endpoints kept.  Same exceptions and messages."""
+    lo, hi = int(min_lag), int(max_lag)
+    if lo < 1:
+        raise ValueError("min_lag must be >= 1")
+    if hi < lo:
+        raise ValueError("max_lag must be >= min_lag")
+    if n_candidates is not None and n_candidates < 1:
+        raise ValueError("n_candidates must be positive")
+    filtered = [x for x in _LAG_LADDER if lo <= x <= hi]
+    if not filtered:
+        raise ValueError(f"No predefined lag values available in range [{lo}, {hi}]")
+    if n_candidates is None or n_candidates >= len(filtered):
+        return filtered
+    if n_candidates == 1:
+        return [filtered[0]]
+    if n_candidates == 2:
+        return [filtered[0], filtered[-1]]
+    step = (len(filtered) - 1) / (n_candidates - 1)
+    picks = sorted({int(round(i * step)) for i in range(n_candidates)})
+    picks[0] = 0
+    picks[-1] = len(filtered) - 1
+    return [filtered[i] for i in picks]
+
+
+def deterministic_its_from_counts(lag: int, counts, n_timescales: int):
+    """``ITSMixin._deterministic_its_from_counts`` (_its.py:742-801), the fallback that fills lags whose
+    Bayesian estimate has no finite timescale: T = row-normalised (C + C^T) / 2, the weights
+    ``mu = max(rowsum(T), 1e-15)`` normalised (uniform over non-empty rows -- what the reference passes as
+    ``mu``), eigenvalues of deeptime's reversible branch = LAPACK ``eigvalsh`` of
+    S = sqrt(mu)_i T_ij / sqrt(mu)_j, which reads the LOWER triangle only; sorted by real part, clipped to
+    [1e-12, 1 - 1e-12]; timescales -lag / ln|lambda| from the magnitude-sorted spectrum (infinite where
+    |lambda| = 1 to 1e-14).  Returns (eigenvalues, timescales, rates), each of length ``n_timescales``.
+    The K x K symmetric eigenproblem runs in libpmb200 (``pmb_sym_eigvals_batched``, cyclic Jacobi)."""
+    dev = kernels.require_cuda()
+    C = torch.as_tensor(np.asarray(counts, dtype=np.float64)).to(dev)
+    K = int(C.shape[0])
+    n_ts = int(n_timescales)
+    C_rev = 0.5 * (C + C.T)
+    row = C_rev.sum(dim=1, keepdim=True)
+    T = C_rev / torch.where(row == 0, torch.ones_like(row), row)
+    mu = torch.clamp(T.sum(dim=1), min=1e-15)
+    mu = mu / mu.sum()
+    smu = torch.sqrt(mu)
+    S = smu[:, None] * T / smu[None, :]
+    L = torch.tril(S)
+    sym = L + torch.tril(S, -1).T
+    lam = kernels.sym_eigvals_batched(sym)[0].cpu().numpy()          # by magnitude, descending
+    k_request = n_ts + 1 if n_ts > 0 else None
+    k_eval = None if (k_request is not None and k_request > K) else k_request
+    ev = lam if k_eval is None else lam[:k_eval]
+    ev_sorted = ev[np.argsort(-ev, kind="stable")]
+    slow = ev_sorted[1:1 + n_ts] if n_ts > 0 else np.empty((0,))
+    slow = np.clip(np.abs(slow), NUMERIC_MIN_POSITIVE, 1.0 - NUMERIC_MIN_POSITIVE)
+    evals = np.zeros((n_ts,), dtype=float)
+    evals[: slow.shape[0]] = slow
+    if n_ts > 0:
+        k_times = None if k_request is None else min(K, n_ts + 1)
+        evt = lam if k_times is None else lam[:k_times]
+        ts_raw = np.zeros(evt.shape[0])
+        one = np.isclose(np.abs(evt), 1.0, rtol=0.0, atol=1e-14)
+        ts_raw[one] = np.inf
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ts_raw[~one] = -float(max(1, int(lag))) / np.log(np.abs(evt[~one]))
+        ts_arr = ts_raw[1:1 + n_ts]
+    else:
+        ts_arr = np.empty((0,))
+    if ts_arr.shape[0] < n_ts:
+        ts_arr = np.pad(ts_arr, (0, n_ts - ts_arr.shape[0]), mode="constant", constant_values=np.nan)
+    rates = np.reciprocal(ts_arr, where=np.isfinite(ts_arr), out=np.full_like(ts_arr, np.nan))
+    return evals, ts_arr, rates

@@ -489,7 +489,72 @@ def make_macro():
     print("macro:", pops.round(3), Tm.shape, float(mf.max()))
 
 
+def make_ladders():
+    """utils.msm_utils.candidate_lag_ladder (utils/msm_utils.py:21-105), the genuine function, and
+    ITSMixin._deterministic_its_from_counts (_its.py:742-801) run with deeptime's two analysis functions
+    stood in for by their documented numpy definitions (eigenvalues(T, k, reversible=True, mu): eigvalsh of
+    sqrt(mu) T / sqrt(mu), sorted by magnitude; timescales: -tau / ln|ev|, inf where |ev| = 1): everything
+    around those two calls -- symmetrisation, the weights passed as mu, sorting, clipping, padding -- is the
+    reference's own arithmetic."""
+    import importlib.util
+    from unittest import mock
+
+    import scipy.linalg
+
+    def dt_eigenvalues(T, k=None, reversible=False, mu=None, **kw):
+        smu = np.sqrt(mu)
+        S = smu[:, None] * np.asarray(T) / smu
+        ev = scipy.linalg.eigvalsh(S)
+        ev = ev[np.argsort(np.abs(ev))[::-1]]
+        return ev if k is None else ev[:k]
+
+    def dt_timescales(T, tau=1, k=None, reversible=False, mu=None, **kw):
+        ev = dt_eigenvalues(T, k=k, reversible=reversible, mu=mu)
+        ts = np.zeros(len(ev))
+        one = np.isclose(np.abs(ev), 1.0, rtol=0.0, atol=1e-14)
+        ts[one] = np.inf
+        ts[~one] = -1.0 * tau / np.log(np.abs(ev[~one]))
+        return ts
+
+    for name in ("deeptime", "deeptime.markov", "deeptime.markov.msm", "deeptime.markov.tools"):
+        sys.modules[name] = mock.MagicMock(name=name)
+    ana = types.ModuleType("deeptime.markov.tools.analysis")
+    ana.eigenvalues, ana.timescales = dt_eigenvalues, dt_timescales
+    ana.stationary_distribution = mock.MagicMock()
+    sys.modules["deeptime.markov.tools.analysis"] = ana
+    spec = importlib.util.spec_from_file_location("_ref_utils_msm", str(REF / "src/pmarlo/utils/msm_utils.py"))
+    mu_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mu_mod)
+    out = {}
+    args = [(1, 200, None), (1, 100, None), (1, 2000, 7), (5, 500, 4), (1, 2000, 1), (1, 2000, 2), (10, 10, None),
+            (3, 1280, 12), (1, 50, 30)]
+    out["ladder_args"] = np.array([[a, b, -1 if c is None else c] for a, b, c in args], dtype=np.int64)
+    for i, (a, b, c) in enumerate(args):
+        out[f"ladder_{i}"] = np.asarray(mu_mod.candidate_lag_ladder(a, b, c), dtype=np.int64)
+    spec = importlib.util.spec_from_file_location("pmarlo.markov_state_model._its_real",
+                                                  str(REF / "src/pmarlo/markov_state_model/_its.py"))
+    its = importlib.util.module_from_spec(spec)
+    its.__package__ = "pmarlo.markov_state_model"
+    spec.loader.exec_module(its)
+    rng = np.random.default_rng(5)
+    cases = []
+    for K, n_ts in ((6, 3), (40, 5), (3, 5), (25, 0), (12, 4)):
+        C = rng.poisson(3.0, size=(K, K)).astype(float) * (rng.random((K, K)) < 0.5)
+        C += np.diag(rng.poisson(30.0, size=K).astype(float))
+        if K == 12:
+            C[4, :] = 0.0
+            C[:, 4] = 0.0              # an empty state: zero row of T
+        ev, ts, rt = its.ITSMixin._deterministic_its_from_counts(None, 7, C, n_ts)
+        i = len(cases)
+        out[f"det_C_{i}"], out[f"det_ev_{i}"], out[f"det_ts_{i}"], out[f"det_rate_{i}"] = C, ev, ts, rt
+        cases.append((K, n_ts))
+    out["det_cases"] = np.asarray(cases, dtype=np.int64)
+    np.savez_compressed(OUT / "ladders.npz", **out)
+    print("ladders:", [out[f"ladder_{i}"].tolist() for i in (0, 2, 3)], out["det_ts_0"])
+
+
 if __name__ == "__main__":
+    make_ladders()
     make_macro()
     make_ck_selector()
     make_ck()

@@ -26,6 +26,17 @@ def run(name, n, D, K, reps=6, sigma_c=1.0):
         idx = torch.randint(0, K, (n,), generator=g, device=dev)
         Y = cen[idx] + torch.randn((n, D), generator=g, device=dev, dtype=torch.float32)
         C = cen.double().contiguous()
+    elif name == "c4":
+        # trajectory-like rows (AR(1), rho = 0.9995, like the bench's TICA coordinates): neighbouring frames
+        # share their candidate centres, which is what the block screening of the epilogue exploits
+        import bench
+        A = (D + 2) // 3
+        xyz = bench.synth_xyz_device(n // 125_000, 125_000, dev, seed=7, rho=0.9995, sigma=1.0,
+                                     base=torch.zeros((A, 3), device=dev))
+        Y = xyz.reshape(xyz.shape[0], -1)[:, :D].contiguous()
+        del xyz
+        n = int(Y.shape[0])
+        C = Y[torch.randperm(n, generator=g, device=dev)[:K]].double().contiguous()
     else:
         Y = torch.randn((n, D), generator=g, device=dev, dtype=torch.float32)
         C = Y[torch.randperm(n, generator=g, device=dev)[:K]].double().contiguous()
@@ -67,5 +78,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("c4", "all"):
         run("c4", 10_000_000, 10, 1000)
+    if which in ("rand", "all"):
+        run("rand", 10_000_000, 10, 1000)
     if which in ("c5", "all"):
         run("c5", 2_000_000, 64, 5000)
