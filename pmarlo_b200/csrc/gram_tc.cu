@@ -242,42 +242,74 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
     }
   } else {
     // ============================================================ MMA issuer
+    // The issuing warp's own instruction stream sets the pace of the tensor pipe (tools/ubench_mma.cu): the
+    // descriptors of a ring slot differ from those of slot 0 by a constant in the 14-bit address field, so the
+    // ten descriptors of a stage (5 tiles x 2 K steps) are slot base + precomputed offsets, and ONE elected
+    // lane issues the stage's eight MMAs and its commit(s) from a single instruction block.
     const uint32_t idesc = tc::idesc_tf32(128, d, 1, 1);
     const uint32_t base = smem_u32(tiles);
+    const uint64_t d0 = tc::smem_desc(base, lbo, sbo, tc::kLayoutSw128Base32);     // tile `a`, K step 0, slot 0
+    const uint64_t oTh = kGtTileB >> 4, oTl = (2 * kGtTileB) >> 4, oT2a = (3 * kGtTileB) >> 4,
+                   oTwh = (3 * kGtTileB + kGtTileA) >> 4, oK = (2u * sbo) >> 4, oSlot = kGtStageBytes >> 4;
+    const uint32_t bar_empty0 = smem_u32(&B->empty[0]), bar_wdone = smem_u32(&B->wdone);
     int n_windows_done = 0;
+    int slot = 0;
+    uint32_t use = 0;
+    int in_window = 0;   // stages issued in the current window
     for (int s = 0; s < n_stages; ++s) {
-      const int slot = s % kGtStages;
-      const uint32_t use = (uint32_t)(s / kGtStages);
-      const bool window_start = (s % stages_per_window) == 0;
+      const bool window_start = in_window == 0;
       if (window_start && n_windows_done > 0) {
         mbar_wait(&B->drained, (uint32_t)((n_windows_done - 1) & 1));
         tc::fence_after_sync();
       }
       mbar_wait(&B->full[slot], use & 1u);
       tc::fence_after_sync();
-      {
-        const uint32_t T = base + (uint32_t)slot * kGtStageBytes;
-        const uint32_t Ta = T, Th = T + kGtTileB, Tl = T + 2 * kGtTileB, T2a = T + 3 * kGtTileB, Twh = T2a + kGtTileA;
-#pragma unroll
-        for (int ks = 0; ks < kGtBK / 8; ++ks) {
-          const uint32_t off = (uint32_t)ks * 2u * sbo;
-          const uint64_t dA2a = tc::smem_desc(T2a + off, lbo, sbo, tc::kLayoutSw128Base32);
-          const uint64_t dAwh = tc::smem_desc(Twh + off, lbo, sbo, tc::kLayoutSw128Base32);
-          const uint64_t dBa = tc::smem_desc(Ta + off, lbo, sbo, tc::kLayoutSw128Base32);
-          const uint64_t dBh = tc::smem_desc(Th + off, lbo, sbo, tc::kLayoutSw128Base32);
-          const uint64_t dBl = tc::smem_desc(Tl + off, lbo, sbo, tc::kLayoutSw128Base32);
-          const uint32_t acc = (window_start && ks == 0) ? 0u : 1u;
-          tc::mma_tf32_elect(tmem, dA2a, dBa, idesc, acc);
-          tc::mma_tf32_elect(tmem + 256u, dA2a, dBh, idesc, acc);
-          tc::mma_tf32_elect(tmem + 256u, dA2a, dBl, idesc, 1u);
-          tc::mma_tf32_elect(tmem + 256u, dAwh, dBh, idesc, 1u);
-        }
-        tc::mma_commit_elect(&B->empty[slot]);
-        const bool window_end = ((s + 1) % stages_per_window == 0) || (s + 1 == n_stages);
-        if (window_end) tc::mma_commit_elect(&B->wdone);
+      const uint64_t dS = d0 + (uint64_t)slot * oSlot;
+      const bool window_end = (in_window + 1 == stages_per_window) || (s + 1 == n_stages);
+      const uint32_t acc0 = window_start ? 0u : 1u;
+      // K step 0 then K step 1: P += (2wa)^T a ; Q += (2wa)^T r_hi + (2wa)^T r_lo + (w r_hi)^T r_hi
+      asm volatile(
+          "{\n\t"
+          ".reg .pred q, p;\n\t"
+          ".reg .b64 a2, awh, ba, bh, bl;\n\t"
+          "elect.sync _|q, 0xffffffff;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "add.u64 a2, %2, %7;\n\t"        // 2wa
+          "add.u64 awh, %2, %8;\n\t"       // w r_hi
+          "add.u64 bh, %2, %5;\n\t"        // r_hi
+          "add.u64 bl, %2, %6;\n\t"        // r_lo
+          "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], a2, %2, %3, p;\n\t"
+          "@q tcgen05.mma.cta_group::1.kind::tf32 [%1], a2, bh, %3, p;\n\t"
+          "@q tcgen05.mma.cta_group::1.kind::tf32 [%1], a2, bl, %3, 1;\n\t"
+          "@q tcgen05.mma.cta_group::1.kind::tf32 [%1], awh, bh, %3, 1;\n\t"
+          "add.u64 a2, a2, %9;\n\t"
+          "add.u64 awh, awh, %9;\n\t"
+          "add.u64 bh, bh, %9;\n\t"
+          "add.u64 bl, bl, %9;\n\t"
+          "add.u64 ba, %2, %9;\n\t"
+          "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], a2, ba, %3, 1;\n\t"
+          "@q tcgen05.mma.cta_group::1.kind::tf32 [%1], a2, bh, %3, 1;\n\t"
+          "@q tcgen05.mma.cta_group::1.kind::tf32 [%1], a2, bl, %3, 1;\n\t"
+          "@q tcgen05.mma.cta_group::1.kind::tf32 [%1], awh, bh, %3, 1;\n\t"
+          "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+          "}" ::"r"(tmem),
+          "r"(tmem + 256u), "l"(dS), "r"(idesc), "r"(acc0), "l"(oTh), "l"(oTl), "l"(oT2a), "l"(oTwh), "l"(oK),
+          "r"(bar_empty0 + (uint32_t)slot * 8u)
+          : "memory");
+      if (window_end) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+            "}" ::"r"(bar_wdone)
+            : "memory");
+        ++n_windows_done;
+        in_window = 0;
+      } else {
+        ++in_window;
       }
-      __syncwarp();
-      if (((s + 1) % stages_per_window == 0) || (s + 1 == n_stages)) ++n_windows_done;
+      if (++slot == kGtStages) { slot = 0; ++use; }
     }
   }
 
