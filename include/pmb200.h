@@ -188,6 +188,12 @@ PMB_API int pmb_kmeans_tc_scores(const float* Y, int64_t n, int D, int64_t ld, c
 
 /* centres <- sums / counts (empty cluster keeps the old centre), also returns
  * shift2 = sum_k counts_k |new_k - old_k|^2 in out_shift2 (may be NULL). */
+/* Per-sample silhouette coefficients (sklearn.metrics.silhouette_samples, Euclidean) behind the automatic
+ * choice of n_states: `_auto_select_n_states`, markov_state_model/clustering.py:155-250.
+ * Y: n x D fp64 row-major, labels in [0, K), K <= 64, sizes[k] = members of cluster k, out: n fp64. */
+PMB_API int pmb_silhouette_samples(const double* Y, int64_t n, int D, const int32_t* labels, int K,
+                                   const int64_t* sizes, double* out, pmb_stream_t stream);
+
 PMB_API int pmb_kmeans_update(double* centers, const double* sums, const int64_t* counts,
                       int K, int D, double* out_shift2, pmb_stream_t stream);
 

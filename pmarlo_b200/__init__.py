@@ -16,13 +16,15 @@ from .features import compute_features, featurize_trajectory, trig_expand_period
 from .msm import (  # noqa: F401
     build_msm_from_labels,
     build_simple_msm,
+    candidate_lag_ladder,
+    deterministic_its_from_counts,
     check_transition_matrix,
     count_transitions,
     ensure_connected_counts,
     implied_timescales,
     safe_timescales,
 )
-from .reduction import TICA, maybe_apply_tica, reduce_features, tica_reduce  # noqa: F401
+from .reduction import TICA, maybe_apply_tica, reduce_features, tica_reduce, vamp_reduce  # noqa: F401
 from .topology import Topology, Trajectory, load_pdb  # noqa: F401
 
 __version__ = "0.1.0"

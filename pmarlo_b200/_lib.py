@@ -46,6 +46,7 @@ PROTOTYPES = {
     "pmb_debug_trace_tica": (_i32, [_p]),
     "pmb_kmeans_tc_scores": (_i32, [_p, _i64, _i32, _i64, _p, _i32, _p, _p, _p, _sz, _p]),
     "pmb_kmeans_update": (_i32, [_p, _p, _p, _i32, _i32, _p, _p]),
+    "pmb_silhouette_samples": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p]),
     "pmb_count_lagged": (_i32, [_p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "pmb_count_lagged_weighted": (_i32, [_p, _p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "pmb_relabel_compact_ws_bytes": (_sz, [_i64]),

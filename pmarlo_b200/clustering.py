@@ -157,6 +157,56 @@ def kmeans_pp_init(Y: torch.Tensor, K: int, seed: int | None) -> torch.Tensor:
     return centers
 
 
+def silhouette_score_device(Y: torch.Tensor, labels: torch.Tensor, K: int) -> float:
+    """``sklearn.metrics.silhouette_score(Y, labels)`` (Euclidean): mean of the per-sample coefficients,
+    computed by ``pmb_silhouette_samples`` without materialising the n x n distance matrix."""
+    return float(kernels.silhouette_samples(Y, labels, K).mean().item())
+
+
+def auto_select_n_states(Yd: torch.Tensor, random_state: int | None, *, sample_size: int | None = None,
+                         override_n_states: int | None = None, max_iter: int = 500, tolerance: float = 1e-5,
+                         return_scores: bool = False):
+    """``_auto_select_n_states`` (clustering.py:155-250): k-means with k = 4 .. 20 on the (optionally
+    sampled) frames, silhouette score of each labelling, the first maximum wins; returns
+    ``(n_states, rationale)``.  Seeding is k-means++ from ``random_state`` (deeptime draws from its own C++
+    RNG, so the fitted centres -- and hence which k wins on a flat score curve -- are not reproducible across
+    the two implementations; the score of a GIVEN labelling is, to 1e-12)."""
+    if override_n_states is not None:
+        if override_n_states <= 0:
+            raise ValueError(f"override_n_states must be a positive integer; received {override_n_states}.")
+        return int(override_n_states), f"auto-override={override_n_states}"
+    if sample_size is not None:
+        if sample_size <= 1:
+            raise ValueError("sample_size must be greater than 1 when sampling for silhouette scoring.")
+        eff = min(int(sample_size), int(Yd.shape[0]))
+        rng = np.random.default_rng(random_state)
+        idx = rng.choice(int(Yd.shape[0]), size=eff, replace=False)
+        Ys = Yd.index_select(0, torch.from_numpy(idx).to(Yd.device))
+        note = f" sample={eff}"
+    else:
+        Ys, note = Yd, ""
+    Ys = Ys.to(torch.float64).contiguous()
+    scores: list[tuple[int, float]] = []
+    for k in range(4, 21):
+        if k > int(Ys.shape[0]):
+            scores.append((k, -1.0))
+            continue
+        c0 = kmeans_pp_init(Ys, k, random_state)
+        res = lloyd_device(Ys, c0, max_iter=max_iter, tolerance=tolerance)
+        lab = assign_device(Ys, res.centers)
+        if int(torch.unique(lab).numel()) <= 1:
+            score = -1.0
+        else:
+            score = silhouette_score_device(Ys, lab, k)
+        scores.append((k, score))
+    chosen, best = max(scores, key=lambda x: x[1])
+    rationale = f"silhouette={best:.3f}{note}"
+    logger.info("Auto-selected %d states with silhouette score %.3f", chosen, best)
+    if return_scores:
+        return chosen, rationale, scores
+    return chosen, rationale
+
+
 def _validate_kwargs(method: str, kwargs: dict) -> None:
     unsupported = set(kwargs) - set(_SUPPORTED_KWARGS)
     if unsupported:
@@ -190,9 +240,10 @@ def cluster_microstates(Y: np.ndarray, method: Literal["auto", "minibatchkmeans"
 
     Differences that are deliberate and documented in INTEGRATION.md: every
     method runs full-batch Lloyd on the device (``"auto"``/``"minibatchkmeans"`` do
-    not subsample: B200 does a full pass over 10 M frames in milliseconds), and
-    ``n_states="auto"`` needs ``auto_n_states_override`` (silhouette scoring is an
-    O(N^2) CPU routine outside the accelerated path).
+    not subsample: B200 does a full pass over 10 M frames in milliseconds).
+    ``n_states="auto"`` runs the reference's silhouette scan (k = 4 .. 20) with the
+    O(n^2) scoring on the device (``pmb_silhouette_samples``); pass
+    ``silhouette_sample_size`` for large inputs, like the reference.
     """
     Y = np.asarray(Y) if not isinstance(Y, torch.Tensor) else Y
     if Y.shape[0] == 0:
@@ -220,19 +271,17 @@ def cluster_microstates(Y: np.ndarray, method: Literal["auto", "minibatchkmeans"
         raise ValueError(f"Unsupported clustering method: {method}")
     _validate_kwargs(method, kwargs)
     rationale = None
-    if isinstance(n_states, str) and n_states == "auto":
-        if auto_n_states_override is None:
-            raise NotImplementedError(
-                "n_states='auto' (silhouette scan) is outside the B200 hot path; pass "
-                "auto_n_states_override or an integer n_states")
+    auto = isinstance(n_states, str) and n_states == "auto"
+    if auto and auto_n_states_override is not None:
         if auto_n_states_override <= 0:
             raise ValueError("override_n_states must be a positive integer; "
                              f"received {auto_n_states_override}.")
         n_states = int(auto_n_states_override)
         rationale = f"auto-override={n_states}"
-    else:
+        auto = False
+    elif not auto:
         n_states = int(n_states)
-    if n_states <= 0:
+    if not auto and n_states <= 0:
         raise ValueError(f"Number of microstates must be a positive integer; received {n_states}.")
     chosen = method
     if method == "auto":
@@ -255,6 +304,10 @@ def cluster_microstates(Y: np.ndarray, method: Literal["auto", "minibatchkmeans"
     else:
         Yd = torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float64)).to(dev)
     Yd = Yd.contiguous()
+    if auto:
+        # silhouette scan over k = 4 .. 20 (clustering.py:155-250, 555-570)
+        n_states, rationale = auto_select_n_states(Yd, random_state, sample_size=silhouette_sample_size,
+                                                   max_iter=max_iter, tolerance=tolerance)
     logger.info("Starting clustering with %s algorithm: %d states, %d samples, %d features",
                 chosen, n_states, Yd.shape[0], Yd.shape[1])
 

@@ -90,6 +90,40 @@ __device__ void tridiag_bisect(const double* a, const double* b, int m, double* 
   }
 }
 
+// the kk smallest and kk largest eigenvalues of the m x m tridiagonal: out[0..kk) ascending from the bottom,
+// out[kk..2kk) descending from the top (threads 0 .. 2 kk - 1, one eigenvalue each)
+__device__ void tridiag_bisect_extremes(const double* a, const double* b, int m, int kk, double* out) {
+  double lo = 1e300, hi = -1e300;
+  for (int i = 0; i < m; ++i) {
+    const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < m ? fabs(b[i]) : 0.0);
+    lo = fmin(lo, a[i] - r);
+    hi = fmax(hi, a[i] + r);
+  }
+  const double span = fmax(fabs(lo), fabs(hi));
+  const double tiny = 2.3e-308 + 1e-30 * span;
+  lo -= 1e-12 * span + 1e-300;
+  hi += 1e-12 * span + 1e-300;
+  const int t = threadIdx.x;
+  if (t < 2 * kk) {
+    const int idx = t < kk ? t : m - 1 - (t - kk);
+    double v = 0.0;
+    if (idx >= 0 && idx < m) {
+      double l = lo, h = hi;
+      for (int it = 0; it < 200; ++it) {
+        const double mid = 0.5 * (l + h);
+        if (mid <= l || mid >= h) break;
+        if (sturm_count(a, b, m, mid, tiny) > idx) h = mid; else l = mid;
+      }
+      v = 0.5 * (l + h);
+    }
+    out[t] = v;
+  }
+}
+
+constexpr int kLanCheckFrom = 48;    // first convergence checkpoint (Lanczos steps done)
+constexpr int kLanCheckEvery = 16;   // ... and the distance between checkpoints
+constexpr int kLanMaxTop = 32;       // early stopping watches at most this many leading Ritz values
+
 struct LanParams {
   const double* T;
   const double* pi;
@@ -120,6 +154,11 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double s_red[32];
   __shared__ int s_order[1024];
+  // every CTA keeps its own copy of the recurrence (a_j, b_j are the same numbers in every thread of the grid),
+  // so that the convergence checkpoints need no extra grid barrier
+  __shared__ double s_alpha[1024], s_beta[1024];
+  __shared__ double s_ext[2 * kLanMaxTop], s_top[kLanMaxTop], s_top_prev[kLanMaxTop];
+  __shared__ int s_stop;
   const int K = p.K, tid = threadIdx.x, lane = tid & 31;
   const int gtid = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
   const int gwarp = gtid >> 5, nwarps = gthreads >> 5;
@@ -244,8 +283,33 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
     }
     const double b_j = sqrt(grid_sum_partials(p.part, gridDim.x));
     if (gtid == 0) { p.alpha[j] = a_j; p.beta[j] = b_j; }
+    if (tid == 0) { s_alpha[j] = a_j; s_beta[j] = b_j; }
     m_eff = j + 1;
     if (!(b_j > 1e-13) || j + 1 == p.m) break;  // invariant subspace / done (uniform across the grid)
+    // Convergence checkpoint: the k leading (by magnitude) Ritz values of T_{j+1} against those of the previous
+    // checkpoint, 16 steps earlier.  Every CTA evaluates it on its own copy of the recurrence with the same
+    // arithmetic, so the decision is uniform across the grid without a barrier.  (The fixed 200 steps this
+    // replaces cost 5.4 ms for K = 1000; the leading values settle after 60-100.)
+    if (p.k <= kLanMaxTop && 2 * p.k <= m_eff && m_eff >= kLanCheckFrom && (m_eff - kLanCheckFrom) % kLanCheckEvery == 0) {
+      __syncthreads();
+      tridiag_bisect_extremes(s_alpha, s_beta, m_eff, p.k, s_ext);
+      __syncthreads();
+      if (tid == 0) {
+        // merge the two sorted ends by magnitude
+        int lo_i = 0, hi_i = 0, stop = (m_eff > kLanCheckFrom) ? 1 : 0;
+        for (int t = 0; t < p.k; ++t) {
+          const double a_lo = s_ext[lo_i], a_hi = s_ext[p.k + hi_i];
+          double v;
+          if (fabs(a_hi) >= fabs(a_lo)) { v = a_hi; ++hi_i; } else { v = a_lo; ++lo_i; }
+          if (stop && fabs(v - s_top_prev[t]) > 1e-12 * fmax(1.0, fabs(v))) stop = 0;
+          s_top[t] = v;
+        }
+        for (int t = 0; t < p.k; ++t) s_top_prev[t] = s_top[t];
+        s_stop = stop;
+      }
+      __syncthreads();
+      if (s_stop) break;
+    }
     binv = 1.0 / b_j;
     { double* t = w_cur; w_cur = w_new; w_new = t; }
   }

@@ -277,6 +277,20 @@ def kmeans_update(centers: torch.Tensor, sums: torch.Tensor, counts: torch.Tenso
                                        stream_handle(centers.device)), "pmb_kmeans_update")
 
 
+def silhouette_samples(Y: torch.Tensor, labels: torch.Tensor, K: int) -> torch.Tensor:
+    """Per-sample silhouette coefficients (fp64) of a labelling with K <= 64 clusters."""
+    _dev(Y, torch.float64, "Y")
+    if Y.dim() != 2 or not Y.is_contiguous():
+        raise ValueError("Y must be a contiguous (n, D) tensor")
+    n, D = int(Y.shape[0]), int(Y.shape[1])
+    _flat(labels, torch.int32, "labels", numel=n)
+    sizes = torch.bincount(labels.to(torch.int64), minlength=int(K)).to(torch.int64).contiguous()
+    out = torch.empty((n,), dtype=torch.float64, device=Y.device)
+    check(_lib.lib().pmb_silhouette_samples(ptr(Y), n, D, ptr(labels), int(K), ptr(sizes), ptr(out),
+                                            stream_handle(Y.device)), "pmb_silhouette_samples")
+    return out
+
+
 def count_lagged(labels: torch.Tensor, seg_offsets: torch.Tensor, K: int, lag: int, step: int = 1,
                  out: torch.Tensor | None = None) -> torch.Tensor:
     """K7.  Accumulates into ``out`` (K,K) int64 (zero-initialised when None)."""

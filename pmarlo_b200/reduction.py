@@ -287,13 +287,88 @@ def tica_reduce(X: np.ndarray, lag: int = 1, n_components: int = 2, scale: bool 
     return np.asarray(Y.cpu().numpy(), dtype=float)
 
 
+def _spd_inv_split_device(C: torch.Tensor, epsilon: float) -> torch.Tensor:
+    """deeptime ``spd_inv_split`` on a d x d fp64 device matrix: L with L^T C L = I on the retained subspace
+    (eigenvalues sorted by magnitude, |s| <= epsilon dropped, epsilon raised to -min(s) for an indefinite C,
+    largest-magnitude entry of every eigenvector positive)."""
+    s, V = torch.linalg.eigh(C)                       # d x d, cold path: library call
+    order = torch.argsort(s.abs(), descending=True, stable=True)
+    s, V = s[order], V[:, order]
+    eps = float(epsilon)
+    smin = float(s.min().item())
+    if smin < 0:
+        eps = max(eps, -smin + 1e-16)
+    m = int((s.abs() > eps).sum().item())
+    if m == 0:
+        raise ValueError("all eigenvalues below epsilon (zero rank)")
+    V, s = V[:, :m], s[:m]
+    piv = V.abs().argmax(dim=0)
+    sign = torch.where(V[piv, torch.arange(m, device=V.device)] < 0, -1.0, 1.0).to(V.dtype)
+    return (V * sign[None, :]) / torch.sqrt(s)[None, :]
+
+
+def vamp_reduce(X: np.ndarray, lag: int = 1, n_components: int = 2, scale: bool = True,
+                epsilon: float = 1e-6) -> np.ndarray:
+    """Drop-in for ``pmarlo.markov_state_model.reduction.vamp_reduce`` (reduction.py:113-148): ``_preprocess``
+    then deeptime ``VAMP(lagtime, dim, epsilon)`` fit on the one trajectory and ``transform`` of it (the call
+    src/pmarlo/api/conformations.py:195 makes).
+
+    The N d^2 work -- C00, C0t (not symmetrised), Ctt about the separate window means -- is ONE pass of the K3
+    Gram kernel over the stacked pairs Z = [x_t | x_{t+lag}] (N - lag, 2 d): G = sum z z^T with the kernel's
+    conditioning z = (Z - block mean) / std holds all three blocks; the fp32 rounding of the conditioning
+    constants is undone exactly in fp64.  The d x d whitening and the SVD of L0^T C0t Lt are library calls on
+    the device (torch.linalg, cold path); the projection is K5.  Singular-vector signs are LAPACK's choice in
+    the reference; here the largest-magnitude entry of every left singular function is positive."""
+    Xp, _ = _as_2d(X)
+    n, d = int(Xp.shape[0]), int(Xp.shape[1])
+    lag = int(lag)
+    if lag < 1:
+        raise ValueError("lagtime must be >= 1")
+    if n <= lag:
+        raise ValueError("no trajectory longer than the lag time")
+    dev = kernels.require_cuda()
+    Xd = torch.from_numpy(np.ascontiguousarray(Xp, dtype=np.float32)).to(dev)
+    moments = kernels.col_moments(Xd)
+    stats, _ = kernels.scaler_from_moments(moments, n, 1, 1 if scale else 0)
+    mean, std = stats[0].contiguous(), stats[1].contiguous()
+    if bool((moments[0] < n).any().item()):           # mean-impute NaNs exactly like SimpleImputer
+        Xd = torch.where(torch.isnan(Xd), mean.to(torch.float32)[None, :], Xd).contiguous()
+    T = n - lag
+    Z = torch.cat([Xd[:T], Xd[lag:]], dim=1).contiguous()            # the lagged pairs, side by side
+    mz = kernels.col_moments(Z)
+    zmean = mz[1] + mz[2] / torch.clamp(mz[0], min=1.0)              # window means mu_0 | mu_t (raw units)
+    inv_std = (1.0 / std).repeat(2)
+    cond = torch.stack([zmean.to(torch.float32), inv_std.to(torch.float32)]).contiguous()
+    ones = torch.ones((T,), dtype=torch.uint8, device=dev)            # weight 1 for every pair
+    G = kernels.gram(Z, ones, 0, 0, cond)
+    # undo the fp32 rounding of the conditioning constants: z_exact = (z32 - delta) * r
+    r = inv_std / cond[1].to(torch.float64)
+    delta = (zmean - cond[0].to(torch.float64)) * cond[1].to(torch.float64)
+    C = (G - float(T) * torch.outer(delta, delta)) * torch.outer(r, r) / float(T)
+    C00, C0t, Ctt = C[:d, :d], C[:d, d:], C[d:, d:]
+    C00, Ctt = 0.5 * (C00 + C00.T), 0.5 * (Ctt + Ctt.T)
+    L0 = _spd_inv_split_device(C00, epsilon)
+    Lt = _spd_inv_split_device(Ctt, epsilon)
+    W = L0.T @ C0t @ Lt
+    A, sv, _ = torch.linalg.svd(W, full_matrices=False)
+    m = min(int(L0.shape[1]), int(Lt.shape[1]), int(n_components))
+    U = L0 @ A[:, :m]
+    piv = U.abs().argmax(dim=0)
+    U = U * torch.where(U[piv, torch.arange(m, device=dev)] < 0, -1.0, 1.0).to(U.dtype)[None, :]
+    Wp = (U / std[:, None]).contiguous()
+    Y = kernels.project(Xd, zmean[:d].contiguous(), mean, Wp, out_f64=True)
+    return np.asarray(Y.cpu().numpy(), dtype=float)
+
+
 def reduce_features(X: np.ndarray, method: str = "tica", lag: int = 10, n_components: int = 2) -> np.ndarray:
-    """Drop-in for ``pmarlo.api.features.reduce_features`` (TICA branch; PCA / VAMP
-    are outside the north-star path and are not silently emulated)."""
+    """Drop-in for ``pmarlo.api.features.reduce_features`` (api/features.py:468-481): TICA and VAMP on the
+    device; PCA (sklearn) is outside the north-star path and is not silently emulated."""
     if method == "tica":
         return tica_reduce(X, lag=lag, n_components=n_components)
-    if method in ("pca", "vamp"):
-        raise NotImplementedError(f"reduce_features(method={method!r}) is outside the B200 hot path")
+    if method == "vamp":
+        return vamp_reduce(X, lag=lag, n_components=n_components)
+    if method == "pca":
+        raise NotImplementedError("reduce_features(method='pca') is outside the B200 hot path")
     raise ValueError(f"Unknown reduction method: {method}")
 
 

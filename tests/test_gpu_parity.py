@@ -915,3 +915,87 @@ def test_macro_helpers_on_device(golden):
 
     z = golden("macro")
     np.testing.assert_allclose(macro.lump_micro_to_macro_T(z["T"], z["pi"], z["lab"]), z["Tm"], rtol=1e-12)
+
+
+# ----------------------------------------------------------------------------- deterministic ITS fallback (a12)
+def test_deterministic_its_from_counts_matches_reference_golden(golden):
+    """_its.py:742-801 run from the reference file itself (deeptime's two analysis functions stood in for by
+    their numpy definitions, see make_golden.py::make_ladders): eigenvalues, timescales, rates."""
+    from pmarlo_b200 import deterministic_its_from_counts
+
+    z = golden("ladders")
+    for i, (K, n_ts) in enumerate(z["det_cases"]):
+        ev, ts, rates = deterministic_its_from_counts(7, z[f"det_C_{i}"], int(n_ts))
+        assert ev.shape == ts.shape == rates.shape == (int(n_ts),)
+        np.testing.assert_allclose(ev, z[f"det_ev_{i}"], rtol=1e-9, atol=1e-12, err_msg=f"case {i}")
+        np.testing.assert_allclose(ts, z[f"det_ts_{i}"], rtol=1e-7, equal_nan=True, err_msg=f"case {i}")
+        np.testing.assert_allclose(rates, z[f"det_rate_{i}"], rtol=1e-7, equal_nan=True, err_msg=f"case {i}")
+
+
+# ----------------------------------------------------------------------------- VAMP reduction (boundary: reduce_features("vamp"))
+@pytest.mark.parametrize("d,lag,m,scale", [(6, 10, 3, True), (12, 3, 2, False), (40, 5, 8, True)])
+def test_vamp_reduce_vs_oracle(d, lag, m, scale):
+    """reduce_features(X, "vamp", lag, n_components) -- the call api/conformations.py:195 makes -- against the
+    oracle's restatement of deeptime VAMP on the same fp32-representable input."""
+    from pmarlo_b200 import reduce_features, vamp_reduce
+
+    X = np.concatenate(synth.ar1_features(1, 6000, d, seed=d + lag), axis=0).astype(np.float32).astype(np.float64)
+    if d == 12:
+        X[100, 3] = np.nan
+        X[2500, 0] = np.nan
+    got = vamp_reduce(X, lag=lag, n_components=m, scale=scale)
+    ref = oracle.tica.vamp_reduce(X, lag=lag, n_components=m, scale=scale)
+    assert got.shape == ref.shape == (6000, m) and got.dtype == np.float64
+    # singular functions are defined up to the conditioning of the whitening; compare like the TICA projection
+    assert parity.rel_err(got, ref) <= 2e-5, parity.rel_err(got, ref)
+    if scale and lag == 10:
+        np.testing.assert_allclose(reduce_features(X, "vamp", lag=10, n_components=m), got, rtol=0, atol=0)
+    with pytest.raises(ValueError):
+        vamp_reduce(X[:3], lag=5)
+
+
+# ----------------------------------------------------------------------------- silhouette / n_states="auto" (a6)
+@pytest.mark.parametrize("n,D,K", [(700, 2, 4), (3000, 5, 11), (1500, 10, 20), (130, 3, 7)])
+def test_silhouette_samples_match_sklearn(n, D, K):
+    from sklearn.metrics import silhouette_samples, silhouette_score
+
+    from pmarlo_b200 import kernels
+    from pmarlo_b200.clustering import silhouette_score_device
+
+    rng = np.random.default_rng(n + D)
+    cen = rng.normal(scale=3.0, size=(K, D))
+    lab = rng.integers(0, K, size=n)
+    lab[:K] = np.arange(K)
+    if n == 130:
+        lab[lab == 3] = 2
+        lab[0] = 3                     # a singleton cluster: coefficient 0
+    Y = cen[lab] + rng.normal(size=(n, D))
+    Yd = torch.from_numpy(Y).cuda()
+    ld = torch.from_numpy(lab.astype(np.int32)).cuda()
+    got = kernels.silhouette_samples(Yd, ld, K).cpu().numpy()
+    ref = silhouette_samples(Y, lab)
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12)
+    assert abs(silhouette_score_device(Yd, ld, K) - silhouette_score(Y, lab)) <= 1e-12
+
+
+def test_cluster_microstates_auto_n_states():
+    """n_states="auto": the silhouette scan picks the planted number of well-separated clusters; the scores it
+    used are sklearn's for the labellings it produced."""
+    from pmarlo_b200 import cluster_microstates
+    from pmarlo_b200.clustering import auto_select_n_states
+
+    rng = np.random.default_rng(4)
+    cen = np.array([[0, 0], [10, 0], [0, 10], [10, 10], [5, 20], [20, 5]], dtype=float)
+    Y = np.concatenate([c + 0.4 * rng.normal(size=(400, 2)) for c in cen])
+    res = cluster_microstates(Y, method="kmeans", n_states="auto", random_state=7)
+    assert res.n_states == 6 and res.rationale.startswith("silhouette=")
+    assert np.unique(res.labels).size == 6
+    chosen, rationale, scores = auto_select_n_states(torch.from_numpy(Y).cuda(), 7, return_scores=True)
+    assert chosen == 6 and [k for k, _ in scores] == list(range(4, 21))
+    assert max(scores, key=lambda x: x[1])[0] == 6
+    sub = cluster_microstates(Y, method="kmeans", n_states="auto", random_state=7, silhouette_sample_size=500)
+    assert sub.rationale.endswith("sample=500") and sub.n_states == 6
+    over = cluster_microstates(Y, n_states="auto", auto_n_states_override=9)
+    assert over.n_states == 9 and over.rationale == "auto-override=9"
+    with pytest.raises(ValueError):
+        cluster_microstates(Y, n_states="auto", silhouette_sample_size=1)

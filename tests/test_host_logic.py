@@ -432,3 +432,17 @@ def test_numpy_models_of_two_kernel_algorithms():
         assert abs(xn @ yn) <= 1e-12 * np.sqrt(a * b)
         assert abs(c * c + s * s - 1.0) < 1e-15
         np.testing.assert_allclose([xn @ xn, yn @ yn], [a - t * g, b + t * g], rtol=1e-9)
+
+
+def test_candidate_lag_ladder_matches_reference_golden(golden):
+    """utils/msm_utils.py:21-105 -- outputs of the genuine reference function (tests/golden/make_golden.py::make_ladders)."""
+    from pmarlo_b200 import candidate_lag_ladder
+
+    z = golden("ladders")
+    for i, (a, b, c) in enumerate(z["ladder_args"]):
+        got = candidate_lag_ladder(int(a), int(b), None if c < 0 else int(c))
+        assert got == [int(v) for v in z[f"ladder_{i}"]], (a, b, c)
+    assert candidate_lag_ladder() == [1, 2, 3, 5, 8, 10, 15, 20, 30, 40, 50, 75, 80, 100, 150, 160, 200]
+    for bad in ((0, 10, None), (5, 4, None), (1, 10, 0), (2001, 3000, None)):
+        with pytest.raises(ValueError):
+            candidate_lag_ladder(*bad)

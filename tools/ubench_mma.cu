@@ -75,16 +75,22 @@ __global__ void __launch_bounds__(128) mma_rate(int N, int ksteps, int tiles, in
   const uint32_t tmem = slot;
   if (warp == 0) {
     // idesc: D = F32; tf32: A/B format 2; f16: format 0; K-major both
-    const uint32_t idesc = (1u << 4) | (KIND == 0 ? ((2u << 7) | (2u << 10)) : 0u) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t lbo = layout == 0 ? 128u : 0u, sbo = layout == 0 ? (uint32_t)ksteps * 256u : 1024u;
+    // layouts 11 / 12: MN-major operands (tf32: 128B swizzle with 32B base, atoms of 4 k-rows; 16-bit: 128B swizzle,
+    // atoms of 8 k-rows), atoms contiguous along K -- the Gram kernel's operand layouts
+    const bool mn = layout >= 10;
+    const uint32_t idesc = (1u << 4) | (KIND == 0 ? ((2u << 7) | (2u << 10)) : ((1u << 7) | (1u << 10))) | (mn ? (3u << 15) : 0u) |
+                           ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t lbo = layout == 0 ? 128u : (layout == 11 ? (uint32_t)ksteps * 8u * 128u : (layout == 12 ? (uint32_t)ksteps * 2u * 1024u : 0u));
+    const uint32_t sbo = layout == 0 ? (uint32_t)ksteps * 256u : (layout == 11 ? 512u : 1024u);
+    const uint64_t ltype = layout == 11 ? 1ull : (layout == 12 ? 2ull : (uint64_t)layout);
     const uint32_t aA = smem_u32(base), aB = aA + 64 * 1024;
     uint32_t phase = 0;
     const long long t0 = clock64();
     for (int t = 0; t < tiles; ++t) {
       const uint32_t d = tmem + (uint32_t)((t % nbuf) * N);
       for (int s = 0; s < ksteps; ++s) {
-        const uint32_t step = layout == 0 ? (uint32_t)s * 256u : (uint32_t)s * 32u;
-        mma<KIND>(d, smem_desc(aA + step, lbo, sbo, (uint64_t)layout), smem_desc(aB + step, lbo, sbo, (uint64_t)layout), idesc, (s > 0) || always_acc);
+        const uint32_t step = layout == 0 ? (uint32_t)s * 256u : (layout == 11 ? (uint32_t)s * 1024u : (layout == 12 ? (uint32_t)s * 2048u : (uint32_t)s * 32u));
+        mma<KIND>(d, smem_desc(aA + step, lbo, sbo, ltype), smem_desc(aB + step, lbo, sbo, ltype), idesc, (s > 0) || always_acc);
       }
       if ((t + 1) % commit_every == 0) {
         commit(&bar);
@@ -290,6 +296,27 @@ int main() {
     }
   }
   if (getenv("UB_RING_ONLY")) return 0;
+  if (getenv("UB_MN_ONLY")) {
+    struct CfgM { int kind, N, ksteps, layout; };
+    const CfgM cm[] = {{0, 256, 16, 0}, {0, 256, 16, 11}, {0, 128, 16, 11}, {1, 256, 16, 0}, {1, 256, 16, 12}, {1, 128, 16, 12}, {0, 256, 8, 11}, {1, 256, 8, 12}};
+    for (const CfgM& c : cm) {
+      const int tiles = 1024;
+      for (int rep = 0; rep < 2; ++rep) {
+        if (c.kind == 0) mma_rate<0><<<148, 128, smem>>>(c.N, c.ksteps, tiles, 2, 1, 0, c.layout, 0, cyc);
+        else mma_rate<1><<<148, 128, smem>>>(c.N, c.ksteps, tiles, 2, 1, 0, c.layout, 0, cyc);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("mn error: %s\n", cudaGetErrorString(e)); return 1; }
+      }
+      long long h[148];
+      cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+      double mean = 0;
+      for (int i = 0; i < 148; ++i) mean += (double)h[i];
+      mean /= 148;
+      printf("kind=%s N=%d ksteps=%d layout=%d (%s): %.1f cycles/MMA\n", c.kind == 0 ? "tf32" : "bf16", c.N, c.ksteps, c.layout,
+             c.layout >= 10 ? "MN-major" : "K-major", mean / ((double)tiles * c.ksteps));
+    }
+    return 0;
+  }
   struct Cfg { int kind, N, ksteps, nbuf, commit_every, wait, layout, always_acc; };
   const Cfg cfgs[] = {
       {0, 256, 4, 2, 1, 0, 0}, {0, 256, 16, 2, 1, 0, 0}, {0, 256, 4, 2, 1, 1, 0}, {0, 128, 4, 4, 1, 0, 0},
