@@ -547,7 +547,8 @@ def gpu_arm(args):
         "stages_ms": stages, "kmeans_iters_run": int(res.kmeans_iters),
         "tica_rank_sweeps": [int(v) for v in res.tica.rank_dev.tolist()],
         "mle_phase_cycles": debug_counters(), "kmeans_role_cycles": kmeans_debug_counters(), "tica_phase_cycles": tica_debug_counters(),
-        "mle_iters": int(res.mle_info[0].item()), "timescales": [None if not np.isfinite(t) else float(t)
+        "mle_iters": int(res.mle_info[0].item()), "lanczos_steps": int(res.extra["eig_info"].reshape(-1)[0].item()),
+        "timescales": [None if not np.isfinite(t) else float(t)
                                                                 for t in (res.timescales if res.timescales is not None else [])],
     }
     print(json.dumps(line))

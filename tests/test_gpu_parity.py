@@ -946,8 +946,19 @@ def test_vamp_reduce_vs_oracle(d, lag, m, scale):
     got = vamp_reduce(X, lag=lag, n_components=m, scale=scale)
     ref = oracle.tica.vamp_reduce(X, lag=lag, n_components=m, scale=scale)
     assert got.shape == ref.shape == (6000, m) and got.dtype == np.float64
-    # singular functions are defined up to the conditioning of the whitening; compare like the TICA projection
-    assert parity.rel_err(got, ref) <= 2e-5, parity.rel_err(got, ref)
+    # singular functions inherit the covariance error (fp32 products with fp64 folds, ~1e-7) amplified by
+    # cond(C00) / singular-value gap, like the TICA projection in parity.check_tica
+    Xp = oracle.tica.preprocess(X, scale=scale)
+    _, _, sv, _, _, (C00, _, _) = oracle.tica.vamp_fit([Xp], lag, m, 1e-6)
+    gap = float(np.min(np.abs(np.diff(sv[: m + 1])))) if sv.size > m else float(np.min(np.abs(np.diff(sv[:m]))))
+    s00 = np.linalg.eigvalsh(C00)
+    cond = float(s00.max() / max(s00[s00 > 1e-6].min(), 1e-6))
+    tol = min(2e-3, max(2e-5, 4.0 * 2e-7 * cond / max(gap, 1e-12)))
+    assert parity.rel_err(got, ref) <= tol, (parity.rel_err(got, ref), tol, cond, gap)
+    # basis-independent check: the projected coordinates are whitened exactly like the oracle's
+    cg = np.cov(got.T, bias=True) if m > 1 else np.array([[np.var(got)]])
+    cr = np.cov(ref.T, bias=True) if m > 1 else np.array([[np.var(ref)]])
+    assert float(np.max(np.abs(cg - cr))) <= 1e-4
     if scale and lag == 10:
         np.testing.assert_allclose(reduce_features(X, "vamp", lag=10, n_components=m), got, rtol=0, atol=0)
     with pytest.raises(ValueError):
