@@ -367,8 +367,21 @@ def multi_rank_parity(comm, device, rank, world, plan):
             a, b = a.double(), b.double()
             return float((a - b).abs().max().item() / max(float(b.abs().max().item()), 1e-300))
 
+        # fp64 reference of the symmetrised covariances on the concatenated shards (torch.matmul, test arithmetic)
+        F = one.features.to(torch.float64)
+        mu_all, sd_all = F.mean(dim=0), F.std(dim=0, unbiased=False)
+        Zs = (F - mu_all) / torch.where(sd_all > 0, sd_all, torch.ones_like(sd_all))
+        Zt = Zs.view(n_traj * world, fpt, -1)
+        X0, Xt = Zt[:, :-cfg.tica_lag].reshape(-1, Zs.shape[1]), Zt[:, cfg.tica_lag:].reshape(-1, Zs.shape[1])
+        mu = 0.5 * (X0.mean(dim=0) + Xt.mean(dim=0))
+        X0c, Xtc = X0 - mu, Xt - mu
+        Tn = float(X0.shape[0])
+        C00_ref = (X0c.T @ X0c + Xtc.T @ Xtc) / (2 * Tn)
+        C0t_ref = (X0c.T @ Xtc + Xtc.T @ X0c) / (2 * Tn)
         rec = {
             "ranks": world, "frames": int(X1.shape[0]), "n_states": K,
+            "C00_rel_vs_fp64": {"n_rank": rel(res.tica.C00, C00_ref), "one_rank": rel(one.tica.C00, C00_ref)},
+            "C0t_rel_vs_fp64": {"n_rank": rel(res.tica.C0t, C0t_ref), "one_rank": rel(one.tica.C0t, C0t_ref)},
             "counts_equal_given_labels": bool(torch.equal(C_given, res.counts)),
             "labels_mismatch": int((labN != one.labels).sum().item()),
             "counts_equal": bool(torch.equal(one.counts, res.counts)),

@@ -245,6 +245,15 @@ PMB_API int pmb_tc_selftest_raw(const void* Aimg, uint32_t a_bytes, const void* 
                                 int nsteps, uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t step_a,
                                 uint32_t step_b, uint32_t idesc, int kind, float* D, pmb_stream_t stream);
 
+/* ---- Bayesian MSM: Gibbs sampler of reversible transition matrices ----------------
+ * Replaces deeptime BayesianMSM(lagtime, n_samples).fit(dtrajs) / TransitionMatrixSampler(reversible=True)
+ * (_its.py:272-357, 670-740).  C: batch x K x K counts (fp64, zero rows / columns outside the connected set),
+ * X: batch x K x K, in = diag(pi) T of the reversible MLE, out = final chain state; Tout: batch x n_samples x K x K
+ * transition-matrix samples (identity rows for states without counts), pi_out: batch x n_samples x K their
+ * stationary vectors (may be NULL).  One CTA per chain; n_steps Gibbs sweeps per sample (deeptime: sqrt(K)). */
+PMB_API int pmb_bayes_rev_sample(const double* C, double* X, int K, int batch, int n_samples, int n_steps,
+                                 uint64_t seed, double* Tout, double* pi_out, pmb_stream_t stream);
+
 /* ---- K8 reversible maximum-likelihood MSM -----------------------------------------
  * Replaces deeptime MaximumLikelihoodMSM(reversible=True).fit(counts)
  * (_msm_utils.py:255-261, ck_its_selector.py:397-399): fixed point on the

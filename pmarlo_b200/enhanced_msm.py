@@ -32,6 +32,7 @@ import torch
 from . import kernels
 from .msm import (NUMERIC_DIRICHLET_ALPHA, NUMERIC_MIN_POSITIVE, count_transitions, ensure_connected_counts,
                   implied_timescales, infer_n_states)
+from .msm import safe_timescales as safe_timescales_np
 
 logger = logging.getLogger("pmarlo")
 
@@ -152,8 +153,16 @@ class EnhancedMSM:
     def compute_implied_timescales(self, lag_times: Optional[List[int]] = None, n_timescales: int = 5, *,
                                    n_samples: int = 100, ci: float = 0.95,
                                    dirichlet_alpha: float = NUMERIC_DIRICHLET_ALPHA,
-                                   plateau_m: int | None = None, plateau_epsilon: float = 0.1) -> None:
-        del n_samples, ci, dirichlet_alpha        # Bayesian sampling parameters: see the module docstring
+                                   plateau_m: int | None = None, plateau_epsilon: float = 0.1,
+                                   estimator: str = "bayesian") -> None:
+        """``ITSMixin.compute_implied_timescales`` (_its.py:137-192).  ``estimator="bayesian"`` (the reference's
+        behaviour): per lag ``n_samples`` reversible transition matrices from the device Gibbs sampler, medians and
+        ``ci`` percentiles of eigenvalues / timescales / rates, lags without any finite timescale filled by
+        ``_deterministic_its_from_counts`` (:403-423).  ``estimator="mle"`` (extension, also used when
+        ``n_samples <= 0``): the deterministic reversible maximum-likelihood sweep of ck_its_selector.py:397-399,
+        CI fields NaN."""
+        if estimator not in ("bayesian", "mle"):
+            raise ValueError(f"unknown estimator {estimator!r}")
         lags = list(DEFAULT_ITS_LAGS) if lag_times is None else [int(max(1, v)) for v in lag_times]
         if not self.dtrajs:
             logger.warning("No trajectories available for implied timescales")
@@ -174,18 +183,82 @@ class EnhancedMSM:
         eff = getattr(self, "effective_frames", None)
         if eff is not None and eff > 0 and max(lags) >= eff:
             raise ValueError(f"Maximum lag {max(lags)} exceeds available effective frames {eff}")
-        sweep = implied_timescales(self.dtrajs, lags, n_states=self.n_states, n_timescales=n_timescales)
-        ts = sweep.timescales
-        ev = np.full((len(lags), n_timescales), np.nan)
-        ev[:, : max(0, sweep.eigenvalues.shape[1] - 1)] = sweep.eigenvalues[:, 1 : 1 + n_timescales]
-        ev = np.where(np.isfinite(ev), np.clip(np.abs(ev), NUMERIC_MIN_POSITIVE, 1.0 - NUMERIC_MIN_POSITIVE), ev)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            rates = np.where(np.isfinite(ts), 1.0 / ts, np.nan)
-        nan_ci = np.full((len(lags), n_timescales, 2), np.nan)
-        result = ITSResultCI(np.asarray(lags, dtype=int), ev, nan_ci.copy(), ts, nan_ci.copy(), rates, nan_ci.copy())
+        if estimator == "bayesian" and int(n_samples) > 0:
+            from .bayes import bayesian_implied_timescales
+            from .msm import deterministic_its_from_counts
+
+            logger.info("Computing implied timescales with Bayesian estimation")
+            if "effective" not in str(self.count_mode).lower():
+                logger.warning("Bayesian MSM confidence sampling expects effective counts; continuing with "
+                               "count_mode='%s' may yield correlated samples.", self.count_mode)
+            b = bayesian_implied_timescales(self.dtrajs, lags, n_states=self.n_states, n_timescales=n_timescales,
+                                            n_samples=int(n_samples), ci=float(ci),
+                                            seed=getattr(self, "random_state", None))
+            result = ITSResultCI(np.asarray(lags, dtype=int), b.eigenvalues, b.eigenvalues_ci, b.timescales,
+                                 b.timescales_ci, b.rates, b.rates_ci)
+            for i, lag in enumerate(lags):                   # _its_fill_missing_timescales
+                if np.any(np.isfinite(result.timescales[i])):
+                    continue
+                C = count_transitions(self.dtrajs, self.n_states, lag)
+                cc = ensure_connected_counts(C, alpha=dirichlet_alpha)
+                if cc.counts.size == 0:
+                    raise RuntimeError(f"Transition counts empty for lag {lag}")
+                ev_d, ts_d, rate_d = deterministic_its_from_counts(int(lag), cc.counts, n_timescales)
+                result.eigenvalues[i], result.timescales[i], result.rates[i] = ev_d, ts_d, rate_d
+            ts = result.timescales
+        else:
+            sweep = implied_timescales(self.dtrajs, lags, n_states=self.n_states, n_timescales=n_timescales)
+            ts = sweep.timescales
+            ev = np.full((len(lags), n_timescales), np.nan)
+            ev[:, : max(0, sweep.eigenvalues.shape[1] - 1)] = sweep.eigenvalues[:, 1 : 1 + n_timescales]
+            ev = np.where(np.isfinite(ev), np.clip(np.abs(ev), NUMERIC_MIN_POSITIVE, 1.0 - NUMERIC_MIN_POSITIVE), ev)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rates = np.where(np.isfinite(ts), 1.0 / ts, np.nan)
+            nan_ci = np.full((len(lags), n_timescales, 2), np.nan)
+            result = ITSResultCI(np.asarray(lags, dtype=int), ev, nan_ci.copy(), ts, nan_ci.copy(), rates, nan_ci.copy())
         if plateau_m is not None:
             result.recommended_lag_window = _plateau_window(lags, ts, int(plateau_m), float(plateau_epsilon))
         self.implied_timescales = result
+
+    def sample_bayesian_timescales(self, n_samples: int = 200, count_mode: str = "effective"):
+        """``ITSMixin.sample_bayesian_timescales`` (_its.py:670-740): timescale and population samples of the
+        reversible posterior at ``self.lag_time``.  ``count_mode="effective"`` (deeptime's statistically
+        uncorrelated counts) is not offered: sliding counts are used and the samples are narrower than deeptime's,
+        which is logged."""
+        from .bayes import sample_reversible_matrices
+        from .msm import largest_connected_set
+
+        if not self.dtrajs:
+            return None
+        if "effective" in str(count_mode).lower():
+            logger.warning("count_mode='effective' is not available on the device path; using sliding counts")
+        lag = int(max(1, self.lag_time))
+        C = count_transitions(self.dtrajs, self.n_states, lag)
+        lcs = largest_connected_set(C)
+        if lcs.size < 2:
+            return None
+        dev = kernels.require_cuda()
+        act = np.zeros((1, C.shape[0]), dtype=np.uint8)
+        act[0, lcs] = 1
+        Ts, pis, _, _ = sample_reversible_matrices(torch.from_numpy(np.asarray(C, dtype=np.float64)).to(dev),
+                                                   torch.from_numpy(act).to(dev), int(max(1, n_samples)),
+                                                   seed=int(getattr(self, "random_state", None) or 0))
+        K = int(C.shape[0])
+        k = min(6, int(lcs.size))
+        ev, _ = kernels.eig_rev_topk(Ts.reshape(-1, K, K), pis.reshape(-1, K), k)
+        evh = -np.sort(-ev.cpu().numpy(), axis=1)
+        ts_list = []
+        for row in evh:
+            ts = safe_timescales_np(lag, row[1:k])
+            ts = ts[np.isfinite(ts)]
+            if ts.size:
+                ts_list.append(ts)
+        out = {}
+        if ts_list:
+            m = max(a.shape[0] for a in ts_list)
+            out["timescales_samples"] = np.vstack([np.pad(a, (0, m - a.shape[0]), constant_values=np.nan) for a in ts_list])
+        out["population_samples"] = pis[0].cpu().numpy()
+        return out
 
 
 def _ck_methods():

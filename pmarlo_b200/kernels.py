@@ -383,6 +383,26 @@ def mle_rev(C: torch.Tensor, active: torch.Tensor | None = None, alpha: float = 
     return T, pi, info
 
 
+def bayes_rev_sample(C: torch.Tensor, T_mle: torch.Tensor, pi: torch.Tensor, n_samples: int, n_steps: int | None = None,
+                     seed: int = 0) -> torch.Tensor:
+    """Reversible transition-matrix samples (B, n_samples, K, K) and their stationary vectors (B, n_samples, K)
+    from counts C (B,K,K) fp64, started at the
+    reversible MLE (T_mle, pi).  n_steps Gibbs sweeps per sample (default sqrt(K), like deeptime)."""
+    _dev(C, torch.float64, "C")
+    _dev(T_mle, torch.float64, "T_mle")
+    _dev(pi, torch.float64, "pi")
+    Cb = (C.unsqueeze(0) if C.dim() == 2 else C).contiguous()
+    B, K = int(Cb.shape[0]), int(Cb.shape[1])
+    X = (pi.reshape(B, K, 1) * T_mle.reshape(B, K, K)).contiguous()
+    if n_steps is None:
+        n_steps = max(1, int(np.sqrt(K)))
+    out = torch.empty((B, int(n_samples), K, K), dtype=torch.float64, device=C.device)
+    pis = torch.empty((B, int(n_samples), K), dtype=torch.float64, device=C.device)
+    check(_lib.lib().pmb_bayes_rev_sample(ptr(Cb), ptr(X), K, B, int(n_samples), int(n_steps), int(seed) & (2**64 - 1),
+                                          ptr(out), ptr(pis), stream_handle(C.device)), "pmb_bayes_rev_sample")
+    return out, pis
+
+
 def eig_rev_topk(T: torch.Tensor, pi: torch.Tensor, k: int, max_steps: int = 0):
     """K9.  Leading k eigenvalues (by magnitude) of reversible T; batched like mle_rev."""
     _dev(T, torch.float64, "T")

@@ -552,7 +552,55 @@ def make_ladders():
     print("ladders:", [out[f"ladder_{i}"].tolist() for i in (0, 2, 3)], out["det_ts_0"])
 
 
+def make_its_stats():
+    """ITSMixin._summarize_its_stats (_its.py:543-668) run from the reference file on seeded reversible
+    transition-matrix samples; deeptime's ``eigenvalues(T, k)`` / ``stationary_distribution`` are stood in for
+    by their numpy definitions (eigvals sorted by magnitude; the left Perron vector)."""
+    import importlib.util
+    from unittest import mock
+
+    sys.path.insert(0, str(OUT.parents[1]))
+    import oracle
+
+    def dt_eigenvalues(T, k=None, **kw):
+        ev = np.linalg.eigvals(np.asarray(T))
+        ev = ev[np.argsort(np.abs(ev))[::-1]]
+        return ev if k is None else ev[:k]
+
+    def dt_stationary(T, check_inputs=True):
+        w, v = np.linalg.eig(np.asarray(T).T)
+        p = np.abs(np.real(v[:, np.argmax(np.real(w))]))
+        return p / p.sum()
+
+    for name in ("deeptime", "deeptime.markov", "deeptime.markov.msm", "deeptime.markov.tools"):
+        sys.modules[name] = mock.MagicMock(name=name)
+    ana = mock.MagicMock(name="deeptime.markov.tools.analysis")
+    ana.eigenvalues, ana.stationary_distribution = dt_eigenvalues, dt_stationary
+    sys.modules["deeptime.markov.tools.analysis"] = ana
+    spec = importlib.util.spec_from_file_location("pmarlo.markov_state_model._its_real2",
+                                                  str(REF / "src/pmarlo/markov_state_model/_its.py"))
+    its = importlib.util.module_from_spec(spec)
+    its.__package__ = "pmarlo.markov_state_model"
+    spec.loader.exec_module(its)
+    rng = np.random.default_rng(11)
+    out, cases = {}, []
+    for K, n_ts, lag in ((5, 3, 4), (4, 6, 10), (8, 5, 1)):
+        C = rng.poisson(4.0, size=(K, K)).astype(float) + np.diag(rng.poisson(60.0, size=K).astype(float))
+        T0, pi0, _ = oracle.msm.mle_rev(C)
+        Ts, pis = oracle.bayes.sample_reversible(C, T0, pi0, 40, seed=K)
+        st = its.ITSMixin._summarize_its_stats(None, lag, Ts, n_ts, 2.5, 97.5)
+        i = len(cases)
+        out[f"T_{i}"], out[f"pi_{i}"] = Ts, pis
+        for j, v in enumerate(st):
+            out[f"stat_{i}_{j}"] = np.asarray(v, dtype=float)
+        cases.append((K, n_ts, lag))
+    out["cases"] = np.asarray(cases, dtype=np.int64)
+    np.savez_compressed(OUT / "its_stats.npz", **out)
+    print("its_stats:", out["stat_0_3"], out["stat_1_3"])
+
+
 if __name__ == "__main__":
+    make_its_stats()
     make_ladders()
     make_macro()
     make_ck_selector()

@@ -791,7 +791,7 @@ def test_enhanced_msm_build_and_its_match_oracle():
     assert m.stationary_distribution[3] == 0.0 and m.transition_matrix[4, 4] == 1.0
     assert m.free_energies.min() == 0.0
     # ITS: per-lag reversible MLE on the largest connected set (ck_its_selector.py:397-399)
-    m.compute_implied_timescales([1, 2, 4, 8, 100000], n_timescales=2, plateau_m=2, plateau_epsilon=0.5)
+    m.compute_implied_timescales([1, 2, 4, 8, 100000], n_timescales=2, plateau_m=2, plateau_epsilon=0.5, estimator="mle")
     its = m.implied_timescales
     np.testing.assert_array_equal(its.lag_times, [1, 2, 4, 8])
     ref = oracle.msm.its_rev_mle(dtrajs, 5, [1, 2, 4, 8], 2)

@@ -95,3 +95,22 @@ def test_oracle_chain_runs_and_is_consistent():
     r2 = oracle.pipeline.run_chain([f[:, :2] for f in feats], tica_dim=0, n_states=10, init_rows=np.arange(10),
                                    kmeans_iters=3, kmeans_tolerance=None, msm_lag=2, n_timescales=2)
     assert r2.tica is None and r2.Y.shape == (9000, 2)
+
+
+def test_oracle_its_summary_matches_reference_golden(golden):
+    """oracle.bayes.summarize_its_stats against _its.py:543-668 run from the reference file (its_stats.npz)."""
+    z = golden("its_stats")
+    for i, (K, n_ts, lag) in enumerate(z["cases"]):
+        st = oracle.bayes.summarize_its_stats(int(lag), z[f"T_{i}"], int(n_ts), 2.5, 97.5)
+        for j in range(9):
+            np.testing.assert_allclose(st[j], z[f"stat_{i}_{j}"], rtol=1e-12, equal_nan=True)
+
+
+def test_oracle_sampler_invariants():
+    C = np.array([[50, 5, 1], [6, 80, 4], [2, 3, 30]], float)
+    T0, pi0, _ = oracle.msm.mle_rev(C)
+    Ts, pis = oracle.bayes.sample_reversible(C, T0, pi0, 300, seed=1)
+    F = pis[:, :, None] * Ts
+    assert np.max(np.abs(F - F.transpose(0, 2, 1))) < 1e-15
+    np.testing.assert_allclose(Ts.sum(axis=2), 1.0, atol=1e-12)
+    assert np.max(np.abs(Ts.mean(axis=0) - T0)) < 0.02
