@@ -5,7 +5,8 @@
   the algorithm of Trendelkamp-Schroer, Wu, Paul, Noe, J. Chem. Phys. 143, 174101 (2015)) as driven by
   ``BayesianMSM(lagtime, n_samples).fit`` at src/pmarlo/markov_state_model/_its.py:289-310: sequential scan over
   the lower triangle, Beta update of the diagonal, Gamma-proposal + log-normal random-walk Metropolis updates of
-  the off-diagonal elements, ``-1`` prior, X normalised after every sweep, n_steps = sqrt(K) sweeps per sample.
+  the off-diagonal elements, ``-1`` prior, row sums recomputed and X normalised at every sweep, n_steps = sqrt(K)
+  sweeps per sample.
   deeptime is absent from this image: PARITY UNPINNED against its binary (and a sampler can only be compared
   in distribution anyway).  The device sampler visits the same conditionals in a round-robin order; the two are
   compared statistically (tests/test_gpu_bayes.py).

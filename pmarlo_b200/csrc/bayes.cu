@@ -141,6 +141,17 @@ __global__ void __launch_bounds__(kBayesThreads) bayes_rev_sampler_kernel(const 
   const int Kp = (K + 1) & ~1;          // even number of players; player K (if any) is a bye
   for (int smp = 0; smp < n_samples; ++smp) {
     for (int step = 0; step < n_steps; ++step) {
+      // Row sums from X itself at the start of EVERY sweep, like the reference sampler.  Carrying them
+      // incrementally is algebraically exact but numerically unstable: the absolute rounding error of x_i is
+      // invariant under the updates while the normalisation rescales it by 1 / total, and E[log(1 / total)] > 0
+      // (Jensen) -- the relative error performs a multiplicative random walk with positive drift.
+      for (int i = tid >> 5; i < K; i += kBayesThreads / 32) {
+        double sx = 0.0;
+        for (int j = lane; j < K; j += 32) sx += Xc[(size_t)i * K + j];
+        sx = warp_sum(sx);
+        if (lane == 0) sumX[i] = sx;
+      }
+      __syncthreads();
       // ---- diagonal elements: independent of each other
       for (int i = tid; i < K; i += kBayesThreads) {
         const double cii = Cc[(size_t)i * K + i], rest_c = sumC[i] - cii;
