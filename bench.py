@@ -664,6 +664,112 @@ PARITY_NOTE = ("partial: integer stages (labels given centres, counts) bit-exact
                "which is unpinned against deeptime/mdtraj binaries (absent from the image)")
 
 
+# ----------------------------------------------------------------------------- config C5 (large-state stress)
+def synth_c5_device(n_traj, frames_per_traj, D, K, device, seed, hop=1e-3, sigma_c=5.0, chunk_traj=40):
+    """Y = 64-dim mixture around K seeded centres (sigma 5), unit noise, a trajectory hops to a
+    new random centre with probability 1e-3 per frame.  Returns (Y (N, D) float32, true centres (K, D))."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    cen = sigma_c * torch.randn((K, D), generator=g, device=device, dtype=torch.float32)
+    Y = torch.empty((n_traj * frames_per_traj, D), dtype=torch.float32, device=device)
+    for t0 in range(0, n_traj, chunk_traj):
+        nt = min(chunk_traj, n_traj - t0)
+        hops = torch.rand((nt, frames_per_traj), generator=g, device=device) < hop
+        hops[:, 0] = True
+        seg = torch.cumsum(hops.to(torch.int32), dim=1) - 1                      # segment number inside the trajectory
+        seg_cen = torch.randint(0, K, (nt, int(seg.max().item()) + 1), generator=g, device=device)
+        idx = torch.gather(seg_cen, 1, seg.to(torch.int64)).reshape(-1)
+        out = Y[t0 * frames_per_traj:(t0 + nt) * frames_per_traj]
+        torch.index_select(cen, 0, idx, out=out)
+        out += torch.randn(out.shape, generator=g, device=device, dtype=torch.float32)
+        del hops, seg, seg_cen, idx
+    return Y, cen
+
+
+def gpu_arm_c5(args):
+    """BASELINE configs[4]: 50 M frames x 64 dims, K = 5000, 10 Lloyd iterations, 5000 x 5000 counts at lag 20,
+    reversible MLE, top-20 eigenvalues -- one GPU (12.8 GB of Y).  Prints one JSON line in the bench contract;
+    the roofline entries are K6 on the tensor roofline (2 D K flop per frame and iteration; issued as fp16-kind
+    MMAs) and K8 against HBM (8 K^2 bytes per iteration: 200 MB, no longer L2-resident)."""
+    import torch
+
+    from pmarlo_b200 import _lib
+    from pmarlo_b200.distributed import Comm
+    from pmarlo_b200.pipeline import PipelineConfig, StageTimer, run_pipeline
+    from pmarlo_b200.shards import Segments
+
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    _lib.load()
+    D, K, lag = 64, 5000, 20
+    n_traj = max(1, args.frames_per_gpu // FRAMES_PER_TRAJ) if args.frames_per_gpu != 10_000_000 else 400
+    frames = n_traj * FRAMES_PER_TRAJ
+    Y, cen = synth_c5_device(n_traj, FRAMES_PER_TRAJ, D, K, device, seed=5)
+    segs = Segments.from_lengths([FRAMES_PER_TRAJ] * n_traj)
+    cfg = PipelineConfig(tica_dim=0, n_states=K, kmeans_max_iter=10, kmeans_tolerance=None, msm_lag=lag, n_timescales=19,
+                         mle_maxerr=1e-12, mle_maxiter=args.c5_mle_maxiter, seed=5)
+    init = (cen + 0.5 * torch.randn(cen.shape, device=device, generator=torch.Generator(device=device).manual_seed(6))).to(torch.float64)
+    bufs: dict = {}
+    res = None
+    for _ in range(max(1, min(args.warmup, 3))):
+        res = run_pipeline(None, segs, None, cfg, Comm(), features=Y, initial_centers=init, buffers=bufs)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    timer = StageTimer(True)
+    l0 = _lib.launch_count()
+    steps = max(1, min(args.steps, 3))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        res = run_pipeline(None, segs, None, cfg, Comm(), features=Y, initial_centers=init, timer=timer, buffers=bufs)
+    b.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = a.elapsed_time(b) / steps
+    stages = {k: v / steps for k, v in timer.totals_ms().items()}
+    counts = timer.counts()
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    n_assign = max(1, counts.get("kmeans_assign", 1)) / steps
+    ms_assign = stages.get("kmeans_assign", 0.0) / n_assign
+    tf = 2.0 * D * K * frames / (ms_assign * 1e-3) / 1e12 if ms_assign else 0.0
+    mle_iters = int(res.mle_info[0].item())
+    ms_mle_iter = stages.get("mle", 0.0) / max(1, mle_iters)
+    mle_gbs = 8.0 * K * K / (ms_mle_iter * 1e-3) / 1e9 if ms_mle_iter else 0.0
+    # properties that hold at any size
+    C = res.counts
+    props = {"counts_total_ok": bool(int(C.sum().item()) == segs.n_pairs(lag)),
+             "rows_stochastic": float((res.T.sum(dim=1) - 1.0).abs().max().item()),
+             "stationarity": float((res.pi @ res.T - res.pi).abs().max().item()),
+             "detailed_balance": float((res.pi[:, None] * res.T - (res.pi[:, None] * res.T).T).abs().max().item()),
+             "mle_converged": bool(int(res.mle_info[1].item()) == 1), "mle_iters": mle_iters,
+             "lanczos_steps": int(res.extra["eig_info"].reshape(-1)[0].item())}
+    line = {
+        "metric": METRIC, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 coordinates / fp16-kind split-K score GEMM with fp64 re-check / f64 MSM", "data": "synthetic",
+        "config": {"workload": "C5 large-state stress: 50 M frames x 64 dims, k-means K=5000 x 10 Lloyd iterations, 5000x5000 counts "
+                               "at lag 20, reversible MLE (1e-12), top-20 eigenvalues", "frames_per_gpu": frames, "n_states": K,
+                   "n_dims": D, "kmeans_iters": 10, "msm_lag": lag,
+                   "l2_policy": "Y (256 B per frame, 12.8 GB) and the 200 MB count / transition matrices exceed the 126 MB L2"},
+        "gpu_launches": int(_lib.launch_count() - l0), "clocks": clocks, "stages_ms": stages,
+        "roofline": {"kernel": "kmeans_assign", "bound": "tensor", "achieved": tf, "peak": bf16 / 2.0, "unit": "TFLOP/s",
+                     "frac": tf / (bf16 / 2.0), "frac_of_fp16_peak": tf / bf16, "traffic": None, "ms_per_launch": ms_assign,
+                     "algorithmic_per_frame": 2 * D * K,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (same TF32-rate denominator as C4; the kernel "
+                                    "issues 3 fp16 MMAs per algorithmic product, so 1/3 of the fp16 peak is its ceiling)",
+                     "all": {"mle": {"bound": "hbm", "achieved": mle_gbs, "peak": hbm, "unit": "GB/s", "frac": mle_gbs / hbm,
+                                     "ms_per_iteration": ms_mle_iter, "algorithmic_bytes_per_iteration": 8 * K * K}}},
+        "properties": props, "e2e": None, "cpu_baseline": None, "parity": PARITY_NOTE,
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -679,6 +785,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the strong-scaling record and the multi-rank parity check (N > 1)")
     ap.add_argument("--gram-impl", type=int, default=0)
+    ap.add_argument("--config", default="C4", choices=["C4", "C5"],
+                    help="C4 (default, the metric's configuration) or the large-state stress configuration C5 (N = 1)")
+    ap.add_argument("--c5-mle-maxiter", type=int, default=200_000)
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -686,6 +795,8 @@ def main():
         print("note: fewer than 3 warm-up steps", file=sys.stderr)
     if args.impl == "reference":
         return reference_arm(args)
+    if args.config == "C5":
+        return gpu_arm_c5(args)
     return gpu_arm(args)
 
 
