@@ -245,6 +245,12 @@ PMB_API int pmb_tc_selftest_raw(const void* Aimg, uint32_t a_bytes, const void* 
                                 int nsteps, uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t step_a,
                                 uint32_t step_b, uint32_t idesc, int kind, float* D, pmb_stream_t stream);
 
+/* Weighted 2-D histogram with np.histogram2d semantics (last bin closed, out-of-range and NaN dropped): the
+ * per-frame part of generate_2d_fes, markov_state_model/free_energy.py:417-865.  x, y, w (may be NULL): n fp64;
+ * H: bx x by fp64, ACCUMULATED into (zero it first); bx * by <= 16384. */
+PMB_API int pmb_hist2d(const double* x, const double* y, const double* w, int64_t n, double xlo, double xhi, int bx,
+                       double ylo, double yhi, int by, double* H, pmb_stream_t stream);
+
 /* ---- Bayesian MSM: Gibbs sampler of reversible transition matrices ----------------
  * Replaces deeptime BayesianMSM(lagtime, n_samples).fit(dtrajs) / TransitionMatrixSampler(reversible=True)
  * (_its.py:272-357, 670-740).  C: batch x K x K counts (fp64, zero rows / columns outside the connected set),

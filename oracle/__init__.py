@@ -23,6 +23,6 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 library is missing instead of falling back to this code.
 """
 
-from . import bayes, cext, ck, counts, featurize, kmeans, msm, pipeline, tica  # noqa: F401
+from . import bayes, cext, ck, tpt, counts, featurize, kmeans, msm, pipeline, tica  # noqa: F401
 
-__all__ = ["featurize", "tica", "kmeans", "counts", "msm", "ck", "pipeline", "cext", "bayes"]
+__all__ = ["featurize", "tica", "kmeans", "counts", "msm", "ck", "pipeline", "cext", "bayes", "tpt"]

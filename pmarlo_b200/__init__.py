@@ -26,5 +26,7 @@ from .msm import (  # noqa: F401
 )
 from .reduction import TICA, maybe_apply_tica, reduce_features, tica_reduce, vamp_reduce  # noqa: F401
 from .topology import Topology, Trajectory, load_pdb  # noqa: F401
+from .analysis import FESResult, TPTAnalysis, TPTResult, free_energy_from_density, generate_2d_fes  # noqa: F401
+from .io import DCDReader, featurize_stream, iterload, save_analysis_results  # noqa: F401
 
 __version__ = "0.1.0"

@@ -56,6 +56,7 @@ PROTOTYPES = {
                                    C.c_uint32, C.c_uint32, C.c_uint32, _i32, _p, _p]),
     "pmb_mle_rev_ws_bytes": (_sz, [_i32, _i32]),
     "pmb_mle_rev": (_i32, [_p, _p, _i32, _i32, _f64, _f64, _i64, _p, _p, _p, _p, _sz, _p]),
+    "pmb_hist2d": (_i32, [_p, _p, _p, _i64, _f64, _f64, _i32, _f64, _f64, _i32, _p, _p]),
     "pmb_bayes_rev_sample": (_i32, [_p, _p, _i32, _i32, _i32, _i32, C.c_uint64, _p, _p, _p]),
     "pmb_counts_active": (_i32, [_p, _i32, _f64, _p, _p, _p]),
     "pmb_trig_expand": (_i32, [_p, _i64, _i32, _p, _p, _p, _i32, _p]),

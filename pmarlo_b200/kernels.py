@@ -277,6 +277,20 @@ def kmeans_update(centers: torch.Tensor, sums: torch.Tensor, counts: torch.Tenso
                                        stream_handle(centers.device)), "pmb_kmeans_update")
 
 
+def hist2d(x: torch.Tensor, y: torch.Tensor, bins: tuple[int, int], ranges, weights: torch.Tensor | None = None) -> torch.Tensor:
+    """np.histogram2d(x, y, bins, range, weights=...)[0] on the device (fp64)."""
+    _flat(x, torch.float64, "x")
+    _flat(y, torch.float64, "y", numel=x.numel())
+    if weights is not None:
+        _flat(weights, torch.float64, "weights", numel=x.numel())
+    bx, by = int(bins[0]), int(bins[1])
+    H = torch.zeros((bx, by), dtype=torch.float64, device=x.device)
+    (xlo, xhi), (ylo, yhi) = ranges
+    check(_lib.lib().pmb_hist2d(ptr(x), ptr(y), ptr(weights), int(x.numel()), float(xlo), float(xhi), bx, float(ylo),
+                                float(yhi), by, ptr(H), stream_handle(x.device)), "pmb_hist2d")
+    return H
+
+
 def silhouette_samples(Y: torch.Tensor, labels: torch.Tensor, K: int) -> torch.Tensor:
     """Per-sample silhouette coefficients (fp64) of a labelling with K <= 64 clusters."""
     _dev(Y, torch.float64, "Y")

@@ -1,0 +1,116 @@
+"""GPU tests for SURVEY.md 8f-3 / 8f-4: histogram free-energy surface, transition-path theory, streaming ingest."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    assert torch.cuda.is_available()
+    from pmarlo_b200 import load_library
+
+    load_library()
+    torch.cuda.set_device(0)
+    yield
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("n,bins", [(1000, (7, 5)), (300000, (100, 100)), (50000, (128, 128))])
+def test_hist2d_matches_numpy(n, bins):
+    from pmarlo_b200 import kernels
+
+    rng = np.random.default_rng(n)
+    x, y = rng.normal(size=n), rng.normal(size=n) * 2 + 1
+    x[::97] = np.nan
+    x[5], y[6] = -2.0, 7.0                         # exactly on the outer edges: last bin is closed
+    x[7] = -2.0 + 4.0 * 3 / bins[0]                 # exactly on an inner edge
+    ranges = ((-2.0, 2.0), (-5.0, 7.0))
+    w = rng.random(n)
+    for weights in (None, w):
+        ok = np.isfinite(x)
+        ref, _, _ = np.histogram2d(x[ok], y[ok], bins=bins, range=ranges, weights=None if weights is None else weights[ok])
+        got = kernels.hist2d(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), bins, ranges,
+                             None if weights is None else torch.from_numpy(weights).cuda()).cpu().numpy()
+        if weights is None:
+            np.testing.assert_array_equal(got, ref)
+        else:
+            np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_generate_2d_fes_matches_numpy_restatement():
+    from pmarlo_b200 import free_energy_from_density, generate_2d_fes
+    from pmarlo_b200.analysis import kT_kJ_per_mol
+
+    rng = np.random.default_rng(2)
+    phi = np.concatenate([rng.normal(-60, 15, 40000), rng.normal(60, 20, 20000)])
+    psi = np.concatenate([rng.normal(-45, 15, 40000), rng.normal(150, 25, 20000)])
+    res = generate_2d_fes(phi, psi, bins=(36, 36), temperature=300.0, periodic=(True, True), min_count=1)
+    xw = (phi + 180) % 360 - 180
+    yw = (psi + 180) % 360 - 180
+    H, xe, ye = np.histogram2d(xw, yw, bins=(36, 36), range=((-180, 180), (-180, 180)))
+    dens = H / (H.sum() * np.diff(xe)[:, None] * np.diff(ye)[None, :])
+    F = free_energy_from_density(dens, 300.0, mask=H < 1)
+    np.testing.assert_array_equal(res.metadata["counts"], H)
+    np.testing.assert_allclose(res.F, F, rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(res.xedges, xe)
+    assert np.nanmin(res.F) == 0.0 and np.isnan(res.F[H < 1]).all()
+    # two wells with populations 2 : 1 differ by about kT ln 2 (different widths: compare basin minima loosely)
+    assert abs(kT_kJ_per_mol(300.0) - 2.494) < 0.01
+    ad = generate_2d_fes(phi, psi, bins=(20, 20), grid_strategy="adaptive")
+    assert ad.xedges[0] > phi.min() and ad.xedges[-1] < phi.max()
+    with pytest.raises(ValueError):
+        free_energy_from_density(dens, -1.0)
+
+
+def test_tpt_matches_oracle_and_conserves_flux():
+    from pmarlo_b200 import TPTAnalysis
+
+    rng = np.random.default_rng(3)
+    K = 40
+    Cm = rng.random((K, K)) ** 3
+    Cm = Cm + Cm.T + np.diag(5 * rng.random(K))
+    T = Cm / Cm.sum(axis=1, keepdims=True)
+    pi = Cm.sum(axis=1) / Cm.sum()
+    A, B = [0, 1, 2], [37, 38, 39]
+    r = TPTAnalysis(T, pi).analyze(A, B, n_paths=5, pathway_fraction=0.9)
+    o = oracle.tpt.reactive_flux(T, pi, A, B)
+    np.testing.assert_allclose(r.forward_committor, o["qf"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(r.backward_committor, o["qb"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(r.flux_matrix, o["gross"], rtol=1e-10, atol=1e-16)
+    np.testing.assert_allclose(r.net_flux, o["net"], rtol=1e-9, atol=1e-16)
+    assert abs(r.total_flux - o["total_flux"]) <= 1e-12 * o["total_flux"] and abs(r.rate - o["rate"]) <= 1e-10 * o["rate"]
+    np.testing.assert_allclose(r.backward_committor, 1.0 - r.forward_committor, atol=1e-10)   # reversible chain
+    inter = np.setdiff1d(np.arange(K), A + B)
+    np.testing.assert_allclose(r.net_flux[inter].sum(axis=1), r.net_flux[:, inter].sum(axis=0), rtol=1e-9)   # conservation
+    assert len(r.pathways) >= 1 and all(p[0] in A and p[-1] in B for p in r.pathways)
+    assert np.all(np.diff(r.pathway_fluxes) <= 1e-15) and r.pathway_fluxes.sum() <= r.total_flux * (1 + 1e-9)
+    with pytest.raises(ValueError):
+        TPTAnalysis(T, pi).analyze([0, 1], [1, 2])
+
+
+def test_featurize_stream_from_dcd_matches_in_memory(tmp_path, topologies):
+    from pmarlo_b200.features import featurize_device, plan_phi_psi_block
+    from pmarlo_b200.io import featurize_stream, write_dcd
+    from pmarlo_b200.topology import Topology
+
+    t = topologies["ala2"]
+    top = Topology(list(t["names"]), np.asarray(t["resid"], dtype=np.int64), np.asarray(t["chain"], dtype=np.int64))
+    trajs, _ = synth.ala2_trajectories(t, n_traj=2, n_frames=[700, 650], seed=3)
+    xyz = np.concatenate(trajs)
+    path = tmp_path / "ala2.dcd"
+    write_dcd(path, xyz)
+    plan = plan_phi_psi_block(top)
+    got = featurize_stream(path, top, plan, chunk=256)
+    from pmarlo_b200.io import DCDReader
+
+    ref = featurize_device(torch.from_numpy(DCDReader(path).read(0, 1350)).cuda(), plan)
+    assert got.shape == (1350, plan.n_cols)
+    assert torch.equal(got, ref)
