@@ -134,6 +134,14 @@ __device__ __forceinline__ float ldg_stream_f(const float* p) {
   return v;
 }
 
+// volatile load of an int32 (the statement cannot be sunk below later asm volatile waits: a prefetch stays a prefetch).
+// NOT the non-coherent path: the hints may alias the labels this kernel writes for OTHER rows.
+__device__ __forceinline__ int ldg_stream_i(const int* p) {
+  int v;
+  asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

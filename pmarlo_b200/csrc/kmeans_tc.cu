@@ -560,10 +560,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       const int64_t row = tile * kTcTile + pt;
       hint_n = -1;
       if (row < p.n) {
-        if (p.hints != nullptr) hint_n = p.hints[row];
+        if (p.hints != nullptr) hint_n = ldg_stream_i(p.hints + row);
         if constexpr (in_regs) {
 #pragma unroll
-          for (int d = 0; d < kTcDReg; ++d) yn[d] = (d < D) ? p.Y[row * p.ld + d] * scale : 0.f;
+          for (int d = 0; d < kTcDReg; ++d) yn[d] = (d < D) ? ldg_stream_f(p.Y + row * p.ld + d) : 0.f;   // scaled at use
         }
       } else {
 #pragma unroll
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       const bool valid = row < p.n;
       float y[kTcDReg];
 #pragma unroll
-      for (int d = 0; d < kTcDReg; ++d) y[d] = yn[d];
+      for (int d = 0; d < kTcDReg; ++d) y[d] = yn[d] * scale;
       const int hint = hint_n;
       if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
       // fp32 distance to the hinted centre (scaled centres written by the prep kernel)
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     auto prefetch = [&](int64_t tile) {
       const int64_t row = tile * kTcTile + pt;
 #pragma unroll
-      for (int d = 0; d < kTcDReg; ++d) yn[d] = (in_regs && d < D && row < p.n) ? p.Y[row * p.ld + d] : 0.f;
+      for (int d = 0; d < kTcDReg; ++d) yn[d] = (in_regs && d < D && row < p.n) ? ldg_stream_f(p.Y + row * p.ld + d) : 0.f;
     };
     uint32_t it = 0;
     double ysq_fix = 0.0;   // |y|^2 of the frames the producers left out of ysq (they did not fit fp16)
