@@ -180,6 +180,8 @@ PMB_API int pmb_debug_counters_tica(int64_t* out8);
 /* trace of the last pmb_tica_solve: [0..15] SM id of CTAs 0..15, then per Jacobi sweep (up to 32) the pair
  * (SM cycles, nanoseconds of the global timer) on CTA 0. */
 PMB_API int pmb_debug_trace_tica(int64_t* out80);
+/* Debug: role-timing counters of the last fp16 tcgen05 Gram launch (zeros unless built with -DPMB_GH_PROF). */
+PMB_API int pmb_debug_counters_gram(int64_t* out16);
 /* Debug: role-timing counters of the last tcgen05 assignment (zeros unless built with -DPMB_KM_PROF). */
 PMB_API int pmb_debug_counters_kmeans(int64_t* out16);
 PMB_API int pmb_kmeans_tc_scores(const float* Y, int64_t n, int D, int64_t ld, const double* centers,

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "pmb_kmeans_assign_ws_bytes": (_sz, [_i64, _i32, _i32]),
     "pmb_kmeans_assign": (_i32, [_p, _i32, _i64, _i32, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _i32, _p]),
     "pmb_debug_counters_kmeans": (_i32, [_p]),
+    "pmb_debug_counters_gram": (_i32, [_p]),
     "pmb_debug_counters_tica": (_i32, [_p]),
     "pmb_debug_trace_tica": (_i32, [_p]),
     "pmb_kmeans_tc_scores": (_i32, [_p, _i64, _i32, _i64, _p, _i32, _p, _p, _p, _sz, _p]),

@@ -38,6 +38,8 @@ struct GramParams {
   int n_chunks;
   int64_t chunk;  // frames per chunk (multiple of kGBK)
   int vec_ok;     // float4 loads legal
+  const unsigned int* run_if;   // nullptr, or a device flag: the kernels return at once while it is 0 (gram_h.cu's
+                                // out-of-range fallback)
 };
 
 __device__ __forceinline__ float4 load4(const float* __restrict__ X, int64_t row, int64_t ld, int c,
@@ -63,6 +65,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kGThreads, 1) gram_simt_kernel(GramParams p) {
   __shared__ __align__(16) float As[2][kGBK][kGT];
   __shared__ __align__(16) float Bs[2][kGBK][kGT];
+  if (p.run_if != nullptr && *p.run_if == 0u) return;
 
   // upper-triangular tile enumeration
   const int nb = (p.d + kGT - 1) / kGT;
@@ -188,7 +191,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_simt_kernel(GramParams p) {
 
 // G[i][j] = sum over chunks (fixed order); lower triangle mirrored.
 __global__ void gram_reduce_kernel(const double* __restrict__ part, int n_chunks, int d,
-                                   double* __restrict__ G) {
+                                   double* __restrict__ G, const unsigned int* run_if) {
+  if (run_if != nullptr && *run_if == 0u) return;
   const int nb = (d + kGT - 1) / kGT;
   int ti = 0, rem = blockIdx.x;
   while (rem >= nb - ti) { rem -= nb - ti; ++ti; }
@@ -223,15 +227,54 @@ int gram_tcgen05(const float* X, int64_t n, int d, int64_t ld, const uint8_t* ma
                  size_t ws_bytes, cudaStream_t stream, bool cta_pairs);  // gram_tc.cu
 bool gram_tcgen05_supported(int d, int64_t ld, const float* X);
 size_t gram_tcgen05_ws_bytes(int d);
+// gram_h.cu: the fp16-kind path (default on tensor cores)
+bool gram_h_supported(int d, int64_t ld, const float* X, int64_t n);
+size_t gram_h_ws_bytes(int d);
+int gram_h(const float* X, int64_t n, int d, int64_t ld, const uint8_t* mask, int lag, int mode, const float* shift,
+           const float* scale, double* G, void* ws, size_t ws_bytes, cudaStream_t st);
+int gram_h_debug_counters(int64_t* out16);
 constexpr int64_t kGramTcMinFrames = 65536;   // auto dispatch: below this the SIMT kernel is as fast
 
+// The SIMT launches; with run_if != nullptr they execute only when *run_if != 0 on the device.
+int gram_simt(const float* X, int64_t n, int d, int64_t ld, const uint8_t* mask, int lag, int mode, const float* shift,
+              const float* scale, double* G, void* ws, cudaStream_t st, const unsigned int* run_if) {
+  GramParams p;
+  p.X = X; p.n = n; p.d = d; p.ld = ld; p.mask = mask; p.lag = lag; p.shift = shift; p.scale = scale;
+  p.part = static_cast<double*>(ws);
+  p.run_if = run_if;
+  const int nt = gram_tiles(d);
+  int nc = gram_chunks(d);
+  int64_t chunk = (n + nc - 1) / nc;
+  chunk = ((chunk + kFoldFrames - 1) / kFoldFrames) * kFoldFrames;
+  nc = (int)((n + chunk - 1) / chunk);
+  p.n_chunks = nc;
+  p.chunk = chunk;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (ld % 4 == 0);
+  dim3 grid(nt, nc);
+  if (mode == 0) gram_simt_kernel<0><<<grid, kGThreads, 0, st>>>(p);
+  else           gram_simt_kernel<1><<<grid, kGThreads, 0, st>>>(p);
+  PMB_LAUNCH_CHECK();
+  dim3 rgrid(nt, 16);
+  gram_reduce_kernel<<<rgrid, 256, 0, st>>>(p.part, nc, d, G, run_if);
+  PMB_LAUNCH_CHECK();
+  return PMB_OK;
+}
+
 }  // namespace pmb
+
+extern "C" int pmb_debug_counters_gram(int64_t* out16) {
+  using namespace pmb;
+  PMB_REQUIRE(out16 != nullptr, "pmb_debug_counters_gram: null pointer");
+  return gram_h_debug_counters(out16);
+}
 
 extern "C" size_t pmb_gram_ws_bytes(int d) {
   if (d <= 0) return 0;
   const size_t simt = (size_t)pmb::gram_tiles(d) * pmb::gram_chunks(d) * pmb::kGT * pmb::kGT * sizeof(double);
-  const size_t tc = pmb::gram_tcgen05_ws_bytes(d);
-  return simt > tc ? simt : tc;
+  size_t tc = pmb::gram_tcgen05_ws_bytes(d);
+  if (pmb::gram_h_ws_bytes(d) > tc) tc = pmb::gram_h_ws_bytes(d);
+  // the fp16 path keeps a 256-byte header in front of the region its SIMT fallback would use
+  return (simt + 256 > tc ? simt + 256 : tc);
 }
 
 extern "C" int pmb_gram(const float* X, int64_t n, int d, int64_t ld, const uint8_t* mask, int lag,
@@ -245,7 +288,15 @@ extern "C" int pmb_gram(const float* X, int64_t n, int d, int64_t ld, const uint
     set_error("pmb_gram: workspace too small (%zu < %zu)", ws_bytes, pmb_gram_ws_bytes(d));
     return PMB_EWORKSPACE;
   }
-  // impl: 0 auto, 1 SIMT, 2 tensor cores, 4 tensor cores with CTA pairs (d = 256; measured slower, see gram_tc.cu)
+  // impl: 0 auto, 1 SIMT, 2 tensor cores (kind::tf32, gram_tc.cu), 4 the same with CTA pairs (d = 256; measured
+  // slower), 5 tensor cores (kind::f16, gram_h.cu: what auto selects)
+  if (impl == 5 || (impl == 0 && n >= kGramTcMinFrames && gram_h_supported(d, ld, X, n))) {
+    if (!gram_h_supported(d, ld, X, n)) {
+      set_error("pmb_gram: the fp16 tcgen05 path needs d %% 32 == 0, 32 <= d <= 256, 16B-aligned rows");
+      return PMB_EUNSUPPORTED;
+    }
+    return gram_h(X, n, d, ld, mask, lag, mode, shift, scale, G, ws, ws_bytes, as_stream(stream));
+  }
   if (impl == 2 || impl == 4 || (impl == 0 && n >= kGramTcMinFrames && gram_tcgen05_supported(d, ld, X))) {
     if (!gram_tcgen05_supported(d, ld, X)) {
       set_error("pmb_gram: tcgen05 path needs d %% 32 == 0, 32 <= d <= 256, 16B-aligned rows");
@@ -253,23 +304,5 @@ extern "C" int pmb_gram(const float* X, int64_t n, int d, int64_t ld, const uint
     }
     return gram_tcgen05(X, n, d, ld, mask, lag, mode, shift, scale, G, ws, ws_bytes, as_stream(stream), impl == 4);
   }
-  GramParams p;
-  p.X = X; p.n = n; p.d = d; p.ld = ld; p.mask = mask; p.lag = lag; p.shift = shift; p.scale = scale;
-  p.part = static_cast<double*>(ws);
-  const int nt = gram_tiles(d);
-  int nc = gram_chunks(d);
-  int64_t chunk = (n + nc - 1) / nc;
-  chunk = ((chunk + kFoldFrames - 1) / kFoldFrames) * kFoldFrames;
-  nc = (int)((n + chunk - 1) / chunk);
-  p.n_chunks = nc;
-  p.chunk = chunk;
-  p.vec_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (ld % 4 == 0);
-  dim3 grid(nt, nc);
-  if (mode == 0) gram_simt_kernel<0><<<grid, kGThreads, 0, as_stream(stream)>>>(p);
-  else           gram_simt_kernel<1><<<grid, kGThreads, 0, as_stream(stream)>>>(p);
-  PMB_LAUNCH_CHECK();
-  dim3 rgrid(nt, 16);
-  gram_reduce_kernel<<<rgrid, 256, 0, as_stream(stream)>>>(p.part, nc, d, G);
-  PMB_LAUNCH_CHECK();
-  return PMB_OK;
+  return gram_simt(X, n, d, ld, mask, lag, mode, shift, scale, G, ws, as_stream(stream), nullptr);
 }

@@ -133,22 +133,66 @@ def test_gram_tensor_path_matches_fp64(d, n_frames, lag):
     v = (z[idx] - z[idx + lag]).astype(np.float32).astype(np.float64)
     G1 = v.T @ v
     for mode, ref in ((0, G0), (1, G1)):
-        tc = kernels.gram(Xd, mask, lag, mode, cond, impl=2).cpu().numpy()
         simt = kernels.gram(Xd, mask, lag, mode, cond, impl=1).cpu().numpy()
         scale_ref = np.max(np.abs(ref))
-        e_tc = np.max(np.abs(tc - ref)) / scale_ref
         e_simt = np.max(np.abs(simt - ref)) / scale_ref
-        e_diag = np.max(np.abs(np.diag(tc) - np.diag(ref)) / np.abs(np.diag(ref)))
-        print(f"gram d={d} mode={mode}: tcgen05 err {e_tc:.2e} (diag rel {e_diag:.2e}), SIMT err {e_simt:.2e}")
-        # diagonal entries of mode 1 are sums of small squared differences: relative to themselves the
-        # stochastic-rounding split is good to a few 1e-7, relative to the matrix scale to ~3e-8
-        assert e_tc <= 1e-7 and e_diag <= 5e-7
-        np.testing.assert_array_equal(tc, tc.T)
+        # impl 5: kind::f16 kernel (gram_h.cu, what impl=0 selects for large n); impl 2: kind::tf32 kernel (its
+        # out-of-range fallback)
+        for impl in (5, 2):
+            tc = kernels.gram(Xd, mask, lag, mode, cond, impl=impl).cpu().numpy()
+            e_tc = np.max(np.abs(tc - ref)) / scale_ref
+            e_diag = np.max(np.abs(np.diag(tc) - np.diag(ref)) / np.abs(np.diag(ref)))
+            print(f"gram d={d} mode={mode} impl={impl}: tcgen05 err {e_tc:.2e} (diag rel {e_diag:.2e}), SIMT err {e_simt:.2e}")
+            # diagonal entries of mode 1 are sums of small squared differences: relative to themselves the
+            # stochastic-rounding split is good to a few 1e-7, relative to the matrix scale to ~3e-8
+            assert e_tc <= 1e-7 and e_diag <= 5e-7
+            np.testing.assert_array_equal(tc, tc.T)
         if d == 256:
             # the CTA-pair kernel (cta_group::2, impl=4) must agree with the default single-CTA kernel
             one = kernels.gram(Xd, mask, lag, mode, cond, impl=4).cpu().numpy()
             assert np.max(np.abs(one - ref)) / scale_ref <= 1e-7
             assert np.max(np.abs(one - tc)) / scale_ref <= 2e-8
+
+
+def test_gram_f16_path_edge_weights_and_out_of_range_fallback():
+    """gram_h.cu specifics.  (i) Many short shards: a third of the frames carry weight 1 in mode 0, i.e. the
+    second (edge-frame) pass matters.  (ii) A z-score beyond the accepted range of the clamped leading term
+    (|z| > 132), or an infinite input: the device flag makes the SIMT kernel recompute the matrix, no host round
+    trip; (iii) |z| = 120 stays on the fp16 path (inside the leading term's range; the exactness budget shortens that window)."""
+    from pmarlo_b200 import kernels
+    from pmarlo_b200.shards import Segments
+
+    d, lag = 128, 5
+    rng = np.random.default_rng(11)
+    lens = [int(v) for v in rng.integers(12, 40, size=700)] + [3, 5, 1]
+    X = rng.normal(size=(sum(lens), d)).astype(np.float32) + 1.5
+    segs = Segments.from_lengths(lens)
+    shift = X.mean(axis=0).astype(np.float32)
+    scale = (1.0 / X.std(axis=0)).astype(np.float32)
+    for case, big in (("edges", 0.0), ("large_z", 120.0), ("out_of_range", 5000.0)):
+        Xc = X.copy()
+        if big:
+            Xc[1234, 7] = shift[7] + big / scale[7]
+            Xc[4321, 9] = np.nan                      # imputed with 0 on every path
+        Xd = torch.from_numpy(Xc).to(dev())
+        mask = kernels.pair_mask(segs.device(dev()), Xc.shape[0], lag)
+        cond = torch.from_numpy(np.stack([shift, scale])).to(dev())
+        m = mask.cpu().numpy()
+        z = np.where(np.isnan(Xc), np.float32(0), (Xc - shift[None]) * scale[None]).astype(np.float32)
+        w0 = ((m & 1) + ((m >> 1) & 1)).astype(np.float64)
+        assert 0.2 < np.mean(w0 == 1) < 0.6
+        G0 = (z.astype(np.float64) * w0[:, None]).T @ z.astype(np.float64)
+        idx = np.flatnonzero(m & 1)
+        v = (z[idx] - z[idx + lag]).astype(np.float32).astype(np.float64)
+        G1 = v.T @ v
+        for mode, ref in ((0, G0), (1, G1)):
+            got = kernels.gram(Xd, mask, lag, mode, cond, impl=5).cpu().numpy()
+            simt = kernels.gram(Xd, mask, lag, mode, cond, impl=1).cpu().numpy()
+            err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+            print(f"gram f16 {case} mode={mode}: err {err:.2e}")
+            assert err <= 1e-7, (case, mode, err)
+            if case == "out_of_range":
+                np.testing.assert_array_equal(got, simt)    # the fallback IS the SIMT kernel
 
 
 @pytest.mark.parametrize("case", ["stationary", "drifting", "nan"])

@@ -28,7 +28,7 @@ for n_traj, fpt, rho in ((4, 20000, 0.995), (8, 125000, 0.9995), (2, 40000, 0.98
     C00 = (X0c.T @ X0c + Xtc.T @ Xtc) / (2 * T)
     C0t = (X0c.T @ Xtc + Xtc.T @ X0c) / (2 * T)
     zmax = float(Z.abs().max().item())
-    for impl in (1, 2):
+    for impl in (1, 2, 5):
         model = TICA(lag, 10, preprocess="standard", gram_impl=impl).fit_device(X, segs)
         e00 = float((model.C00 - C00).abs().max().item() / C00.abs().max().item())
         e0t = float((model.C0t - C0t).abs().max().item() / C0t.abs().max().item())

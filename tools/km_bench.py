@@ -11,6 +11,11 @@ import torch
 sys.path.insert(0, ".")
 from pmarlo_b200 import _lib, kernels  # noqa: E402
 
+import os  # noqa: E402
+
+if os.environ.get("PMB_LIB"):   # experiment builds (e.g. -DPMB_KM_PROF) live outside the package
+    _lib.load(os.environ["PMB_LIB"])
+
 
 def counters():
     buf = (ctypes.c_int64 * 16)()

@@ -1,7 +1,6 @@
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/tests_gpu.log 2>&1; echo "pytest_exit=$?"; tail -n 3 gpurun_out/tests_gpu.log
-python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err; echo "bench=$?"
-python - <<'PY'
-import json
-d=json.loads([l for l in open("gpurun_out/bench_default.log") if l.startswith("{")][-1])
-print(round(d["value"]/1e6,2), round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"]/1e6,2), d["mle_iters"], {k: round(v,2) for k,v in d["stages_ms"].items()})
-PY
+# Experiment round (edit freely)
+set -x
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -x -q -m gpu -k "kmeans or gram or assign or cluster or c5_assignment or nan_and_inf" > gpurun_out/t_km.log 2>&1; echo "pytest=$?"; tail -n 6 gpurun_out/t_km.log
+python tools/km_bench.py c4 > gpurun_out/km_plain.log 2>&1; echo "km_plain=$?"; cat gpurun_out/km_plain.log
+PMB_LIB=build_exp/libpmb200_kmprof.so python tools/km_bench.py c4 > gpurun_out/km_prof.log 2>&1; echo "km_prof=$?"; cat gpurun_out/km_prof.log
+python tools/gram_bench.py 10000000 5 > gpurun_out/gram_bench.log 2>&1; echo "gb=$?"; cat gpurun_out/gram_bench.log
