@@ -8,7 +8,7 @@ K x K work: the 2-D free-energy surface and transition-path theory.
   ``MarkovStateModel.reactive_flux``: committors from two K x K linear solves (torch.linalg on the device, a
   library call on a cold path), gross / net flux, total flux, rate, MFPT, and the dominant pathways by
   bottleneck decomposition of the net flux (graph search on the K x K matrix, host).
-PCCA+ (deeptime ``pcca``) stays an injected callable (see ck.py): its simplex optimisation is outside this path.
+PCCA+ (deeptime ``pcca``) lives in macro.py (``pcca_memberships`` / ``pcca_like_macrostates``).
 """
 
 from __future__ import annotations

@@ -21,10 +21,11 @@ adjacency (_ck.py:263-272) and ``np.linalg.eigvals`` of a non-symmetric K x K ma
 test and the slowest implied timescale (ck_runner.py:98-108, _ck.py:326-340).
 
 The macrostate branch of ``run_ck`` needs PCCA+ memberships, which the reference takes from deeptime
-(``_msm_utils.pcca_like_macrostates`` :284-299).  That lumping is an injected callable here
-(``macro_lumper(T1_micro, macro_k) -> labels | None``); the binding shown in INTEGRATION.md passes the
-reference's own function.  Without one the branch reports "not feasible" and the microstate branch runs,
-exactly as when PCCA+ returns ``None`` (ck_runner.py:201-203).  ``ck.png`` is written only when matplotlib
+(``_msm_utils.pcca_like_macrostates`` :284-299).  That lumping is the ``macro_lumper`` argument here:
+``"pcca"`` selects this package's PCCA+ (``macro.pcca_like_macrostates``), a callable
+``macro_lumper(T1_micro, macro_k) -> labels | None`` is used as given (e.g. the reference's own function, see
+INTEGRATION.md), and None reports "not feasible" so that the microstate branch runs, exactly as when PCCA+
+returns ``None`` (ck_runner.py:201-203).  ``ck.png`` is written only when matplotlib
 is importable.
 """
 
@@ -226,11 +227,25 @@ def _save_outputs(result: CKRunResult, out: Path) -> None:
         plt.close()
 
 
+def _resolve_lumper(macro_lumper):
+    """``macro_lumper="pcca"`` selects this package's PCCA+ (`macro.pcca_like_macrostates`, what the reference
+    calls at ck_runner.py:196-203 / ck_its_selector.py:300-330); a callable is used as given; None disables the
+    macrostate branch (the reference's behaviour when PCCA+ returns None)."""
+    if isinstance(macro_lumper, str):
+        if macro_lumper != "pcca":
+            raise ValueError(f"unknown macro_lumper {macro_lumper!r}")
+        from .macro import pcca_like_macrostates
+
+        return lambda T, k: pcca_like_macrostates(T, n_macrostates=int(k))
+    return macro_lumper
+
+
 def run_ck(dtrajs, lag_time: int, output_dir: str | Path | None = None, macro_k: int = 4, min_trans: int = 50,
            top_n_micro: int = 50, factors: Iterable[int] = (2, 3, 4, 5), *,
            macro_lumper: Optional[Callable[[np.ndarray, int], Optional[np.ndarray]]] = None) -> CKRunResult:
     """``ck_runner.run_ck``.  ``dtrajs``: sequence of integer arrays, or a ``LabelShard`` already in HBM.
     ``output_dir=None`` skips the csv/json/png side outputs."""
+    macro_lumper = _resolve_lumper(macro_lumper)
     factors_list = [int(f) for f in factors if int(f) > 1]
     n_traj = int(dtrajs.offsets.numel()) - 1 if isinstance(dtrajs, LabelShard) else len(dtrajs)
     if n_traj == 0:
@@ -555,6 +570,7 @@ def select_optimal_lag_ck_its(dtrajs: Sequence[np.ndarray], tau_candidates: Opti
     Differences, both documented in INTEGRATION.md: PCCA+ is the injected ``macro_lumper(T, n_macro)`` (None:
     microstate CK test, the reference's fallback); ``LagEvaluationResult.timescales`` holds the leading
     ``n_timescales`` values (the reference stores all n - 1; they do not enter the selection)."""
+    macro_lumper = _resolve_lumper(macro_lumper)
     if dtrajs is None or len(dtrajs) == 0:
         raise ValueError("No discrete trajectories provided")
     usable = [np.asarray(t) for t in dtrajs if t is not None and np.asarray(t).size > 0]

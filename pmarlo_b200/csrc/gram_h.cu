@@ -38,6 +38,12 @@
 // device flag and the launcher's follow-up launch of the SIMT kernel (gram.cu, fp32 products folded into fp64: any
 // range) recomputes the matrix instead of returning at once -- no host round trip.  So does an infinite input.
 //
+// Tried and measured slower (kept out of the tree): the two row-block CTAs of a chunk as a cluster that shares the
+// producer work, each CTA producing every other stage and storing the tiles into both CTAs' rings with
+// st.shared::cluster (multicast commit frees a slot when both CTAs' MMAs have read it).  Correct, same accuracy,
+// 8.4 / 9.9 ms per launch against 7.8 / 8.6 ms: 24 KB of remote stores per stage cost more than the arithmetic
+// they save -- the same finding as the cta_group::2 variant of gram_tc.cu, from the other side.
+//
 // One CTA per (128-row block of G, frame chunk): 148 CTAs = 2 row blocks x 74 chunks for d = 256.
 //   warps 0-15 producers: warp w = frame w of the stage; a lane owns features [4 L, 4 L + 4) and [128 + 4 L, ...):
 //              two conflict-free 16-byte reads of the raw row, six conflict-free 8-byte stores; drains
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
   for (int i = tid; i < n_words; i += kGhThreads) bitmap[i] = 0u;
   if (tid == 0) {
     for (int s = 0; s < kGhStages; ++s) {
-      mbar_init(&B->full[s], kGhProdWarps * 32);
+      mbar_init(&B->full[s], kGhProdWarps);
       mbar_init(&B->empty[s], 1);
     }
     for (int s = 0; s < kGhRawStages; ++s) {
@@ -381,7 +387,8 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
       }
       if (lane == 0) B->budget[slot][warp] = m * m;
       fence_proxy_async_smem();
-      tc::mbar_arrive(&B->full[slot]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&B->full[slot]);
       if (++slot == kGhStages) { slot = 0; ++use; }
     }
     if (n_active == 0) {

@@ -67,10 +67,13 @@ def seeded_initial_centers(Y: torch.Tensor, K: int, seed: int, comm: Comm) -> to
     """K distinct frames of rank 0's shard chosen by a seeded permutation, broadcast
     to every rank (the ``initial_centers=`` kwarg of clustering.py:243-250)."""
     centers = torch.empty((K, int(Y.shape[1])), dtype=torch.float64, device=Y.device)
+    # validated collectively: a raise on rank 0 alone would leave the other ranks inside the broadcast
+    n0 = torch.tensor([int(Y.shape[0]) if comm.rank == 0 else 0], dtype=torch.int64, device=Y.device)
+    comm.allreduce_sum(n0)
+    if int(n0.item()) < K:
+        raise ValueError(f"rank 0 holds {int(n0.item())} frames, fewer than n_states={K}")
     if comm.rank == 0:
         n = int(Y.shape[0])
-        if n < K:
-            raise ValueError(f"rank 0 holds {n} frames, fewer than n_states={K}")
         # O(K) draw (numpy's Generator.choice without replacement does not permute all n frames)
         pick = np.sort(np.random.default_rng(int(seed)).choice(n, size=K, replace=False))
         idx = torch.from_numpy(pick).to(Y.device)
@@ -219,6 +222,9 @@ def estimate_msm_from_host(xyz_host, lengths, plan: FeaturePlan, cfg: PipelineCo
         if acc is not None:
             lo, hi = int(np.searchsorted(offs, a)), int(np.searchsorted(offs, b))
             acc.add(X[a:b], Segments(offs[lo:hi + 1] - a))
+    if acc is not None and acc.moments is None:
+        # this rank holds no frames: it still joins the first chunk's broadcasts of the other ranks
+        acc.add(X[0:0], Segments(np.zeros((1,), dtype=np.int64)))
     model = acc.finish() if acc is not None else None
     res = run_pipeline(None, segs, plan, cfg, comm, features=X, read_back=False, buffers=buffers, tica_model=model)
     # what the reference's API hands back: labels (cluster_microstates), T and pi (build_msm_from_labels),

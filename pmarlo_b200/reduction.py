@@ -97,7 +97,13 @@ class TICA:
         mask = kernels.pair_mask(off, n_local, lag)
         shift = None
         if comm.size > 1:
-            shift = torch.nan_to_num(X[0].to(torch.float64), nan=0.0).contiguous()
+            # rank 0's first frame; an empty shard elsewhere still takes part in the broadcast, and an empty
+            # rank 0 is reported on every rank
+            n0 = comm.sum_int(n_local if comm.rank == 0 else 0, dev)
+            if n0 <= 0:
+                raise ValueError("rank 0 holds no frames")
+            shift = (torch.nan_to_num(X[0].to(torch.float64), nan=0.0).contiguous() if comm.rank == 0
+                     else torch.empty((int(X.shape[1]),), dtype=torch.float64, device=dev))
             comm.broadcast(shift, src=0)
         with timer.stage("col_moments"):
             moments = kernels.col_moments(X, mask, shift)
@@ -172,7 +178,14 @@ class TicaAccumulator:
 
     def _start(self, X: torch.Tensor) -> None:
         comm = self.est.comm
-        self.shift = torch.nan_to_num(X[0].to(torch.float64), nan=0.0).contiguous()
+        if comm.size > 1:
+            n0 = comm.sum_int(int(X.shape[0]) if comm.rank == 0 else 0, X.device)
+            if n0 <= 0:
+                raise ValueError("rank 0's first chunk holds no frames")
+        if comm.size > 1 and comm.rank != 0:
+            self.shift = torch.empty((int(X.shape[1]),), dtype=torch.float64, device=X.device)
+        else:
+            self.shift = torch.nan_to_num(X[0].to(torch.float64), nan=0.0).contiguous()
         if comm.size > 1:
             comm.broadcast(self.shift, src=0)
 
@@ -181,6 +194,15 @@ class TicaAccumulator:
         if self.shift is None:
             self._start(X)
         n = int(X.shape[0])
+        if n == 0:
+            # an empty shard still takes part in the first chunk's broadcasts (shift above, conditioning here)
+            if self.moments is None:
+                self.moments = torch.zeros((6, self.d), dtype=torch.float64, device=self.device)
+                self.moments[1].copy_(self.shift)
+                self.cond = torch.empty((2, self.d), dtype=torch.float32, device=self.device)
+                if comm.size > 1:
+                    comm.broadcast(self.cond, src=0)
+            return
         mask = kernels.pair_mask(segs.device(self.device), n, lag)
         with timer.stage("col_moments"):
             mom = kernels.col_moments(X, mask, self.shift)

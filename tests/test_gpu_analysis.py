@@ -114,3 +114,75 @@ def test_featurize_stream_from_dcd_matches_in_memory(tmp_path, topologies):
     ref = featurize_device(torch.from_numpy(DCDReader(path).read(0, 1350)).cuda(), plan)
     assert got.shape == (1350, plan.n_cols)
     assert torch.equal(got, ref)
+
+
+def _metastable_T(rng, n_blocks, size, eps):
+    K = n_blocks * size
+    C = np.zeros((K, K))
+    for b in range(n_blocks):
+        C[b * size:(b + 1) * size, b * size:(b + 1) * size] = rng.integers(20, 100, size=(size, size))
+    C = C + C.T
+    for b in range(n_blocks):                       # weak symmetric links between neighbouring blocks
+        i, j = b * size + size - 1, ((b + 1) % n_blocks) * size
+        C[i, j] += eps
+        C[j, i] += eps
+    pi = C.sum(axis=1) / C.sum()
+    return C / C.sum(axis=1, keepdims=True), pi
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_blocks,size", [(3, 5), (4, 40), (6, 25)])
+def test_pcca_memberships_match_oracle_and_recover_blocks(n_blocks, size):
+    """PCCA+ (macro.pcca_memberships: device eigenvectors + device inner simplex + host Nelder-Mead) against the
+    oracle's loop restatement of the published algorithm, and against the known answer of a nearly uncoupled
+    block matrix.  The optimiser's tolerances (fmin defaults, xtol = ftol = 1e-4) bound the agreement."""
+    from oracle import pcca as opcca
+    from pmarlo_b200 import macro
+
+    rng = np.random.default_rng(n_blocks * 100 + size)
+    T, pi = _metastable_T(rng, n_blocks, size, eps=1.0)
+    chi = macro.pcca_memberships(T, n_blocks, pi)
+    ref = opcca.pcca_memberships(T, n_blocks, pi)
+    assert chi.shape == (n_blocks * size, n_blocks)
+    np.testing.assert_allclose(chi.sum(axis=1), 1.0, atol=1e-12)
+    assert chi.min() >= 0.0
+    # columns may come out permuted relative to the oracle only if the simplex vertices differ: they must not
+    np.testing.assert_allclose(chi, ref, atol=2e-3)
+    hard = chi.argmax(axis=1)
+    for b in range(n_blocks):
+        assert len(set(hard[b * size:(b + 1) * size])) == 1          # one macrostate per block
+    assert len(set(hard)) == n_blocks
+    assert chi.max(axis=1).min() > 0.9
+    # pi omitted: computed on the device
+    np.testing.assert_allclose(macro.pcca_memberships(T, n_blocks), chi, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_pcca_like_macrostates_contract_and_ck_macro_branch():
+    """Reference contract of pcca_like_macrostates (_msm_utils.py:284-299): labels numbered by descending
+    population, None for a matrix with <= n_macrostates states or one PCCA+ rejects (irreversible / disconnected);
+    and the macrostate branch of run_ck with macro_lumper="pcca"."""
+    from pmarlo_b200 import ck, macro
+
+    rng = np.random.default_rng(5)
+    T, pi = _metastable_T(rng, 3, 6, eps=0.5)
+    lab = macro.pcca_like_macrostates(T, 3)
+    assert lab.shape == (18,) and set(lab) == {0, 1, 2}
+    pops = macro.compute_macro_populations(pi, lab)
+    assert np.all(np.diff(pops) <= 1e-12)                                # descending
+    assert macro.pcca_like_macrostates(T[:3, :3] / T[:3, :3].sum(1, keepdims=True), 4) is None
+    cyc = np.roll(np.eye(6), 1, axis=1) * 0.9 + np.eye(6) * 0.1          # irreversible cycle
+    assert macro.pcca_like_macrostates(cyc, 2) is None
+    two = np.kron(np.eye(2), np.full((3, 3), 1.0 / 3.0))                 # disconnected
+    assert macro.pcca_like_macrostates(two, 2) is None
+    # a three-well trajectory: the macro CK test runs on PCCA+ macrostates
+    K = 18
+    P = T
+    s = np.zeros(60000, dtype=np.int64)
+    cum = np.cumsum(P, axis=1)
+    u = rng.random(s.size)
+    for t in range(1, s.size):
+        s[t] = min(int(np.searchsorted(cum[s[t - 1]], u[t])), K - 1)
+    res = ck.run_ck([s], 5, None, macro_k=3, min_trans=20, macro_lumper="pcca")
+    assert res.mode == "macro" and len(res.mse) >= 1
+    assert all(np.isfinite(v) for v in res.mse.values())

@@ -306,3 +306,51 @@ def test_ck_selector_oracle_matches_reference(golden):
         ock.select_optimal_lag_ck_its([])
     with pytest.raises(ValueError, match="exceed the available trajectory length"):
         ock.select_optimal_lag_ck_its([np.array([0, 1, 0, 1])], tau_candidates=[10])
+
+
+def test_oracle_pcca_known_answers():
+    """oracle.pcca (PARITY UNPINNED against deeptime: restated from Roeblitz & Weber 2013 / the msmtools form):
+    nearly uncoupled blocks give indicator-like memberships; for m = 2 the membership is an affine function of
+    the second eigenvector reaching 0 and 1 at its extremes; rows sum to one."""
+    from oracle import pcca
+
+    rng = np.random.default_rng(2)
+    K, nb = 15, 3
+    C = np.zeros((K, K))
+    for b in range(nb):
+        C[5 * b:5 * b + 5, 5 * b:5 * b + 5] = rng.integers(30, 90, size=(5, 5))
+    C = C + C.T
+    C[4, 5] = C[5, 4] = 1.0
+    C[9, 10] = C[10, 9] = 1.0
+    C[0, 14] = C[14, 0] = 1.0
+    T = C / C.sum(axis=1, keepdims=True)
+    pi = C.sum(axis=1) / C.sum()
+    chi = pcca.pcca_memberships(T, 3, pi)
+    np.testing.assert_allclose(chi.sum(axis=1), 1.0, atol=1e-12)
+    hard = chi.argmax(axis=1)
+    assert [len(set(hard[5 * b:5 * b + 5])) for b in range(nb)] == [1, 1, 1] and len(set(hard)) == 3
+    assert chi.max(axis=1).min() > 0.95
+    # m = 2 on a birth-death chain: chi[:, j] = (r2 - min r2) / (max r2 - min r2) or its complement
+    n = 9
+    P = np.zeros((n, n))
+    for i in range(n):
+        up = 0.3 if i < n - 1 else 0.0
+        dn = 0.3 if i > 0 else 0.0
+        if i == 4:
+            up, dn = 0.02, 0.02
+        if i < n - 1:
+            P[i, i + 1] = up
+        if i > 0:
+            P[i, i - 1] = dn
+        P[i, i] = 1.0 - up - dn
+    # make it reversible: birth-death chains are; stationary distribution from detailed balance
+    pi2 = np.ones(n)
+    for i in range(1, n):
+        pi2[i] = pi2[i - 1] * P[i - 1, i] / P[i, i - 1]
+    pi2 /= pi2.sum()
+    chi2 = pcca.pcca_memberships(P, 2, pi2)
+    R = pcca.right_eigenvectors(P, pi2, 2)
+    r2 = R[:, 1]
+    aff = (r2 - r2.min()) / (r2.max() - r2.min())
+    err = min(np.abs(chi2[:, 0] - aff).max(), np.abs(chi2[:, 1] - aff).max())
+    assert err < 5e-3, err
