@@ -1,3 +1,5 @@
 set -x
-bash tools/run_gpu_round.sh
-bash tools/run_ncu_round.sh
+for i in 1 2; do
+python tools/km_bench.py c4 2>&1 | grep "^c4 n=" 
+PMB_LIB=build_exp/libpmb200_kmhead.so python tools/km_bench.py c4 2>&1 | grep "^c4 n="
+done
