@@ -234,3 +234,62 @@ def test_two_rank_gloo_streaming_accumulator_matches_oracle():
         np.testing.assert_allclose(r["C0t"], om.C0t, rtol=0, atol=1e-6 * np.abs(om.C0t).max())
         np.testing.assert_allclose(r["ev"][:3], om.eigenvalues[:3], atol=1e-6)
     np.testing.assert_allclose(r0["C00"], r1["C00"], rtol=0, atol=1e-14)
+
+
+# ----------------------------------------------------------------------------- empty shards
+def _empty_rank_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pmarlo_b200.distributed import Comm
+        from pmarlo_b200.pipeline import seeded_initial_centers
+        from pmarlo_b200.reduction import TICA
+        from pmarlo_b200.shards import Segments
+
+        fake_kernels.install(None)
+        feats = [f.copy() for f in _feats()]
+        feats[0][17, 2] = 0.25
+        cfg = _cfg()
+        comm = Comm()
+        # rank 1 holds NO frames: it must still take part in every broadcast of the first chunk
+        est = TICA(cfg.tica_lag, cfg.tica_dim, preprocess=cfg.preprocess, comm=comm)
+        acc = est.accumulator(feats[0].shape[1], torch.device("cpu"))
+        if rank == 0:
+            for f in feats:
+                acc.add(torch.from_numpy(f), Segments.from_lengths([f.shape[0]]))
+        else:
+            acc.add(torch.zeros((0, feats[0].shape[1]), dtype=torch.float32), Segments(np.zeros((1,), dtype=np.int64)))
+        m = acc.finish()
+        # a rank-0 shard that is too small for the seeding raises on EVERY rank instead of deadlocking the others
+        Y = torch.zeros((3 if rank == 0 else 50, 2), dtype=torch.float32)
+        try:
+            seeded_initial_centers(Y, 9, 0, comm)
+            raised = 0
+        except ValueError:
+            raised = 1
+        np.savez(f"{out_path}.{rank}.npz", C00=m.C00.numpy(), ev=m.eigenvalues.numpy(), n_pairs=m.n_pairs, raised=raised)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_empty_shard_and_collective_validation():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "res")
+        mp.spawn(_empty_rank_worker, args=(2, port, out), nprocs=2, join=True)
+        r0, r1 = np.load(out + ".0.npz"), np.load(out + ".1.npz")
+    feats = [f.copy() for f in _feats()]
+    feats[0][17, 2] = 0.25
+    om = _oracle(feats, _c0(feats))[0]
+    for r in (r0, r1):
+        assert int(r["n_pairs"]) == om.n_pairs and int(r["raised"]) == 1
+        np.testing.assert_allclose(r["C00"], om.C00, rtol=0, atol=1e-6 * np.abs(om.C00).max())
+        np.testing.assert_allclose(r["ev"][:3], om.eigenvalues[:3], atol=1e-6)
