@@ -230,7 +230,10 @@ def _save_outputs(result: CKRunResult, out: Path) -> None:
 def _resolve_lumper(macro_lumper):
     """``macro_lumper="pcca"`` selects this package's PCCA+ (`macro.pcca_like_macrostates`, what the reference
     calls at ck_runner.py:196-203 / ck_its_selector.py:300-330); a callable is used as given; None disables the
-    macrostate branch (the reference's behaviour when PCCA+ returns None)."""
+    macrostate branch (the reference's behaviour when PCCA+ returns None).  Note that PCCA+ -- deeptime's as well --
+    rejects a transition matrix without detailed balance, which the row-normalised count matrices of this module
+    are unless the counts happen to be symmetric: with "pcca" the macrostate branch then reports "not feasible",
+    exactly as in the reference."""
     if isinstance(macro_lumper, str):
         if macro_lumper != "pcca":
             raise ValueError(f"unknown macro_lumper {macro_lumper!r}")

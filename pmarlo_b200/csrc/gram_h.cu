@@ -45,8 +45,9 @@
 // they save -- the same finding as the cta_group::2 variant of gram_tc.cu, from the other side.
 //
 // One CTA per (128-row block of G, frame chunk): 148 CTAs = 2 row blocks x 74 chunks for d = 256.
-//   warps 0-15 producers: warp w = frame w of the stage; a lane owns features [4 L, 4 L + 4) and [128 + 4 L, ...):
-//              two conflict-free 16-byte reads of the raw row, six conflict-free 8-byte stores; drains
+//   warps 0-15 producers: two teams of eight warps take alternate stages, a warp converts frames w and w + 8 of its
+//              stage; a lane owns features [4 L, 4 L + 4) and [128 + 4 L, ...): two conflict-free 16-byte reads of
+//              the raw row, six conflict-free 8-byte stores per frame; all sixteen warps drain
 //   warp  16   MMA issuer: 4 tcgen05.mma (M = 128, N = d, K = 16) + 1 commit per stage from one elected block
 //   warp  17   loader: bulk copies of raw rows, kGhRawStages ahead
 #include <cuda_fp16.h>
@@ -127,7 +128,7 @@ struct GhBars {
   uint32_t n_active;
   volatile uint32_t drain_seq;    // number of drains requested so far (written by the MMA warp)
   volatile uint32_t finished;     // 0 while running; total number of drains + 1 once the last one is requested
-  uint32_t budget[kGhStages][kGhProdWarps];
+  uint32_t budget[kGhStages][kGhProdWarps / 2];
 };
 
 // iterator over the set bits of the stage bitmap (every role walks the same sequence)
@@ -194,12 +195,12 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
   for (int i = tid; i < n_words; i += kGhThreads) bitmap[i] = 0u;
   if (tid == 0) {
     for (int s = 0; s < kGhStages; ++s) {
-      mbar_init(&B->full[s], kGhProdWarps);
+      mbar_init(&B->full[s], kGhProdWarps / 2);
       mbar_init(&B->empty[s], 1);
     }
     for (int s = 0; s < kGhRawStages; ++s) {
       mbar_init(&B->raw_full[s], 1);
-      mbar_init(&B->raw_empty[s], kGhProdWarps);
+      mbar_init(&B->raw_empty[s], kGhProdWarps / 2);
     }
     mbar_init(&B->wdone, 1);
     mbar_init(&B->drained, kGhProdWarps);
@@ -243,7 +244,6 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
 
   if (warp < kGhProdWarps) {
     // ============================================================ producers
-    const int fr = warp;              // frame within the stage
     const int cA = lane * 4, cB = 128 + lane * 4;
     const bool okA = cA < d, okB = cB < d;
     float sh[8], sc[8];
@@ -274,17 +274,12 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
     GhIter it;
     it.init(bitmap, n_words);
     bool bad = false;     // some |z| does not fit the fp16 residual (or is not finite)
-    int slot = 0, rslot = 0;
-    uint32_t use = 0, ruse = 0;
-    for (int a = 0; a < n_active; ++a) {
-      const int s = it.next();
-      const int64_t g = g_begin + (int64_t)s * kGhBK + fr;
-      // raw rows and the stage's mask bytes -> registers (no global access on this path)
-      GH_T(t0);
-      mbar_wait(&B->raw_full[rslot], ruse & 1u);
-      GH_T(t1);
-      GH_ACC(0, t0, t1);
-      const unsigned char* R0 = raw + (size_t)rslot * kGhRawStageBytes;
+    // Two teams of eight warps take alternate stages; a warp converts TWO frames of its stage (wi and wi + 8) one
+    // after the other, so the per-stage costs that do not depend on the amount of data (three barrier
+    // round trips, the proxy fence, the loop bookkeeping) are paid once per two frames.
+    const int team = warp >> 3, wi = warp & 7;
+    // one frame: raw row -> the three packed tile rows (8 features per lane); returns max |k|
+    auto convert = [&](const unsigned char* R0, int fr, int64_t g, uint2 (&wa)[2], uint2 (&wh)[2], uint2 (&wl)[2]) -> uint32_t {
       const bool sel_now = (g < g_end) && gh_selected((int)R0[2 * kGhRawBlock + fr], p.sel);
       const unsigned char* R = R0 + (size_t)fr * row_bytes;
       float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa, ya = xa, yb = xa;
@@ -294,10 +289,6 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
         if (okA) ya = *reinterpret_cast<const float4*>(R + kGhRawBlock + cA * 4);
         if (okB) yb = *reinterpret_cast<const float4*>(R + kGhRawBlock + cB * 4);
       }
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&B->raw_empty[rslot]);
-      if (++rslot == kGhRawStages) { rslot = 0; ++ruse; }
-
       // one dither per frame (hash of the frame index): E[r | z] = 0, see gram_tc.cu
       float dith;
       {
@@ -351,7 +342,6 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
         }
         m = (uint32_t)kGhKMax;
       }
-      uint2 wa[2], wh[2], wl[2];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float r0 = fmaf(kq[2 * q], -0.5f, z4[2 * q]);          // r' = 4 z - k / 2 = 4 (z - k / 8), exact
@@ -367,12 +357,9 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
         *ph = *reinterpret_cast<const uint32_t*>(&h2);
         *pl = *reinterpret_cast<const uint32_t*>(&l2);
       }
-      GH_T(t2);
-      wait_serving(&B->empty[slot], (use & 1u) ^ 1u);
-      GH_T(t3);
-      GH_ACC(1, t2, t3);
-      GH_ACC(2, t1, t2);
-      unsigned char* T = tiles + (size_t)slot * kGhStageBytes;
+      return m;
+    };
+    auto store = [&](unsigned char* T, int fr, const uint2 (&wa)[2], const uint2 (&wh)[2], const uint2 (&wl)[2]) {
       if (okA) {
         const uint32_t o = gh_off(cA, fr);
         *reinterpret_cast<uint2*>(T + o) = wa[0];
@@ -385,11 +372,36 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
         *reinterpret_cast<uint2*>(T + kGhTile + o) = wh[1];
         *reinterpret_cast<uint2*>(T + 2 * kGhTile + o) = wl[1];
       }
-      if (lane == 0) B->budget[slot][warp] = m * m;
+    };
+    for (int a = 0; a < n_active; ++a) {
+      const int s = it.next();
+      if ((a & 1) != team) continue;
+      const int slot = a % kGhStages, rslot = a % kGhRawStages;
+      const uint32_t use = (uint32_t)(a / kGhStages), ruse = (uint32_t)(a / kGhRawStages);
+      const int64_t g0 = g_begin + (int64_t)s * kGhBK;
+      // raw rows and the stage's mask bytes (no global access on this path)
+      GH_T(t0);
+      mbar_wait(&B->raw_full[rslot], ruse & 1u);
+      GH_T(t1);
+      GH_ACC(0, t0, t1);
+      const unsigned char* R0 = raw + (size_t)rslot * kGhRawStageBytes;
+      unsigned char* T = tiles + (size_t)slot * kGhStageBytes;
+      uint2 wa[2], wh[2], wl[2];
+      const uint32_t m0 = convert(R0, wi, g0 + wi, wa, wh, wl);
+      GH_T(t2);
+      wait_serving(&B->empty[slot], (use & 1u) ^ 1u);
+      GH_T(t3);
+      GH_ACC(1, t2, t3);
+      GH_ACC(2, t1, t2);
+      store(T, wi, wa, wh, wl);
+      const uint32_t m1 = convert(R0, wi + 8, g0 + wi + 8, wa, wh, wl);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&B->raw_empty[rslot]);      // both rows are in registers
+      store(T, wi + 8, wa, wh, wl);
+      if (lane == 0) B->budget[slot][wi] = m0 * m0 + m1 * m1;
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&B->full[slot]);
-      if (++slot == kGhStages) { slot = 0; ++use; }
     }
     if (n_active == 0) {
       for (int i = tid; i < 2 * d * 128; i += kGhProdWarps * 32) ws[i] = 0.0;
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(kGhThreads, 1) gram_h_kernel(GramHParams p) {
       mbar_wait(&B->full[slot], use & 1u);
       GH_T(m1);
       GH_ACC(0, m0, m1);
-      const uint32_t b = __reduce_add_sync(0xffffffffu, lane < kGhProdWarps ? B->budget[slot][lane] : 0u);
+      const uint32_t b = __reduce_add_sync(0xffffffffu, lane < kGhProdWarps / 2 ? B->budget[slot][lane] : 0u);
       if (in_window > 0 && (spent + b > kGhBudget || in_window == max_stages)) {
         GH_T(m2);
         close_window();

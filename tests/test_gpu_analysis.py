@@ -183,6 +183,18 @@ def test_pcca_like_macrostates_contract_and_ck_macro_branch():
     u = rng.random(s.size)
     for t in range(1, s.size):
         s[t] = min(int(np.searchsorted(cum[s[t - 1]], u[t])), K - 1)
+    # The row-normalised count matrix run_ck lumps is not reversible, and PCCA+ (deeptime's as well) insists on
+    # detailed balance: the reference's wrapper turns that ValueError into None and the microstate test runs.
     res = ck.run_ck([s], 5, None, macro_k=3, min_trans=20, macro_lumper="pcca")
+    assert res.mode == "micro" and len(res.mse) >= 1
+
+    def reversibilised_pcca(Tm, k):
+        w, V = np.linalg.eig(Tm.T)
+        p = np.abs(np.real(V[:, np.argmax(np.real(w))]))
+        F = (p / p.sum())[:, None] * Tm
+        Fs = 0.5 * (F + F.T)
+        return macro.pcca_like_macrostates(Fs / Fs.sum(axis=1, keepdims=True), k)
+
+    res = ck.run_ck([s], 5, None, macro_k=3, min_trans=20, macro_lumper=reversibilised_pcca)
     assert res.mode == "macro" and len(res.mse) >= 1
     assert all(np.isfinite(v) for v in res.mse.values())
