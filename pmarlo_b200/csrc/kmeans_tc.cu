@@ -95,8 +95,14 @@ struct KmTcParams {
   int* recheck_list;    // n entries
   int* recheck_count;   // zeroed by the host wrapper
   double* ysq;          // sum over frames of |y|^2 (zeroed by the host wrapper)
-  double* lsums;        // K x D, this call's sums (zeroed by the host wrapper)
-  unsigned long long* lcounts;   // K
+  // This call's sums / counts: `ncopies` private copies of [K x D sums | K counts] (zeroed by the host wrapper),
+  // CTA b accumulates into copy b % ncopies.  All CTAs adding into ONE copy serialise on the L2 atomic unit (every
+  // address takes ~10^4 adds per launch); copies at distinct addresses do not, and the commit kernel adds them up
+  // in a fixed order.
+  double* lsums;        // copy 0: K x D
+  unsigned long long* lcounts;   // copy 0: K
+  int ncopies;
+  size_t copy_stride;   // in 8-byte words
   int accumulate;       // sums / counts / inertia requested
   float* dbg_scores;    // n x Kpad (tests only) or nullptr
   // written by kmeans_tc_prep_kernel
@@ -702,6 +708,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     // fused Lloyd accumulation
     const int pt = tid - kTcFinWarp0 * 32;
     constexpr bool in_regs = INREG;
+    double* const my_sums = p.lsums + (size_t)(blockIdx.x % p.ncopies) * p.copy_stride;
+    unsigned long long* const my_counts = p.lcounts + (size_t)(blockIdx.x % p.ncopies) * p.copy_stride;
     int recheck_acc = 0;
     KM_DECL;
     float yn[kTcDReg];   // UNSCALED coordinates (they feed the Lloyd sums)
@@ -784,25 +792,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
 #pragma unroll
               for (int r = 0; r < 16; ++r) acc += (double)stg[(r0 + r) * (kTcDReg + 1) + dd];
               acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-              if (lane < D) atomicAdd(p.lsums + (size_t)lab0 * D + lane, acc);
+              if (lane < D) atomicAdd(my_sums + (size_t)lab0 * D + lane, acc);
               __syncwarp();
             } else {
               for (int d = 0; d < D; ++d) {
                 const double v = warp_sum((double)p.Y[row * p.ld + d]);
-                if (lane == 0) atomicAdd(p.lsums + (size_t)lab0 * D + d, v);
+                if (lane == 0) atomicAdd(my_sums + (size_t)lab0 * D + d, v);
               }
             }
-            if (lane == 0) atomicAdd(p.lcounts + lab0, 32ull);
+            if (lane == 0) atomicAdd(my_counts + lab0, 32ull);
           }
         } else if (lab >= 0) {
           if constexpr (in_regs) {
 #pragma unroll
             for (int d = 0; d < kTcDReg; ++d)
-              if (d < D) atomicAdd(p.lsums + (size_t)lab * D + d, (double)y[d]);
+              if (d < D) atomicAdd(my_sums + (size_t)lab * D + d, (double)y[d]);
           } else {
-            for (int d = 0; d < D; ++d) atomicAdd(p.lsums + (size_t)lab * D + d, (double)p.Y[row * p.ld + d]);
+            for (int d = 0; d < D; ++d) atomicAdd(my_sums + (size_t)lab * D + d, (double)p.Y[row * p.ld + d]);
           }
-          atomicAdd(p.lcounts + lab, 1ull);
+          atomicAdd(my_counts + lab, 1ull);
         }
       }
       KM_T(f2);
@@ -860,6 +868,23 @@ __global__ void __launch_bounds__(256) kmeans_recheck_kernel(KmTcParams p) {
     }
     if (p.accumulate)
       for (int d = lane; d < D; d += 32) atomicAdd(p.lsums + (size_t)bk * D + d, (double)p.Y[row * p.ld + d]);
+  }
+}
+
+// Fold the private accumulator copies into copy 0, in a fixed order (one thread per accumulator word; adjacent
+// threads read adjacent words of every copy).
+__global__ void __launch_bounds__(256) kmeans_tc_fold_kernel(KmTcParams p) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n_sum = (size_t)p.K * p.D, n_all = n_sum + (size_t)p.K;
+  if (e >= n_all) return;
+  if (e < n_sum) {
+    double v = 0.0;
+    for (int c = 0; c < p.ncopies; ++c) v += p.lsums[(size_t)c * p.copy_stride + e];
+    p.lsums[e] = v;
+  } else {
+    unsigned long long v = 0;
+    for (int c = 0; c < p.ncopies; ++c) v += p.lcounts[(size_t)c * p.copy_stride + (e - n_sum)];
+    p.lcounts[e - n_sum] = v;
   }
 }
 
@@ -925,11 +950,17 @@ bool kmeans_tc_supported(int D, int K) {
 }
 
 static inline size_t tc_align256(size_t x) { return (x + 255) / 256 * 256; }
+// private accumulator copies: one per CTA while they stay below 16 MB in total (zeroed every call)
+static inline size_t tc_copy_bytes(int D, int K) { return tc_align256(((size_t)K * D + K) * sizeof(double)); }
+static inline int tc_ncopies(int D, int K) {
+  const size_t fit = ((size_t)16 << 20) / tc_copy_bytes(D, K);
+  return fit >= (size_t)kNumSMs ? kNumSMs : (fit < 1 ? 1 : (int)fit);
+}
 
 size_t kmeans_tc_ws_bytes(int64_t n, int D, int K) {
-  // [count | ysq | meta | pad to 256 B][local sums K x D][local counts K][scaled centres K x D fp32]
+  // [count | ysq | meta | pad to 256 B][ncopies x (local sums K x D, local counts K)][scaled centres K x D fp32]
   // [centre operand image Kpad x KS fp16][re-check list n]
-  return 256 + tc_align256(((size_t)K * D + K) * sizeof(double)) + tc_align256((size_t)K * D * sizeof(float)) +
+  return 256 + (size_t)tc_ncopies(D, K) * tc_copy_bytes(D, K) + tc_align256((size_t)K * D * sizeof(float)) +
          tc_align256((size_t)tc_kpad(K) * tc_slots(D) * 2) + (size_t)n * sizeof(int) + 256;
 }
 
@@ -948,7 +979,9 @@ int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double*
   size_t off = 256;
   p.lsums = reinterpret_cast<double*>(w8 + off);
   p.lcounts = reinterpret_cast<unsigned long long*>(p.lsums + (size_t)K * D);
-  off += tc_align256(((size_t)K * D + K) * sizeof(double));
+  p.ncopies = tc_ncopies(D, K);
+  p.copy_stride = tc_copy_bytes(D, K) / 8;
+  off += (size_t)p.ncopies * tc_copy_bytes(D, K);
   p.cs32 = reinterpret_cast<float*>(w8 + off);
   off += tc_align256((size_t)K * D * sizeof(float));
   p.Bg = w8 + off;
@@ -959,7 +992,7 @@ int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double*
   PMB_REQUIRE(n < (int64_t)0x7fffffff, "pmb_kmeans_assign: tensor path needs n < 2^31");
   PMB_REQUIRE(p.nslots > 0, "pmb_kmeans_assign: D=%d does not fit the tensor path's shared memory", D);
   const size_t smem = (size_t)p.nslots * tc_chunk_bytes(D) + tc_fixed_smem(D);
-  PMB_CUDA(cudaMemsetAsync(ws, 0, 256 + (p.accumulate ? ((size_t)K * D + K) * sizeof(double) : 0), st));
+  PMB_CUDA(cudaMemsetAsync(ws, 0, 256 + (p.accumulate ? (size_t)p.ncopies * tc_copy_bytes(D, K) : 0), st));
   kmeans_tc_prep_kernel<<<1, 1024, 0, st>>>(p);
   PMB_LAUNCH_CHECK();
   const int64_t n_tiles = (n + kTcTile - 1) / kTcTile;
@@ -977,6 +1010,11 @@ int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double*
   kmeans_recheck_kernel<<<2 * kNumSMs, 256, 0, st>>>(p);
   PMB_LAUNCH_CHECK();
   if (p.accumulate) {
+    if (p.ncopies > 1) {
+      const size_t n_all = (size_t)K * D + K;
+      kmeans_tc_fold_kernel<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(p);
+      PMB_LAUNCH_CHECK();
+    }
     kmeans_tc_commit_kernel<<<(K + 255) / 256 < 64 ? (K + 255) / 256 : 64, 256, 0, st>>>(p);
     PMB_LAUNCH_CHECK();
   }

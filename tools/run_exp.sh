@@ -1,4 +1,3 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_analysis.py -x -q -m gpu -k "gram or tica or pipeline_small or host_buffer or pcca" > gpurun_out/t_gram.log 2>&1; echo "pytest=$?"; tail -n 5 gpurun_out/t_gram.log
-timeout 300 python tools/gram_bench.py 10000000 5 > gpurun_out/gram_bench.log 2>&1; echo "gb=$?"; cat gpurun_out/gram_bench.log
-timeout 300 python tools/gram_accuracy.py > gpurun_out/gram_acc.log 2>&1; echo "acc=$?"; grep "impl=5" gpurun_out/gram_acc.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -x -q -m gpu -k "kmeans or assign or cluster or c5_assignment or nan_and_inf or pipeline_small" > gpurun_out/t_km.log 2>&1; echo "pytest=$?"; tail -n 5 gpurun_out/t_km.log
+python tools/km_bench.py c4 > gpurun_out/km_plain.log 2>&1; echo "km_plain=$?"; cat gpurun_out/km_plain.log
