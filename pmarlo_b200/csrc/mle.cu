@@ -294,8 +294,12 @@ __device__ long long g_dbg[8];  // phase cycle counters of the last grid-kernel 
 // The kernel keeps the fp64 work per matrix element at 4 instructions (add, 2 Newton FMAs, accumulate
 // FMA; B200 issues 57 fp64 FMA/clk/SM, profiles/r01a_ubench.log); an iteration is bound by the
 // latency of the K-vector exchange between the CTAs.
+// The streamed variant (REG = false: K > 1024, the rows of S come from L2 / HBM every iteration) runs 1024 threads
+// per CTA with four independent loads in flight per lane: with 256 threads and two loads it reached 0.96 TB/s at
+// K = 5000 (latency-bound: 0.6 MB in flight on the whole GPU), the 200 MB of S per iteration want HBM speed.
+constexpr int kMleStreamThreads = 1024;
 template <bool REG>
-__global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) {
+__global__ void __launch_bounds__(REG ? kMleGridThreads : kMleStreamThreads) mle_grid_kernel(MleParams p) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double s_red[32];
   const int K = p.K;
@@ -349,6 +353,15 @@ __global__ void __launch_bounds__(kMleGridThreads) mle_grid_kernel(MleParams p) 
     } else {
       const double* __restrict__ Srow = p.S + (size_t)i * K;
       int j = lane;
+      // four loads in flight; the accumulation order (even entries -> a0, odd -> a1) is that of the two-at-a-time
+      // loop it replaces, so the iterates are bit-identical
+      for (; j + 96 < K; j += 128) {
+        const double s0 = __ldcs(Srow + j), s1 = __ldcs(Srow + j + 32), s2 = __ldcs(Srow + j + 64), s3 = __ldcs(Srow + j + 96);
+        a0 = fma(s0, rcp_newton1(qi + q[j], qfi + qf[j]), a0);
+        a1 = fma(s1, rcp_newton1(qi + q[j + 32], qfi + qf[j + 32]), a1);
+        a0 = fma(s2, rcp_newton1(qi + q[j + 64], qfi + qf[j + 64]), a0);
+        a1 = fma(s3, rcp_newton1(qi + q[j + 96], qfi + qf[j + 96]), a1);
+      }
       for (; j + 32 < K; j += 64) {
         const double s0 = Srow[j], s1 = Srow[j + 32];
         a0 = fma(s0, rcp_newton1(qi + q[j], qfi + qf[j]), a0);
@@ -540,7 +553,13 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
   int dev = 0, sms = 0;
   PMB_CUDA(cudaGetDevice(&dev));
   PMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int warps_per_cta = kMleGridThreads / 32;
+  const bool streamed = K > 1024;
+  const int threads = streamed ? kMleStreamThreads : kMleGridThreads;
+  if (streamed) {
+    PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mle_grid_kernel<false>, threads, smem));
+    PMB_REQUIRE(per_sm >= 1, "pmb_mle_rev: the streamed kernel does not fit on an SM");
+  }
+  const int warps_per_cta = threads / 32;
   int grid = (K + warps_per_cta - 1) / warps_per_cta;
   if (grid > sms * per_sm) grid = sms * per_sm;
   if (grid > sms) grid = sms;  // one CTA per SM
@@ -554,9 +573,9 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
     pb.cvec = p.cvec + (size_t)b * K;
     PMB_CUDA(cudaMemsetAsync(p.ubuf, 0, (size_t)4 * K * sizeof(double), st));   // tags start at 1
     void* args[] = {&pb};
-    const bool reg = (K <= 1024) && ((long long)grid * warps_per_cta >= K);
+    const bool reg = !streamed && ((long long)grid * warps_per_cta >= K);
     PMB_CUDA(cudaLaunchCooperativeKernel(reg ? (void*)mle_grid_kernel<true> : (void*)mle_grid_kernel<false>,
-                                         dim3(grid), dim3(kMleGridThreads), args,
+                                         dim3(grid), dim3(threads), args,
                                          smem, st));
     count_launch();
   }
