@@ -294,9 +294,11 @@ __device__ long long g_dbg[8];  // phase cycle counters of the last grid-kernel 
 // The kernel keeps the fp64 work per matrix element at 4 instructions (add, 2 Newton FMAs, accumulate
 // FMA; B200 issues 57 fp64 FMA/clk/SM, profiles/r01a_ubench.log); an iteration is bound by the
 // latency of the K-vector exchange between the CTAs.
-// The streamed variant (REG = false: K > 1024, the rows of S come from L2 / HBM every iteration) runs 1024 threads
-// per CTA with four independent loads in flight per lane: with 256 threads and two loads it reached 0.96 TB/s at
-// K = 5000 (latency-bound: 0.6 MB in flight on the whole GPU), the 200 MB of S per iteration want HBM speed.
+// The streamed variant (REG = false: K > 1024, the rows of S come from L2 / HBM every iteration) runs up to 1024
+// threads per CTA with eight independent loads in flight per lane: with 256 threads and two loads it reached
+// 0.96 TB/s at K = 5000 (latency-bound: 0.6 MB in flight on the whole GPU), the 200 MB of S per iteration want HBM
+// speed.  The launcher sizes the CTAs so that every warp owns the same number of rows (K = 5000: 17 warps per CTA,
+// two rows each): a last round with a few busy warps is latency-bound again and costs as much as a full one.
 constexpr int kMleStreamThreads = 1024;
 template <bool REG>
 __global__ void __launch_bounds__(REG ? kMleGridThreads : kMleStreamThreads) mle_grid_kernel(MleParams p) {
@@ -353,14 +355,17 @@ __global__ void __launch_bounds__(REG ? kMleGridThreads : kMleStreamThreads) mle
     } else {
       const double* __restrict__ Srow = p.S + (size_t)i * K;
       int j = lane;
-      // four loads in flight; the accumulation order (even entries -> a0, odd -> a1) is that of the two-at-a-time
+      // eight loads in flight; the accumulation order (even entries -> a0, odd -> a1) is that of the two-at-a-time
       // loop it replaces, so the iterates are bit-identical
-      for (; j + 96 < K; j += 128) {
-        const double s0 = __ldcs(Srow + j), s1 = __ldcs(Srow + j + 32), s2 = __ldcs(Srow + j + 64), s3 = __ldcs(Srow + j + 96);
-        a0 = fma(s0, rcp_newton1(qi + q[j], qfi + qf[j]), a0);
-        a1 = fma(s1, rcp_newton1(qi + q[j + 32], qfi + qf[j + 32]), a1);
-        a0 = fma(s2, rcp_newton1(qi + q[j + 64], qfi + qf[j + 64]), a0);
-        a1 = fma(s3, rcp_newton1(qi + q[j + 96], qfi + qf[j + 96]), a1);
+      for (; j + 224 < K; j += 256) {
+        double sv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sv[u] = __ldcs(Srow + j + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          a0 = fma(sv[u], rcp_newton1(qi + q[j + 32 * u], qfi + qf[j + 32 * u]), a0);
+          a1 = fma(sv[u + 1], rcp_newton1(qi + q[j + 32 * u + 32], qfi + qf[j + 32 * u + 32]), a1);
+        }
       }
       for (; j + 32 < K; j += 64) {
         const double s0 = Srow[j], s1 = Srow[j + 32];
@@ -554,7 +559,14 @@ extern "C" int pmb_mle_rev(const double* C, const uint8_t* active, int K, int ba
   PMB_CUDA(cudaGetDevice(&dev));
   PMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const bool streamed = K > 1024;
-  const int threads = streamed ? kMleStreamThreads : kMleGridThreads;
+  int threads = kMleGridThreads;
+  if (streamed) {
+    const int max_warps = sms * (kMleStreamThreads / 32);
+    const int rounds = (K + max_warps - 1) / max_warps;                  // rows per warp
+    int wpc = (K + rounds * sms - 1) / (rounds * sms);                   // warps per CTA that make the rounds even
+    wpc = wpc < 4 ? 4 : (wpc > kMleStreamThreads / 32 ? kMleStreamThreads / 32 : wpc);
+    threads = wpc * 32;
+  }
   if (streamed) {
     PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mle_grid_kernel<false>, threads, smem));
     PMB_REQUIRE(per_sm >= 1, "pmb_mle_rev: the streamed kernel does not fit on an SM");
