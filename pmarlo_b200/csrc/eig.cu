@@ -6,9 +6,10 @@
 //  * K <= kEigJacobiMaxK: A is formed explicitly and handed to the batched
 //    one-sided Jacobi solver of tica.cu (one CTA per matrix) -- the ITS sweep
 //    path, one CTA per lag time;
-//  * larger K: Lanczos with periodic re-orthogonalisation (two consecutive full
-//    two-pass Gram-Schmidt steps out of eight, the three-term recurrence in
-//    between) in ONE cooperative kernel: the mat-vec streams T once per step
+//  * larger K: Lanczos with partial re-orthogonalisation (pairs of full
+//    two-pass Gram-Schmidt steps whenever a scalar bound on the lost
+//    orthogonality nears sqrt(eps), the three-term recurrence in between) in
+//    ONE cooperative kernel: the mat-vec streams T once per step
 //    (8 K^2 bytes, L2-resident for K = 1000), a step costs 3-5 grid barriers and
 //    is latency-bound; the Ritz values of the m x m
 //    tridiagonal matrix come from Sturm-sequence bisection (one thread per
@@ -23,7 +24,8 @@ namespace cg = cooperative_groups;
 namespace pmb {
 
 constexpr int kEigJacobiMaxK = 256;
-constexpr int kLanPeriod = 8;   // re-orthogonalisation period (see lanczos_kernel)
+constexpr double kLanOmegaReset = 1e-15;  // orthogonality level right after a pair of full steps
+constexpr double kLanOmegaMax = 1e-8;     // semi-orthogonality bound (sqrt(eps)) that local steps must keep
 constexpr int kLanThreads = 256;
 
 int sym_eigvals_launch(double* A, int n, int batch, double* evals, double* scratch, int* order,
@@ -202,13 +204,20 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
   // `binv` its scale, and phase A of step j both stores V[j] = binv w_cur and applies the operator to it.
   double binv = 1.0 / nrm;
 
-  // Re-orthogonalisation schedule (periodic, Grcar / Simon): two consecutive steps out of every kLanPeriod
-  // orthogonalise w against ALL previous vectors, twice (CGS2, "twice is enough"); the steps in between only
-  // against v_{j-1} and v_j (the three-term recurrence).  Orthogonality lost to a converged Ritz vector grows
-  // by a bounded factor per step, so it stays far below sqrt(eps) over the 6 local steps and is reset to eps
-  // by the pair of full steps; the Ritz values of T_m keep full accuracy (semi-orthogonality suffices).
-  // A full step costs 5 grid barriers, a local one 3 (it was 6 for every step).
+  // Re-orthogonalisation schedule (partial, after Simon): a pair of consecutive steps orthogonalises w against
+  // ALL previous vectors, twice (CGS2, "twice is enough"); the steps in between only against v_{j-1} and v_j
+  // (the three-term recurrence).  In a local step the orthogonality lost to a converged Ritz vector grows by at
+  // most g_j = (max_k |a_k| + |a_j| + 2 max_k b_k) / b_j (the omega recurrence with every term at its bound), so
+  // a scalar `omega` carries the bound: reset to ~eps by a full pair, multiplied by g_j per local step, and the
+  // next full pair starts when one more local step could pass sqrt(eps) -- semi-orthogonality, which keeps the
+  // Ritz values of T_m at full accuracy.  g_j is 1 / (the relative width of the bulk spectrum): ~40 for the
+  // K = 1000 bench matrix (4 local steps per pair), ~55 for K = 2000..5000, where a fixed period of 8 lost
+  // orthogonality completely after ~100 steps (55^6 eps = 3e-6 per period) and the projections diverged.
+  // Every thread evaluates the rule on the same numbers: uniform without a barrier.
+  // A full step costs 5 grid barriers, a local one 3.
   int m_eff = 0;
+  double omega = kLanOmegaReset, g_last = 1.0, a_max = 0.0, b_max = 0.0;
+  int full_left = 2;
   for (int j = 0; j < p.m; ++j) {
     const double* wc = w_cur;
     double* wn = w_new;
@@ -237,7 +246,8 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
       if (lane == 0) wn[i] = s;
     }
     grid.sync();
-    const bool full = (j < 2) || (j % kLanPeriod) >= kLanPeriod - 2;
+    if (full_left == 0 && omega * 1.5 * g_last > kLanOmegaMax) full_left = 2;
+    const bool full = full_left > 0;
     const int i_lo = full ? 0 : (j > 0 ? j - 1 : 0);
     const int npass = full ? 2 : 1;
     double a_j = 0.0;
@@ -285,6 +295,10 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
     if (gtid == 0) { p.alpha[j] = a_j; p.beta[j] = b_j; }
     if (tid == 0) { s_alpha[j] = a_j; s_beta[j] = b_j; }
     m_eff = j + 1;
+    a_max = fmax(a_max, fabs(a_j));
+    b_max = fmax(b_max, b_j);
+    g_last = fmax(1.0, (a_max + fabs(a_j) + 2.0 * b_max) / b_j);
+    if (full) { if (--full_left == 0) omega = kLanOmegaReset; } else omega = fmin(omega * g_last, 1.0);
     if (!(b_j > 1e-13) || j + 1 == p.m) break;  // invariant subspace / done (uniform across the grid)
     // Convergence checkpoint: the k leading (by magnitude) Ritz values of T_{j+1} against those of the previous
     // checkpoint, 16 steps earlier.  Every CTA evaluates it on its own copy of the recurrence with the same

@@ -380,9 +380,11 @@ def test_ck_host_logic_fuzz_against_oracle(monkeypatch):
 def test_numpy_models_of_two_kernel_algorithms():
     """CPU models of two algorithmic choices made inside kernels, so that the claims in DESIGN.md are checked
     without a GPU:
-    (1) eig.cu: Lanczos with periodic re-orthogonalisation (2 full CGS2 steps out of 8, three-term recurrence
-        in between, the schedule of lanczos_kernel) gives the Ritz values of full re-orthogonalisation on a
-        clustered spectrum; without any re-orthogonalisation a ghost copy of the top eigenvalue appears;
+    (1) eig.cu: Lanczos with partial re-orthogonalisation (pairs of full CGS2 steps placed by the scalar omega
+        bound of lanczos_kernel, three-term recurrence in between) gives the Ritz values of full
+        re-orthogonalisation on a clustered spectrum and on a narrow-bulk matrix (K = 2000, relative bulk width
+        ~1/50) where a fixed period of 8 loses orthogonality completely; without any re-orthogonalisation a
+        ghost copy of the top eigenvalue appears;
     (2) tica_grid.cu: the division-free Jacobi rotation c^2 = (1 + |alpha|/r)/2, s = sign(alpha) g / (2 r c)
         orthogonalises two rows, and the carried squared norms follow a' = a - t g, b' = b + t g."""
     rng = np.random.default_rng(0)
@@ -392,15 +394,24 @@ def test_numpy_models_of_two_kernel_algorithms():
     S = (Q * lam) @ Q.T
     S = 0.5 * (S + S.T)
 
-    def lanczos(m, period, all_full=False):
+    def lanczos(S, m, mode):
+        # mode: "full" | "partial" (the kernel's rule) | "period8" (the rule it replaced) | "none"
+        K = S.shape[0]
         V = np.zeros((m + 1, K))
         w = 1.0 + 0.5 * np.sin(0.7548776662466927 * np.arange(1, K + 1))
         binv = 1.0 / np.linalg.norm(w)
         alpha, beta = np.zeros(m), np.zeros(m)
+        omega, g_last, a_max, b_max, full_left, n_full = 1e-15, 1.0, 0.0, 0.0, 2, 0
         for j in range(m):
             V[j] = w * binv
             wn = S @ V[j]
-            full = all_full or j < 2 or (j % period) >= period - 2
+            if mode == "partial":
+                if full_left == 0 and omega * 1.5 * g_last > 1e-8:
+                    full_left = 2
+                full = full_left > 0
+            else:
+                full = mode == "full" or (mode == "period8" and (j < 2 or j % 8 >= 6))
+            n_full += full
             lo = 0 if full else max(0, j - 1)
             a = 0.0
             for _ in range(2 if full else 1):
@@ -408,17 +419,41 @@ def test_numpy_models_of_two_kernel_algorithms():
                 wn = wn - h @ V[lo:j + 1]
                 a += h[-1]
             alpha[j], beta[j] = a, np.linalg.norm(wn)
+            a_max, b_max = max(a_max, abs(a)), max(b_max, beta[j])
+            g_last = max(1.0, (a_max + abs(a) + 2.0 * b_max) / beta[j])
+            if full:
+                full_left -= 1
+                if full_left == 0:
+                    omega = 1e-15
+            else:
+                omega = min(omega * g_last, 1.0)
             w, binv = wn, 1.0 / beta[j]
         Tm = np.diag(alpha) + np.diag(beta[:-1], 1) + np.diag(beta[:-1], -1)
         ev = np.linalg.eigvalsh(Tm)
-        return ev[np.argsort(-np.abs(ev))], np.abs(V[:m] @ V[:m].T - np.eye(m)).max()
+        return ev[np.argsort(-np.abs(ev))], np.abs(V[:m] @ V[:m].T - np.eye(m)).max(), n_full
 
-    ev_full, orth_full = lanczos(150, 8, all_full=True)
-    ev_per, orth_per = lanczos(150, 8)
-    ev_none, orth_none = lanczos(150, 10 ** 6)
-    np.testing.assert_allclose(ev_per[:6], ev_full[:6], rtol=0, atol=1e-13)
-    assert orth_full < 1e-13 and orth_per < 1e-12
+    ev_full, orth_full, _ = lanczos(S, 150, "full")
+    ev_par, orth_par, n_full = lanczos(S, 150, "partial")
+    ev_none, orth_none, _ = lanczos(S, 150, "none")
+    np.testing.assert_allclose(ev_par[:6], ev_full[:6], rtol=0, atol=1e-13)
+    assert orth_full < 1e-13 and orth_par < 1e-9 and n_full < 100
     assert orth_none > 1e-3 and abs(ev_none[1] - 1.0) < 1e-6       # ghost of the Perron eigenvalue
+
+    # narrow bulk: five metastable blocks, K = 2000 (the matrix of tools/eig_bench.py); growth per local step ~50
+    Kb = 2000
+    Cb = rng.random((Kb, Kb)) * 0.02
+    for i in range(5):
+        Cb[i * 400:(i + 1) * 400, i * 400:(i + 1) * 400] += rng.random((400, 400))
+    Cb = Cb + Cb.T
+    sq = np.sqrt(Cb.sum(1))
+    Sb = Cb / sq[:, None] / sq[None, :]
+    ref = np.linalg.eigvalsh(Sb)
+    ref = ref[np.argsort(-np.abs(ref))][:10]
+    ev_par, orth_par, n_full = lanczos(Sb, 200, "partial")
+    np.testing.assert_allclose(ev_par[:10], ref, rtol=0, atol=1e-12)
+    assert orth_par < 1e-9 and n_full <= 100
+    _, orth_p8, _ = lanczos(Sb, 200, "period8")
+    assert orth_p8 > 0.5                                           # what the fixed period did here
 
     for _ in range(200):
         x, y = rng.standard_normal(64) * 10 ** rng.uniform(-3, 3), rng.standard_normal(64) * 10 ** rng.uniform(-3, 3)
