@@ -168,24 +168,42 @@ static int launch_project_fast(const float* X, int64_t n, int d, int64_t ld, con
 }
 
 // Warp-per-frame path (d <= 256, fp32 output): a lane owns the same 4 J columns of every frame, so its
-// slice of W (4 J x MP fp32) and of the centring vector live in REGISTERS -- no shared memory, and a frame
+// slice of W (4 J x MPF fp32) and of the centring vector live in REGISTERS -- no shared memory, and a frame
 // is two fully coalesced 512-byte loads instead of 64 strided ones (the thread-per-frame kernel above is
-// bound by the L1 tag stage: 32 different lines per load instruction).  The MP = 16 partial sums of a
-// frame are reduced over the 32 lanes by recursive halving (16 shuffles instead of 80); precision as in
-// project_fast_kernel (fp32 products, pairwise fp32 sums, fp64 remainder of the centring added once).
-constexpr int kPwWarps = 8;
-constexpr int kPwFrames = 4;   // frames in flight per warp
+// bound by the L1 tag stage: 32 different lines per load instruction).  The kernel is bound by instruction
+// issue, not by the FMA pipe, so the products run as packed fma.rn.f32x2 (FFMA2: two outputs per issue slot,
+// each half rounded exactly like fmaf) over MPF = m rounded up to even outputs instead of a fixed 16.  The
+// partial sums of a frame are reduced over the 32 lanes by recursive halving on a virtual width of 16 (15
+// shuffles instead of 5 per output); slots known to be zero at compile time are skipped, and where only the
+// upper half of a pair is zero both lanes simply add (no selects; the duplicate is never stored).
+// Precision as in project_fast_kernel (fp32 products, pairwise fp32 sums, fp64 remainder of the centring
+// added once).
 
-template <int J>
-__global__ void __launch_bounds__(kPwWarps * 32) project_warp_kernel(
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+template <int J, int MPF, int kPwWarps, int kPwMinBlocks, int kPwFrames>   // kPwFrames: frames in flight per warp
+__global__ void __launch_bounds__(kPwWarps * 32, kPwMinBlocks) project_warp_kernel(
     const float* __restrict__ X, int64_t n, int d, int64_t ld, const double* __restrict__ a,
     const double* __restrict__ nanfill, const double* __restrict__ W, int m, int ldw,
     float* __restrict__ Y, int64_t ldy) {
-  constexpr int MP = 16;
+  static_assert(MPF % 2 == 0 && MPF >= 2 && MPF <= 16, "MPF: even, at most 16");
   const int lane = threadIdx.x & 31;
   const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float w[J][4][MP], a32[J][4], fz[J][4];
+  unsigned long long w2[J][4][MPF / 2];
+  float a32[J][4], fz[J][4];
 #pragma unroll
   for (int j = 0; j < J; ++j)
 #pragma unroll
@@ -195,7 +213,9 @@ __global__ void __launch_bounds__(kPwWarps * 32) project_warp_kernel(
       a32[j][e] = ok ? (float)a[col] : 0.f;
       fz[j][e] = ok ? (float)(nanfill[col] - a[col]) : 0.f;
 #pragma unroll
-      for (int c = 0; c < MP; ++c) w[j][e][c] = (ok && c < m) ? (float)W[(size_t)col * ldw + c] : 0.f;
+      for (int c = 0; c < MPF; c += 2)
+        w2[j][e][c / 2] = pack_f32x2((ok && c < m) ? (float)W[(size_t)col * ldw + c] : 0.f,
+                                     (ok && c + 1 < m) ? (float)W[(size_t)col * ldw + c + 1] : 0.f);
     }
   // after the halving steps lane L holds output index oidx(L); its fp64 remainder -sum_j (a_j - a32_j) W_jc
   const int oidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
@@ -216,29 +236,39 @@ __global__ void __launch_bounds__(kPwWarps * 32) project_warp_kernel(
       }
 #pragma unroll
     for (int u = 0; u < kPwFrames; ++u) {
-      float acc[MP];
+      unsigned long long acc2[MPF / 2];
 #pragma unroll
-      for (int c = 0; c < MP; ++c) acc[c] = 0.f;
+      for (int c = 0; c < MPF / 2; ++c) acc2[c] = 0ull;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const float x[4] = {xv[u][j].x, xv[u][j].y, xv[u][j].z, xv[u][j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float z = (x[e] == x[e]) ? x[e] - a32[j][e] : fz[j][e];
+          const unsigned long long z2 = pack_f32x2(z, z);
 #pragma unroll
-          for (int c = 0; c < MP; ++c) acc[c] = fmaf(z, w[j][e][c], acc[c]);
+          for (int c = 0; c < MPF / 2; ++c) acc2[c] = ffma2(z2, w2[j][e][c], acc2[c]);
         }
       }
-      // recursive halving: 16 -> 8 -> 4 -> 2 -> 1 values per lane, then the two lanes of a pair add up
+      float acc[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int c = 0; c < MPF / 2; ++c) unpack_f32x2(acc2[c], acc[2 * c], acc[2 * c + 1]);
+      // recursive halving: 16 -> 8 -> 4 -> 2 -> 1 slots per lane, then the two lanes of a pair add up
 #pragma unroll
       for (int step = 0; step < 4; ++step) {
         const int off = 16 >> step, half = 8 >> step;
         const bool up = (lane & off) != 0;
 #pragma unroll
         for (int i = 0; i < half; ++i) {
-          const float keep = up ? acc[i + half] : acc[i];
-          const float give = up ? acc[i] : acc[i + half];
-          acc[i] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+          if (i + half < MPF) {
+            const float keep = up ? acc[i + half] : acc[i];
+            const float give = up ? acc[i] : acc[i + half];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+          } else if (i < MPF) {
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);   // slot i + half is identically zero
+          }
         }
       }
       float r = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
@@ -247,14 +277,41 @@ __global__ void __launch_bounds__(kPwWarps * 32) project_warp_kernel(
   }
 }
 
+template <int J, int MPF, int kPwWarps, int kPwMinBlocks, int kPwFrames>
+static int launch_project_warp_cfg(const float* X, int64_t n, int d, int64_t ld, const double* a, const double* nanfill,
+                                   const double* W, int m, float* Y, int64_t ldy, cudaStream_t st) {
+  int64_t blocks = (n + (int64_t)kPwWarps * kPwFrames - 1) / ((int64_t)kPwWarps * kPwFrames);
+  if (blocks > (int64_t)kPwMinBlocks * kNumSMs) blocks = (int64_t)kPwMinBlocks * kNumSMs;
+  project_warp_kernel<J, MPF, kPwWarps, kPwMinBlocks, kPwFrames>
+      <<<(unsigned)blocks, kPwWarps * 32, 0, st>>>(X, n, d, ld, a, nanfill, W, m, m, Y, ldy);
+  PMB_LAUNCH_CHECK();
+  return PMB_OK;
+}
+
+template <int J, int MPF>
+static int launch_project_warp_mpf(const float* X, int64_t n, int d, int64_t ld, const double* a, const double* nanfill,
+                                   const double* W, int m, float* Y, int64_t ldy, cudaStream_t st) {
+  // Measured at 10 M x 256 -> 10 (tools/prj_bench.py): 8 warps x 4 frames in flight at 226 registers 2.86 ms,
+  // 3 CTAs of 4 warps at 168 registers 2.70 ms, 2 frames in flight 3.8 ms (bytes in flight bound it); staging
+  // the rows through a bulk-copy ring in shared memory gave 2.77 ms for 2..6 stages (issue-bound by then).
+  // The 168-register form spills for the wide slices, which stay on one CTA of 8 warps.
+  if (J * MPF <= 20) return launch_project_warp_cfg<J, MPF, 4, 3, 4>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+  return launch_project_warp_cfg<J, MPF, 8, 1, 4>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+}
+
 template <int J>
 static int launch_project_warp(const float* X, int64_t n, int d, int64_t ld, const double* a, const double* nanfill,
                                const double* W, int m, float* Y, int64_t ldy, cudaStream_t st) {
-  int64_t blocks = (n + (int64_t)kPwWarps * kPwFrames - 1) / ((int64_t)kPwWarps * kPwFrames);
-  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
-  project_warp_kernel<J><<<(unsigned)blocks, kPwWarps * 32, 0, st>>>(X, n, d, ld, a, nanfill, W, m, m, Y, ldy);
-  PMB_LAUNCH_CHECK();
-  return PMB_OK;
+  switch ((m + 1) / 2) {
+    case 1: return launch_project_warp_mpf<J, 2>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+    case 2: return launch_project_warp_mpf<J, 4>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+    case 3: return launch_project_warp_mpf<J, 6>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+    case 4: return launch_project_warp_mpf<J, 8>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+    case 5: return launch_project_warp_mpf<J, 10>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+    case 6: return launch_project_warp_mpf<J, 12>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+    case 7: return launch_project_warp_mpf<J, 14>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+    default: return launch_project_warp_mpf<J, 16>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+  }
 }
 
 template <int MP>
