@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
         // four independent accumulators: four L2 round trips in flight instead of one
         double s1 = 0.0, s2 = 0.0, s3 = 0.0;
         int c = lane;
+#pragma unroll 4
         for (; c + 96 < K; c += 128) {
           s = fma(Trow[c], __ldcg(wc + c) * rs[c], s);
           s1 = fma(Trow[c + 32], __ldcg(wc + c + 32) * rs[c + 32], s1);
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
         double s = 0.0;
         double s1 = 0.0, s2 = 0.0, s3 = 0.0;
         int c = lane;
+#pragma unroll 4
         for (; c + 96 < K; c += 128) {
           s = fma(__ldcg(vi + c), __ldcg(wn + c), s);
           s1 = fma(__ldcg(vi + c + 32), __ldcg(wn + c + 32), s1);
@@ -272,20 +274,46 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
       grid.sync();
       // C: w -= sum_i h_i v_i  (+ partial |w|^2 on the last pass)
       double nn = 0.0;
-      for (int e = gtid; e < K; e += gthreads) {
-        double v = __ldcg(wn + e);
-        double v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        int i = i_lo;
-        for (; i + 3 <= j; i += 4) {
-          v = fma(-__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), v);
-          v1 = fma(-__ldcg(h + i + 1), __ldcg(p.V + (size_t)(i + 1) * K + e), v1);
-          v2 = fma(-__ldcg(h + i + 2), __ldcg(p.V + (size_t)(i + 2) * K + e), v2);
-          v3 = fma(-__ldcg(h + i + 3), __ldcg(p.V + (size_t)(i + 3) * K + e), v3);
+      if (full) {
+        // one warp per element, the previous vectors spread over its lanes: a thread per element walked the
+        // j + 1 vectors as a chain of (j + 1) / 4 dependent L2 round trips on 1000 of the grid's 32 000
+        // threads (9 us per pass at j = 100); this is one round trip and a shuffle tree.  Four elements per
+        // warp are in flight for K > the number of warps.
+        constexpr int EU = 4;
+        for (int e0 = gwarp; e0 < K; e0 += EU * nwarps) {
+          double part[EU];
+#pragma unroll
+          for (int u = 0; u < EU; ++u) {
+            const int e = e0 + u * nwarps;
+            double s0 = 0.0, s1 = 0.0;
+            if (e < K) {
+              int i = lane;
+              for (; i + 32 <= j; i += 64) {
+                s0 = fma(__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), s0);
+                s1 = fma(__ldcg(h + i + 32), __ldcg(p.V + (size_t)(i + 32) * K + e), s1);
+              }
+              if (i <= j) s0 = fma(__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), s0);
+            }
+            part[u] = s0 + s1;
+          }
+#pragma unroll
+          for (int u = 0; u < EU; ++u) {
+            const int e = e0 + u * nwarps;
+            const double sub = warp_sum(part[u]);
+            if (e < K && lane == 0) {
+              const double v = __ldcg(wn + e) - sub;
+              wn[e] = v;
+              nn = fma(v, v, nn);
+            }
+          }
         }
-        for (; i <= j; ++i) v = fma(-__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), v);
-        v += (v1 + v2) + v3;
-        wn[e] = v;
-        nn = fma(v, v, nn);
+      } else {
+        for (int e = gtid; e < K; e += gthreads) {
+          double v = __ldcg(wn + e);
+          for (int i = i_lo; i <= j; ++i) v = fma(-__ldcg(h + i), __ldcg(p.V + (size_t)i * K + e), v);
+          wn[e] = v;
+          nn = fma(v, v, nn);
+        }
       }
       a_j += __ldcg(h + j);
       if (pass == npass - 1) block_partial(nn);
