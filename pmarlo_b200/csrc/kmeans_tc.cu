@@ -217,8 +217,10 @@ struct TcSmem {
 };
 
 // DBG: also write the raw scores (tests).  INREG: D <= kTcDReg, a frame's coordinates live in registers.
-template <bool DBG, bool INREG>
+// DRP: coordinate registers of a producer thread (12 when D <= 12: the producers hold three such arrays).
+template <bool DBG, bool INREG, int DRP>
 __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) {
+  static_assert(DRP <= kTcDReg, "DRP");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KS = p.KS, D = p.D, K = p.K, Kpad = p.Kpad;
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     }
     for (int b = 0; b < kTcRing; ++b) {
       mbar_init(&S->t_full[b], 1);
-      mbar_init(&S->t_empty[b], PMB_KM_EPI == 0 ? kTcEpiWarps : 4);
+      mbar_init(&S->t_empty[b], PMB_KM_EPI == 0 ? kTcEpiWarps : (PMB_KM_EPI == 2 ? 8 : 4));
     }
     for (int b = 0; b < 4; ++b) mbar_init(&S->thr_ready[b], 1);
     for (int b = 0; b < kTcMaxSlots; ++b) {
@@ -327,6 +329,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
             }
             if (best != blk_before) bblock = c * (kTcChunk / 32) + grp;   // low 5 key bits refer to this block
           }
+        }
+        KM_T(e4);
+        KM_ACC(2, e3, e4);
+      }
+#elif PMB_KM_EPI == 2
+      // Two super-groups of eight warps, each ping-ponging between TWO ring slots (s and s + 2: the chunks issued by
+      // MMA warp s).  A warp reads two of the four 32-column blocks of its lane quarter per visit and the eight warps
+      // release the slot after their second load, so the round trip release -> MMA -> commit of one slot (~550
+      // cycles, fully exposed when a group owns a single slot) overlaps the two blocks read from the other slot.
+      const uint32_t j0 = it * (uint32_t)n_chunks;
+      const int sg = warp >> 3, half = (warp >> 2) & 1;
+      for (int c = sg; c < n_chunks; c += 2) {
+        const uint32_t j = j0 + (uint32_t)c, tb = j & (kTcRing - 1);
+        KM_T(e2);
+        mbar_wait(&S->t_full[tb], (j >> 2) & 1u);
+        KM_T(e3);
+        KM_ACC(1, e2, e3);
+        tc::fence_after_sync();
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + tb * kTcChunk + (uint32_t)(half * 64);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float v[32];
+          tc::tmem_ld32(tbase + (uint32_t)(hh * 32), v);
+          if (hh == 1) {
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&S->t_empty[tb]);
+          }
+          if constexpr (DBG) {
+            const int64_t grow = tile * kTcTile + row;
+            if (grow < p.n)
+              for (int q = 0; q < 32; ++q)
+                p.dbg_scores[grow * Kpad + c * kTcChunk + (half * 2 + hh) * 32 + q] = (v[q] + xn2) * inv_s2;
+          }
+          float t12[12];
+#pragma unroll
+          for (int q = 0; q < 10; ++q) t12[q] = fminf(fminf(v[3 * q], v[3 * q + 1]), v[3 * q + 2]);
+          t12[10] = v[30];
+          t12[11] = v[31];
+          float t4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) t4[q] = fminf(fminf(t12[3 * q], t12[3 * q + 1]), t12[3 * q + 2]);
+          const float bmin = fminf(fminf(fminf(t4[0], t4[1]), t4[2]), t4[3]);
+          if (!__any_sync(0xffffffffu, bmin <= thr)) continue;
+          const int blk_before = best;
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            const int k0 = (int)((__float_as_uint(fmaxf(v[q] + xn2, 0.f)) & 0xFFFFFFE0u) | (uint32_t)q);
+            const int k1 = (int)((__float_as_uint(fmaxf(v[q + 1] + xn2, 0.f)) & 0xFFFFFFE0u) | (uint32_t)(q + 1));
+            const int lo = min(k0, k1), hi = max(k0, k1);
+            const int t = max(best, lo);
+            second = min(min(second, hi), t);
+            best = min(best, lo);
+          }
+          if (best != blk_before) bblock = c * (kTcChunk / 32) + half * 2 + hh;
         }
         KM_T(e4);
         KM_ACC(2, e3, e4);
@@ -560,50 +617,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
     // =========================================================== producers: A tile + screening threshold
     const int pt = tid - kTcProdWarp0 * 32;   // 0..127: row of the tile
     constexpr bool in_regs = INREG;
-    float yn[kTcDReg];   // SCALED coordinates of this thread's row of the NEXT tile (prefetched)
-    int hint_n = -1;
-    auto prefetch = [&](int64_t tile) {
+    // Two levels of prefetch: the hint of tile t + 2 is requested while tile t is built, so that the gather of
+    // the HINTED centre of tile t + 1 (an address that depends on the hint) is issued a whole tile ahead as
+    // well.  With the gather issued at use, every tile paid its L2 round trip on the producers' serial path
+    // (1 700 of their 3 400 cycles per tile).
+    float yn[DRP];    // coordinates of this thread's row of the NEXT tile (scaled at use)
+    float chn[DRP];   // scaled hinted centre of that row (INREG)
+    int hint_n = -1, hint_nn = -1;   // hints of the next tile and of the one after
+    auto load_hint = [&](int64_t tile) -> int {
       const int64_t row = tile * kTcTile + pt;
-      hint_n = -1;
+      return (tile < n_tiles && row < p.n && p.hints != nullptr) ? ldg_stream_i(p.hints + row) : -1;
+    };
+    auto prefetch = [&](int64_t tile) {   // hint_n holds this tile's hint
+      const int64_t row = tile * kTcTile + pt;
       if (row < p.n) {
-        if (p.hints != nullptr) hint_n = ldg_stream_i(p.hints + row);
         if constexpr (in_regs) {
 #pragma unroll
-          for (int d = 0; d < kTcDReg; ++d) yn[d] = (d < D) ? ldg_stream_f(p.Y + row * p.ld + d) : 0.f;   // scaled at use
+          for (int d = 0; d < DRP; ++d) yn[d] = (d < D) ? ldg_stream_f(p.Y + row * p.ld + d) : 0.f;   // scaled at use
+          if (hint_n >= 0 && hint_n < K) {
+            const float* ch = p.cs32 + (size_t)hint_n * D;
+#pragma unroll
+            for (int d = 0; d < DRP; ++d) chn[d] = (d < D) ? __ldg(ch + d) : 0.f;
+          }
         }
       } else {
 #pragma unroll
-        for (int d = 0; d < kTcDReg; ++d) yn[d] = 0.f;
+        for (int d = 0; d < DRP; ++d) yn[d] = 0.f;
       }
     };
     uint32_t it = 0;
     double ysq_acc = 0.0;
     const double inv_s2d = (double)p.meta[2];
     KM_DECL;
+    hint_n = load_hint(blockIdx.x);
+    hint_nn = load_hint((int64_t)blockIdx.x + gridDim.x);
     if ((int64_t)blockIdx.x < n_tiles) prefetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ab = it & 1u;
       const int64_t row = tile * kTcTile + pt;
       const bool valid = row < p.n;
-      float y[kTcDReg];
+      float y[DRP];
 #pragma unroll
-      for (int d = 0; d < kTcDReg; ++d) y[d] = yn[d] * scale;
+      for (int d = 0; d < DRP; ++d) y[d] = yn[d] * scale;
       const int hint = hint_n;
-      if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
       // fp32 distance to the hinted centre (scaled centres written by the prep kernel)
       float u = __int_as_float(0x7f800000);
       if (valid && hint >= 0 && hint < K) {
         u = 0.f;
-        const float* ch = p.cs32 + (size_t)hint * D;
         if constexpr (in_regs) {
 #pragma unroll
-          for (int d = 0; d < kTcDReg; ++d) {
+          for (int d = 0; d < DRP; ++d) {
             if (d < D) {
-              const float t = y[d] - ch[d];
+              const float t = y[d] - chn[d];
               u = fmaf(t, t, u);
             }
           }
         } else {
+          const float* ch = p.cs32 + (size_t)hint * D;
 #pragma unroll 4
           for (int d = 0; d < D; ++d) {
             const float t = p.Y[row * p.ld + d] * scale - ch[d];
@@ -611,6 +681,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
           }
         }
       }
+      hint_n = hint_nn;
+      if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+      hint_nn = load_hint(tile + 2 * (int64_t)gridDim.x);
       KM_T(p0);
       mbar_wait(&S->a_empty[ab], ((it >> 1) & 1u) ^ 1u);
       KM_T(p1);
@@ -621,7 +694,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
       if constexpr (in_regs) {
         double rowsq = 0.0;   // |y s|^2 in fp64: the inertia identity cancels, fp32 would not do
 #pragma unroll
-        for (int d = 0; d < kTcDReg; ++d) {
+        for (int d = 0; d < DRP; ++d) {
           const float v = y[d];          // zero beyond D and for rows past the end
           xn2 = fmaf(v, v, xn2);
           rowsq = fma((double)v, (double)v, rowsq);
@@ -629,7 +702,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
         }
         if (!fits) {
 #pragma unroll
-          for (int d = 0; d < kTcDReg; ++d) y[d] = 0.f;
+          for (int d = 0; d < DRP; ++d) y[d] = 0.f;
         }
         const float one = valid ? kTcNormUnit : 0.0f;
         // slot s: 0-1 -> 2^13, 2 + 3 d + r -> (r == 1 ? y_lo[d] : y_hi[d]); 16-byte stores (8 slots), 8 lanes
@@ -637,13 +710,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_tc_kernel(KmTcParams p) 
         auto slot_val = [&](int sl) -> float {
           if (sl < 2) return one;
           const int d = (sl - 2) / 3, r = (sl - 2) % 3;
-          if (d >= kTcDReg) return 0.f;
+          if (d >= DRP) return 0.f;
           const float hi = __half2float(__float2half_rn(y[d]));   // recomputed per use: keeps the register count low
           return r == 1 ? (y[d] - hi) : hi;
         };
         unsigned char* arow = A + (uint32_t)(pt >> 3) * sbo + (uint32_t)(pt & 7) * 16u;
 #pragma unroll
-        for (int j = 0; j < (3 * kTcDReg + 2 + 15) / 16 * 2; ++j) {
+        for (int j = 0; j < (3 * DRP + 2 + 15) / 16 * 2; ++j) {
           if (8 * j < KS) {
             __half2 h0 = __floats2half2_rn(slot_val(8 * j), slot_val(8 * j + 1));
             __half2 h1 = __floats2half2_rn(slot_val(8 * j + 2), slot_val(8 * j + 3));
@@ -1004,8 +1077,12 @@ int kmeans_tc_assign(const float* Y, int64_t n, int D, int64_t ld, const double*
     return PMB_OK;
   };
   int rc;
-  if (dbg_scores != nullptr) rc = (D <= kTcDReg) ? launch(kmeans_tc_kernel<true, true>) : launch(kmeans_tc_kernel<true, false>);
-  else rc = (D <= kTcDReg) ? launch(kmeans_tc_kernel<false, true>) : launch(kmeans_tc_kernel<false, false>);
+  if (dbg_scores != nullptr)
+    rc = (D <= 12) ? launch(kmeans_tc_kernel<true, true, 12>)
+                   : (D <= kTcDReg) ? launch(kmeans_tc_kernel<true, true, kTcDReg>) : launch(kmeans_tc_kernel<true, false, kTcDReg>);
+  else
+    rc = (D <= 12) ? launch(kmeans_tc_kernel<false, true, 12>)
+                   : (D <= kTcDReg) ? launch(kmeans_tc_kernel<false, true, kTcDReg>) : launch(kmeans_tc_kernel<false, false, kTcDReg>);
   if (rc != PMB_OK) return rc;
   kmeans_recheck_kernel<<<2 * kNumSMs, 256, 0, st>>>(p);
   PMB_LAUNCH_CHECK();

@@ -50,7 +50,7 @@ def run(name, n, D, K, reps=6, sigma_c=1.0):
     cnt = torch.zeros((K,), dtype=torch.int64, device=dev)
     inertia = torch.zeros((1,), dtype=torch.float64, device=dev)
     nre = torch.zeros((1,), dtype=torch.int64, device=dev)
-    for mode in ("cold", "hints", "hints+accumulate"):
+    for mode in ("cold", "cold-subsampled-hints", "hints", "hints+accumulate"):
         ts = []
         for it in range(reps):
             nre.zero_()
@@ -58,6 +58,9 @@ def run(name, n, D, K, reps=6, sigma_c=1.0):
             a.record()
             if mode == "cold":
                 kernels.kmeans_assign(Y, C, labels=labels, impl=2, n_rechecked=nre)
+            elif mode == "cold-subsampled-hints":
+                from pmarlo_b200.clustering import subsampled_hints
+                kernels.kmeans_assign(Y, C, labels=labels, impl=2, hints=subsampled_hints(Y, C), n_rechecked=nre)
             elif mode == "hints":
                 kernels.kmeans_assign(Y, C, labels=labels, impl=2, hints=labels, n_rechecked=nre)
             else:
