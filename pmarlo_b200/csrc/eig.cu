@@ -92,9 +92,44 @@ __device__ void tridiag_bisect(const double* a, const double* b, int m, double* 
   }
 }
 
+// Number of eigenvalues of the tridiagonal (a, b) of size m below x, from the sign changes of the leading
+// principal minors p_i(x) = (a_i - x) p_{i-1} - b_{i-1}^2 p_{i-2}: ONE dependent fma per row.  The quotient form
+// d_i = p_i / p_{i-1} of sturm_count above puts a double-precision division (~110 cycles of latency) on the
+// chain; with it the Ritz values took half of the Lanczos kernel.  The problem is scaled by `inv` = 1 / (its
+// Gershgorin span) so that a minor changes by at most 2^24 in eight rows, and the pair is renormalised every
+// eight rows.  A minor that is exactly zero takes the sign opposite to its predecessor (the d = -tiny rule).
+// The scaled rows are prepared once per call in shared memory, eight rows are unrolled between renormalisations.
+__device__ __forceinline__ int sturm_count_minors(const double* as, const double* bb, int m, double xs) {
+  // as[i] = a_i inv, bb[i] = (b_{i-1} inv)^2 (bb[0] unused), xs = x inv
+  double p0 = 1.0, p1 = as[0] - xs;
+  bool neg = p1 < 0.0 || p1 == 0.0;   // sign of p_1 (p_0 > 0)
+  int cnt = neg ? 1 : 0;
+  auto row = [&](int i) {
+    const double pn = fma(as[i] - xs, p1, -bb[i] * p0);
+    p0 = p1;
+    p1 = pn;
+    const bool ng = pn < 0.0 || (pn == 0.0 && !neg);
+    cnt += (ng != neg) ? 1 : 0;
+    neg = ng;
+  };
+  int i = 1;
+  for (; i + 8 <= m; i += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) row(i + u);
+    const double mx = fmax(fabs(p0), fabs(p1));
+    if (mx > 0x1p256) { p0 *= 0x1p-256; p1 *= 0x1p-256; }
+    else if (mx < 0x1p-256) { p0 *= 0x1p256; p1 *= 0x1p256; }
+  }
+  for (; i < m; ++i) row(i);
+  return cnt;
+}
+
 // the kk smallest and kk largest eigenvalues of the m x m tridiagonal: out[0..kk) ascending from the bottom,
-// out[kk..2kk) descending from the top (threads 0 .. 2 kk - 1, one eigenvalue each)
-__device__ void tridiag_bisect_extremes(const double* a, const double* b, int m, int kk, double* out) {
+// out[kk..2kk) descending from the top.  One WARP per eigenvalue: the 32 lanes evaluate the Sturm count at 32
+// points of the bracket at once (a factor 33 per pass, 11-12 passes to the last bit instead of ~60 bisections).
+// Every lane of every warp computes the same brackets from the same numbers: the result is uniform.
+__device__ void tridiag_bisect_extremes(const double* a, const double* b, int m, int kk, double* out,
+                                        double* as, double* bb /* shared scratch, m entries each */) {
   double lo = 1e300, hi = -1e300;
   for (int i = 0; i < m; ++i) {
     const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < m ? fabs(b[i]) : 0.0);
@@ -102,23 +137,48 @@ __device__ void tridiag_bisect_extremes(const double* a, const double* b, int m,
     hi = fmax(hi, a[i] + r);
   }
   const double span = fmax(fabs(lo), fabs(hi));
-  const double tiny = 2.3e-308 + 1e-30 * span;
+  const double inv = span > 0.0 ? 1.0 / span : 1.0;
   lo -= 1e-12 * span + 1e-300;
   hi += 1e-12 * span + 1e-300;
-  const int t = threadIdx.x;
-  if (t < 2 * kk) {
+  __syncthreads();   // scratch free (previous call)
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    as[i] = a[i] * inv;
+    const double bi = i > 0 ? b[i - 1] * inv : 0.0;
+    bb[i] = bi * bi;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = threadIdx.x >> 5; t < 2 * kk; t += nw) {
     const int idx = t < kk ? t : m - 1 - (t - kk);
     double v = 0.0;
     if (idx >= 0 && idx < m) {
       double l = lo, h = hi;
-      for (int it = 0; it < 200; ++it) {
-        const double mid = 0.5 * (l + h);
-        if (mid <= l || mid >= h) break;
-        if (sturm_count(a, b, m, mid, tiny) > idx) h = mid; else l = mid;
+      for (int pass = 0; pass < 16; ++pass) {
+        const double w = (h - l) * (1.0 / 33.0);
+        const double x_first = l + w, x_last = l + 32.0 * w;
+        if (!(x_first > l) || !(x_last < h)) break;   // the grid no longer separates the bracket
+        const int c = sturm_count_minors(as, bb, m, (l + (double)(lane + 1) * w) * inv);
+        const unsigned above = __ballot_sync(0xffffffffu, c > idx);   // points with more than idx eigenvalues below
+        if (above == 0u) {
+          l = x_last;
+        } else {
+          const int f = __ffs(above) - 1;
+          h = l + (double)(f + 1) * w;
+          if (f > 0) l = l + (double)f * w;
+        }
       }
       v = 0.5 * (l + h);
     }
-    out[t] = v;
+    if (lane == 0) out[t] = v;
+  }
+}
+
+// the k leading eigenvalues by magnitude out of the two sorted ends produced above (needs 2 k <= m)
+__device__ __forceinline__ void merge_extremes_by_magnitude(const double* ext, int k, double* top) {
+  int lo_i = 0, hi_i = 0;
+  for (int t = 0; t < k; ++t) {
+    const double a_lo = ext[lo_i], a_hi = ext[k + hi_i];
+    if (fabs(a_hi) >= fabs(a_lo)) { top[t] = a_hi; ++hi_i; } else { top[t] = a_lo; ++lo_i; }
   }
 }
 
@@ -159,6 +219,7 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
   // every CTA keeps its own copy of the recurrence (a_j, b_j are the same numbers in every thread of the grid),
   // so that the convergence checkpoints need no extra grid barrier
   __shared__ double s_alpha[1024], s_beta[1024];
+  __shared__ double s_as[1024], s_bb[1024];   // scaled copies for the Sturm counts
   __shared__ double s_ext[2 * kLanMaxTop], s_top[kLanMaxTop], s_top_prev[kLanMaxTop];
   __shared__ int s_stop;
   const int K = p.K, tid = threadIdx.x, lane = tid & 31;
@@ -215,12 +276,21 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
   // orthogonality completely after ~100 steps (55^6 eps = 3e-6 per period) and the projections diverged.
   // Every thread evaluates the rule on the same numbers: uniform without a barrier.
   // A full step costs 5 grid barriers, a local one 3.
+#ifdef PMB_LAN_PROF
+  long long lp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define LAN_T(v) const long long v = clock64()
+#define LAN_ACC(i, a, b) lp[i] += (b) - (a)
+#else
+#define LAN_T(v)
+#define LAN_ACC(i, a, b)
+#endif
   int m_eff = 0;
   double omega = kLanOmegaReset, g_last = 1.0, a_max = 0.0, b_max = 0.0;
   int full_left = 2;
   for (int j = 0; j < p.m; ++j) {
     const double* wc = w_cur;
     double* wn = w_new;
+    LAN_T(t0);
     // A: V[j] = binv w_cur;  w_new = D^{1/2} T D^{-1/2} V[j]
     {
       double* vj = p.V + (size_t)j * K;
@@ -246,7 +316,11 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
       }
       if (lane == 0) wn[i] = s;
     }
+    LAN_T(t1);
     grid.sync();
+    LAN_T(t2);
+    LAN_ACC(0, t0, t1);
+    LAN_ACC(1, t1, t2);
     if (full_left == 0 && omega * 1.5 * g_last > kLanOmegaMax) full_left = 2;
     const bool full = full_left > 0;
     const int i_lo = full ? 0 : (j > 0 ? j - 1 : 0);
@@ -254,6 +328,7 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
     double a_j = 0.0;
     for (int pass = 0; pass < npass; ++pass) {
       double* h = p.h + (size_t)pass * (p.m + 1);
+      LAN_T(t3);
       // B: h_i = v_i . w
       for (int i = i_lo + gwarp; i <= j; i += nwarps) {
         const double* vi = p.V + (size_t)i * K;
@@ -271,7 +346,11 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
         s = warp_sum((s + s1) + (s2 + s3));
         if (lane == 0) h[i] = s;
       }
+      LAN_T(t4);
       grid.sync();
+      LAN_T(t5);
+      LAN_ACC(2, t3, t4);
+      LAN_ACC(3, t4, t5);
       // C: w -= sum_i h_i v_i  (+ partial |w|^2 on the last pass)
       double nn = 0.0;
       if (full) {
@@ -317,8 +396,13 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
       }
       a_j += __ldcg(h + j);
       if (pass == npass - 1) block_partial(nn);
+      LAN_T(t6);
       grid.sync();
+      LAN_T(t7);
+      LAN_ACC(4, t5, t6);
+      LAN_ACC(5, t6, t7);
     }
+    LAN_T(t8);
     const double b_j = sqrt(grid_sum_partials(p.part, gridDim.x));
     if (gtid == 0) { p.alpha[j] = a_j; p.beta[j] = b_j; }
     if (tid == 0) { s_alpha[j] = a_j; s_beta[j] = b_j; }
@@ -334,19 +418,15 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
     // replaces cost 5.4 ms for K = 1000; the leading values settle after 60-100.)
     if (p.k <= kLanMaxTop && 2 * p.k <= m_eff && m_eff >= kLanCheckFrom && (m_eff - kLanCheckFrom) % kLanCheckEvery == 0) {
       __syncthreads();
-      tridiag_bisect_extremes(s_alpha, s_beta, m_eff, p.k, s_ext);
+      tridiag_bisect_extremes(s_alpha, s_beta, m_eff, p.k, s_ext, s_as, s_bb);
       __syncthreads();
       if (tid == 0) {
-        // merge the two sorted ends by magnitude
-        int lo_i = 0, hi_i = 0, stop = (m_eff > kLanCheckFrom) ? 1 : 0;
+        merge_extremes_by_magnitude(s_ext, p.k, s_top);
+        int stop = (m_eff > kLanCheckFrom) ? 1 : 0;
         for (int t = 0; t < p.k; ++t) {
-          const double a_lo = s_ext[lo_i], a_hi = s_ext[p.k + hi_i];
-          double v;
-          if (fabs(a_hi) >= fabs(a_lo)) { v = a_hi; ++hi_i; } else { v = a_lo; ++lo_i; }
-          if (stop && fabs(v - s_top_prev[t]) > 1e-12 * fmax(1.0, fabs(v))) stop = 0;
-          s_top[t] = v;
+          if (stop && fabs(s_top[t] - s_top_prev[t]) > 1e-12 * fmax(1.0, fabs(s_top[t]))) stop = 0;
+          s_top_prev[t] = s_top[t];
         }
-        for (int t = 0; t < p.k; ++t) s_top_prev[t] = s_top[t];
         s_stop = stop;
       }
       __syncthreads();
@@ -354,45 +434,74 @@ __global__ void __launch_bounds__(kLanThreads, 1) lanczos_kernel(LanParams p) {
     }
     binv = 1.0 / b_j;
     { double* t = w_cur; w_cur = w_new; w_new = t; }
+    LAN_T(t9);
+    LAN_ACC(6, t8, t9);
   }
   grid.sync();
   if (blockIdx.x != 0) return;
+#ifdef PMB_LAN_PROF
+  const long long t_tail0 = clock64();
+#endif
   // Ritz values of T_m and of a shorter recurrence, CTA 0 only
   const int m2 = m_eff - (m_eff / 8 > 1 ? m_eff / 8 : 1);
-  double* r1 = p.ritz;
-  double* r2 = p.ritz + p.m;
-  for (int i = tid; i < m_eff; i += blockDim.x) { r1[i] = 0.0; r2[i] = 0.0; }
-  __syncthreads();
-  tridiag_bisect(p.alpha, p.beta, m_eff, r1);
-  if (m2 >= 1) tridiag_bisect(p.alpha, p.beta, m2, r2);
-  __syncthreads();
-  // top-k by magnitude of each set (m_eff <= 1024 guaranteed by the launcher)
-  auto rank = [&](const double* vals, int n, int* order) {
-    for (int jj = tid; jj < n; jj += blockDim.x) {
-      const double aj = fabs(vals[jj]);
-      int rk = 0;
-      for (int i = 0; i < n; ++i) {
-        const double ai = fabs(vals[i]);
-        rk += (ai > aj) || (ai == aj && i < jj);
-      }
-      order[rk] = jj;
-    }
-    __syncthreads();
-  };
-  rank(r1, m_eff, s_order);
   int ok = 1;
-  for (int t = tid; t < p.k; t += blockDim.x) p.evals[t] = (t < m_eff) ? r1[s_order[t]] : 0.0;
-  __syncthreads();
-  if (m2 >= 1) {
-    rank(r2, m2, s_order);
-    for (int t = tid; t < p.k && t < m2; t += blockDim.x) {
-      const double a = p.evals[t], b = r2[s_order[t]];
+  if (p.k <= kLanMaxTop && 2 * p.k <= m2) {
+    // only the two ends of the spectrum are needed: k values from each, merged by magnitude
+    __syncthreads();
+    tridiag_bisect_extremes(s_alpha, s_beta, m_eff, p.k, s_ext, s_as, s_bb);
+    __syncthreads();
+    if (tid == 0) merge_extremes_by_magnitude(s_ext, p.k, s_top);
+    __syncthreads();
+    tridiag_bisect_extremes(s_alpha, s_beta, m2, p.k, s_ext, s_as, s_bb);
+    __syncthreads();
+    if (tid == 0) merge_extremes_by_magnitude(s_ext, p.k, s_top_prev);
+    __syncthreads();
+    for (int t = tid; t < p.k; t += blockDim.x) {
+      const double a = s_top[t], b = s_top_prev[t];
+      p.evals[t] = a;
       if (fabs(a - b) > 1e-10 * fmax(1.0, fabs(a))) ok = 0;
+    }
+  } else {
+    double* r1 = p.ritz;
+    double* r2 = p.ritz + p.m;
+    for (int i = tid; i < m_eff; i += blockDim.x) { r1[i] = 0.0; r2[i] = 0.0; }
+    __syncthreads();
+    tridiag_bisect(p.alpha, p.beta, m_eff, r1);
+    if (m2 >= 1) tridiag_bisect(p.alpha, p.beta, m2, r2);
+    __syncthreads();
+    // top-k by magnitude of each set (m_eff <= 1024 guaranteed by the launcher)
+    auto rank = [&](const double* vals, int n, int* order) {
+      for (int jj = tid; jj < n; jj += blockDim.x) {
+        const double aj = fabs(vals[jj]);
+        int rk = 0;
+        for (int i = 0; i < n; ++i) {
+          const double ai = fabs(vals[i]);
+          rk += (ai > aj) || (ai == aj && i < jj);
+        }
+        order[rk] = jj;
+      }
+      __syncthreads();
+    };
+    rank(r1, m_eff, s_order);
+    for (int t = tid; t < p.k; t += blockDim.x) p.evals[t] = (t < m_eff) ? r1[s_order[t]] : 0.0;
+    __syncthreads();
+    if (m2 >= 1) {
+      rank(r2, m2, s_order);
+      for (int t = tid; t < p.k && t < m2; t += blockDim.x) {
+        const double a = p.evals[t], b = r2[s_order[t]];
+        if (fabs(a - b) > 1e-10 * fmax(1.0, fabs(a))) ok = 0;
+      }
     }
   }
   ok = __syncthreads_and(ok);
   if (m_eff >= K || m_eff < p.m) ok = 1;  // exhausted the (active) space: Ritz values are exact
   if (tid == 0) { p.info[0] = m_eff; p.info[1] = ok; }
+#ifdef PMB_LAN_PROF
+  if (tid == 0) {
+    lp[7] = clock64() - t_tail0;
+    for (int i = 0; i < 8; ++i) p.part[256 + i] = (double)lp[i];
+  }
+#endif
 }
 
 static int lanczos_steps(int K, int k, int max_steps) {

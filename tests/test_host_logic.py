@@ -469,6 +469,73 @@ def test_numpy_models_of_two_kernel_algorithms():
         np.testing.assert_allclose([xn @ xn, yn @ yn], [a - t * g, b + t * g], rtol=1e-9)
 
 
+def test_numpy_model_of_the_ritz_value_multisection():
+    """eig.cu: the Ritz values of the Lanczos tridiagonal come from a 32-way multisection per eigenvalue (one
+    warp, 32 Sturm counts per pass) with the DIVISION-FREE Sturm count on the scaled leading principal minors
+    (renormalised every eight rows).  The model restates sturm_count_minors / tridiag_bisect_extremes and is
+    compared with eigvalsh on tridiagonals shaped like the kernel's (a few large leading entries, a narrow
+    bulk, one nearly decoupled row), at three scales."""
+    def sturm_minors(a, b, x, inv):
+        xs = x * inv
+        p0, p1 = 1.0, a[0] * inv - xs
+        neg = p1 < 0 or p1 == 0
+        cnt = int(neg)
+        for i in range(1, len(a)):
+            bi = b[i - 1] * inv
+            pn = (a[i] * inv - xs) * p1 - (bi * bi) * p0
+            p0, p1 = p1, pn
+            ng = pn < 0 or (pn == 0 and not neg)
+            cnt += ng != neg
+            neg = ng
+            if i % 8 == 0:
+                mx = max(abs(p0), abs(p1))
+                if mx > 2.0 ** 256:
+                    p0, p1 = p0 * 2.0 ** -256, p1 * 2.0 ** -256
+                elif mx < 2.0 ** -256:
+                    p0, p1 = p0 * 2.0 ** 256, p1 * 2.0 ** 256
+        return cnt
+
+    def extremes(a, b, kk):
+        m = len(a)
+        r = np.zeros(m)
+        r[1:] += np.abs(b[:m - 1])
+        r[:-1] += np.abs(b[:m - 1])
+        lo, hi = (a - r).min(), (a + r).max()
+        span = max(abs(lo), abs(hi))
+        inv = 1.0 / span
+        lo -= 1e-12 * span + 1e-300
+        hi += 1e-12 * span + 1e-300
+        out, passes = [], 0
+        for t in range(2 * kk):
+            idx = t if t < kk else m - 1 - (t - kk)
+            lb, hb = lo, hi
+            for _ in range(16):
+                w = (hb - lb) * (1.0 / 33.0)
+                if not (lb + w > lb) or not (lb + 32.0 * w < hb):
+                    break
+                passes += 1
+                above = [sturm_minors(a, b, lb + (ln + 1) * w, inv) > idx for ln in range(32)]
+                if not any(above):
+                    lb = lb + 32.0 * w
+                else:
+                    f = above.index(True)
+                    hb, lb = lb + (f + 1) * w, (lb + f * w if f > 0 else lb)
+            out.append(0.5 * (lb + hb))
+        return np.array(out), passes / (2 * kk)
+
+    rng = np.random.default_rng(1)
+    for m, scale in ((48, 1.0), (96, 1e6), (64, 1e-9)):
+        a = rng.normal(0, 0.01, m) * scale
+        a[:5] = np.array([0.9, 0.8, 0.1, 0.5, -0.3]) * scale
+        b = np.abs(rng.normal(0.02, 0.005, m)) * scale
+        b[:4] = np.array([0.3, 0.2, 0.1, 0.05]) * scale
+        b[10] = 1e-13 * scale
+        ev = np.linalg.eigvalsh(np.diag(a) + np.diag(b[:m - 1], 1) + np.diag(b[:m - 1], -1))
+        got, passes = extremes(a, b, 4)
+        np.testing.assert_allclose(got, np.concatenate([ev[:4], ev[::-1][:4]]), rtol=0, atol=4e-15 * scale)
+        assert passes <= 12
+
+
 def test_candidate_lag_ladder_matches_reference_golden(golden):
     """utils/msm_utils.py:21-105 -- outputs of the genuine reference function (tests/golden/make_golden.py::make_ladders)."""
     from pmarlo_b200 import candidate_lag_ladder

@@ -1,8 +1,3 @@
-python tools/km_bench.py c4 2>&1 | tail -5
-timeout 900 python -m pytest tests -x -q -m gpu -k "kmeans or cluster or lloyd or assign or config or c1 or c2 or c3" 2>&1 | tail -3
-python bench.py --steps 3 --warmup 1 > gpurun_out/bench_x.log 2> gpurun_out/bench_x.err; tail -c 300 gpurun_out/bench_x.err
-python - <<'PY'
-import json
-d=json.loads([l for l in open("gpurun_out/bench_x.log") if l.startswith("{")][-1])
-print(round(d["value"]/1e6,2), round(d["ms_per_step"],2), {k: round(v,2) for k,v in d["stages_ms"].items()}, d["e2e"]["ms_per_step"])
-PY
+PMB_LIB=build_exp/libpmb200_lanprof.so python tools/eig_prof.py 1000 6
+for a in "1000 6" "2000 10" "5000 20" "700 3" "300 40"; do python tools/eig_bench.py $a 3; done 2>&1 | grep -v "rep [12]"
+timeout 600 python -m pytest tests -x -q -m gpu -k "eig or c5 or implied or lanczos or enhanced or msm" 2>&1 | tail -3
