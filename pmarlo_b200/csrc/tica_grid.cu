@@ -7,6 +7,7 @@
 // barriers instead of d - 1 (see jacobi_grid).  Data that other CTAs wrote is always read with
 // ld.global.cg (L2), never through L1.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -90,8 +91,25 @@ __device__ __forceinline__ void tg_rotation(double a, double b, double g, double
 // in-block pairs nb - 1 times per sweep: 1.8x the depth for the same number of sweeps.)
 // NPL = elements of a row per lane (n <= 32 NPL): the loops are fully unrolled, a warp holds its two
 // rows in registers for the duration of a rotation and the global loads are batched.
+// The barrier between rounds.  Only d / (2 b) <= 16 CTAs own a block pair, so the whole solve runs on ONE
+// 16-CTA thread-block cluster when the device can place it: barrier.cluster (hardware, release / acquire at
+// cluster scope, which orders the global-memory traffic between the CTAs of the cluster) instead of the
+// cooperative-groups grid barrier over 148 CTAs (an atomic counter in L2 and a polling loop, ~1.5 us per
+// barrier, 960 barriers per solve).  cluster == false is the cooperative launch (fallback).
+struct TgBar {
+  bool cluster;
+  __device__ __forceinline__ void sync() const {
+    if (cluster) {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+      cg::this_grid().sync();
+    }
+  }
+};
+
 template <int NPL>
-__device__ int jacobi_grid(cg::grid_group& grid, double* W, int n, int b, int* flags, double* sm) {
+__device__ int jacobi_grid(TgBar& grid, double* W, int n, int b, int* flags, double* sm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   int nb = (n + b - 1) / b;
   if (nb & 1) ++nb;
@@ -375,7 +393,7 @@ __device__ int jacobi_grid(cg::grid_group& grid, double* W, int n, int b, int* f
 }
 
 // order[rk] = index of the rk-th largest |vals| (stable); one value per thread over the grid, then a grid barrier
-__device__ void rank_grid(cg::grid_group& grid, const double* vals, int n, int* order) {
+__device__ void rank_grid(TgBar& grid, const double* vals, int n, int* order) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const double aj = fabs(ldg_cg(vals + j));
     int rk = 0;
@@ -393,9 +411,9 @@ template <int NPL>
 __global__ void __launch_bounds__(kTgThreads, 1) tica_solve_grid_kernel(
     const double* __restrict__ C00, const double* __restrict__ C0t, int d, double eps,
     double* __restrict__ evals, double* __restrict__ evecs, int32_t* __restrict__ rank_out, TicaGridWs ws,
-    int blk) {
+    int blk, int cluster_mode) {
   extern __shared__ __align__(16) double tg_sm[];
-  cg::grid_group grid = cg::this_grid();
+  TgBar grid{cluster_mode != 0};
   const long long t_begin = clock64();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int q = 0; q < 8; ++q) g_tg_dbg[q] = 0;
@@ -653,11 +671,39 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   // the dense phases.  (The in-kernel trace -- clock64 against %globaltimer per sweep, pmb_debug_trace_tica --
   // shows the kernel at the full SM clock in every run; stage-time outliers seen in round 1 were host-side
   // allocator stalls in front of the launch, not the kernel.)
+  int cluster_mode = 0;
+  void* args[] = {(void*)&C00, (void*)&C0t, (void*)&d, (void*)&eps, (void*)&evals, (void*)&evecs, (void*)&rank, (void*)&w,
+                  (void*)&blk, (void*)&cluster_mode};
+  // Preferred: one cluster of 16 CTAs (non-portable size), hardware cluster barriers.
+  static const int allow_cluster = [] { const char* e = getenv("PMB_TICA_CLUSTER"); return e ? atoi(e) : 1; }();
+  if (allow_cluster && nb / 2 <= 16) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16);
+    cfg.blockDim = dim3(kTgThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) == cudaSuccess && n_clusters >= 1) {
+      cluster_mode = 1;
+      PMB_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+      count_launch();
+      return PMB_OK;
+    }
+    (void)cudaGetLastError();   // no room for a 16-CTA cluster: cooperative launch below
+  }
+  // One CTA per SM even though only nb / 2 of them own a block pair: the others join the grid barriers and
+  // the dense phases.
   int grid = sms;
   if (grid < nb / 2) grid = nb / 2;
   if (grid > sms * per_sm) grid = sms * per_sm;
-  void* args[] = {(void*)&C00, (void*)&C0t, (void*)&d, (void*)&eps, (void*)&evals, (void*)&evecs, (void*)&rank, (void*)&w,
-                  (void*)&blk};
   PMB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kTgThreads), args, smem, st));
   count_launch();
   return PMB_OK;

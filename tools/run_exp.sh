@@ -1,3 +1,6 @@
-PMB_LIB=build_exp/libpmb200_lanprof.so python tools/eig_prof.py 1000 6
-for a in "1000 6" "2000 10" "5000 20" "700 3" "300 40"; do python tools/eig_bench.py $a 3; done 2>&1 | grep -v "rep [12]"
-timeout 600 python -m pytest tests -x -q -m gpu -k "eig or c5 or implied or lanczos or enhanced or msm" 2>&1 | tail -3
+PMB_TICA_CLUSTER=0 python tools/tica_bench.py 256
+PMB_TICA_CLUSTER=1 python tools/tica_bench.py 256
+PMB_TICA_CLUSTER=0 python tools/tica_bench.py 84
+PMB_TICA_CLUSTER=1 python tools/tica_bench.py 84
+PMB_TICA_CLUSTER=1 python tools/tica_bench.py 512 3
+timeout 600 python -m pytest tests -x -q -m gpu -k "tica or vamp or reduce" 2>&1 | tail -3
