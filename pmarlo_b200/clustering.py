@@ -104,7 +104,12 @@ def subsampled_hints(Y: torch.Tensor, centers: torch.Tensor, stride: int = _HINT
     10 M frames, K = 1000).  Hints only ever skip work; labels do not depend on them."""
     n = int(Y.shape[0])
     sub = kernels.kmeans_assign(Y[::stride], centers)
-    return sub.repeat_interleave(stride)[:n].contiguous()
+    hints = sub.repeat_interleave(stride)[:n].contiguous()
+    # Frames in no particular order (shuffled data) make the neighbour's centre a useless bound that only costs
+    # the gather: when fewer than a tenth of the consecutive subsampled frames share their label the hints
+    # are withdrawn (-1 = no hint), decided on the device without a host read-back.
+    smooth = (sub[1:] == sub[:-1]).to(torch.float32).mean() >= 0.1 if sub.numel() > 1 else torch.ones((), dtype=torch.bool, device=Y.device)
+    return torch.where(smooth, hints, torch.full_like(hints, -1))
 
 
 def lloyd_device(Y: torch.Tensor, initial_centers: torch.Tensor, max_iter: int = 500,

@@ -161,6 +161,54 @@ __global__ void __launch_bounds__(1024) kmeans_tc_prep_kernel(KmTcParams p) {
   const uint32_t sbo = (uint32_t)(KS / 8) * 128u;
   const size_t chunk_bytes = (size_t)kTcChunk * KS * 2;
   float cmax2 = 0.f;
+  if (D <= kTcDReg) {
+    // a centre's row of the operand image is KS / 8 pieces of 16 bytes (8 slots of one core-matrix row): built in
+    // registers and stored as vectors, the D coordinate loads issued together (the generic loop below pays D
+    // dependent L2 round trips and 2-byte stores: 23 us per launch, 22 launches per Lloyd run)
+    for (int k = tid; k < p.Kpad; k += blockDim.x) {
+      const int src = k < K ? k : K - 1;
+      double cd[kTcDReg];
+#pragma unroll
+      for (int d = 0; d < kTcDReg; ++d) cd[d] = d < D ? p.centers[(size_t)src * D + d] : 0.0;
+      __half hs[64];
+#pragma unroll
+      for (int sl = 0; sl < 64; ++sl) hs[sl] = __float2half_rn(0.f);
+      double n2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < kTcDReg; ++d) {
+        if (d < D) {
+          const float c32 = (float)cd[d];
+          n2 = fma((double)c32, (double)c32, n2);
+          const float cs = c32 * sc;
+          if (k < K) p.cs32[(size_t)k * D + d] = cs;
+          const float cm = -2.0f * cs;
+          const __half hh = __float2half_rn(cm);
+          hs[2 + 3 * d + 0] = hh;
+          hs[2 + 3 * d + 1] = hh;
+          hs[2 + 3 * d + 2] = __float2half_rn(cm - __half2float(hh));
+        }
+      }
+      const double n2s = n2 * (double)sc * (double)sc;
+      const double q = n2s / (double)kTcNormUnit;
+      const float p1 = __half2float(__float2half_rn((float)q));
+      hs[0] = __float2half_rn(p1);
+      hs[1] = __float2half_rn(k < K ? (float)(q - (double)p1) : 30000.0f);
+      if (k < K) cmax2 = fmaxf(cmax2, (float)n2s * 1.0001f);
+      unsigned char* rowp = p.Bg + (size_t)(k / kTcChunk) * chunk_bytes + (uint32_t)((k % kTcChunk) >> 3) * sbo +
+                            (uint32_t)(k & 7) * 16u;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (8 * g < KS) {
+          uint4 w;
+          w.x = (uint32_t)__half_as_ushort(hs[8 * g + 0]) | ((uint32_t)__half_as_ushort(hs[8 * g + 1]) << 16);
+          w.y = (uint32_t)__half_as_ushort(hs[8 * g + 2]) | ((uint32_t)__half_as_ushort(hs[8 * g + 3]) << 16);
+          w.z = (uint32_t)__half_as_ushort(hs[8 * g + 4]) | ((uint32_t)__half_as_ushort(hs[8 * g + 5]) << 16);
+          w.w = (uint32_t)__half_as_ushort(hs[8 * g + 6]) | ((uint32_t)__half_as_ushort(hs[8 * g + 7]) << 16);
+          *reinterpret_cast<uint4*>(rowp + (uint32_t)g * 128u) = w;
+        }
+      }
+    }
+  } else
   for (int k = tid; k < p.Kpad; k += blockDim.x) {
     unsigned char* base = p.Bg + (size_t)(k / kTcChunk) * chunk_bytes;
     const int r = k % kTcChunk;
@@ -924,6 +972,34 @@ __global__ void __launch_bounds__(256) kmeans_recheck_kernel(KmTcParams p) {
     // labelled 0 instead of indexing the accumulators out of bounds
     double bd = 1.7976931348623157e308;
     int bk = 0;
+    if (D <= kTcDReg) {
+      // the row in registers and four centres per lane in flight: the per-centre sum keeps the oracle's order
+      // (sub, mul, add, no fma) and the centres are still visited in increasing k, so labels are unchanged; the
+      // plain loop below is a chain of ~32 x D dependent operations per lane (45 us per launch)
+      double yr[kTcDReg];
+#pragma unroll
+      for (int d = 0; d < kTcDReg; ++d) yr[d] = d < D ? (double)p.Y[row * p.ld + d] : 0.0;
+      for (int k0 = lane; k0 < K; k0 += 128) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = 0; d < kTcDReg; ++d) {
+          if (d < D) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k = k0 + 32 * u;
+              const double cv = k < K ? p.centers[(size_t)k * D + d] : 0.0;
+              const double t = __dsub_rn(yr[d], cv);
+              acc[u] = __dadd_rn(acc[u], __dmul_rn(t, t));
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 32 * u;
+          if (k < K && acc[u] < bd) { bd = acc[u]; bk = k; }
+        }
+      }
+    } else
     for (int k = lane; k < K; k += 32) {
       double acc = 0.0;
       const double* c = p.centers + (size_t)k * D;
@@ -954,14 +1030,34 @@ __global__ void __launch_bounds__(256) kmeans_tc_fold_kernel(KmTcParams p) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n_sum = (size_t)p.K * p.D, n_all = n_sum + (size_t)p.K;
   if (e >= n_all) return;
+  // four partial sums in a fixed pattern, sixteen loads in flight: a single running sum walked the copies as a
+  // chain of dependent L2 round trips (36 us per launch)
   if (e < n_sum) {
-    double v = 0.0;
-    for (int c = 0; c < p.ncopies; ++c) v += p.lsums[(size_t)c * p.copy_stride + e];
-    p.lsums[e] = v;
+    const double* src = p.lsums + e;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    int c = 0;
+#pragma unroll 4
+    for (; c + 4 <= p.ncopies; c += 4) {
+      v0 += __ldcg(src + (size_t)c * p.copy_stride);
+      v1 += __ldcg(src + (size_t)(c + 1) * p.copy_stride);
+      v2 += __ldcg(src + (size_t)(c + 2) * p.copy_stride);
+      v3 += __ldcg(src + (size_t)(c + 3) * p.copy_stride);
+    }
+    for (; c < p.ncopies; ++c) v0 += __ldcg(src + (size_t)c * p.copy_stride);
+    p.lsums[e] = (v0 + v1) + (v2 + v3);
   } else {
-    unsigned long long v = 0;
-    for (int c = 0; c < p.ncopies; ++c) v += p.lcounts[(size_t)c * p.copy_stride + (e - n_sum)];
-    p.lcounts[e - n_sum] = v;
+    const unsigned long long* src = p.lcounts + (e - n_sum);
+    unsigned long long v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    int c = 0;
+#pragma unroll 4
+    for (; c + 4 <= p.ncopies; c += 4) {
+      v0 += __ldcg(src + (size_t)c * p.copy_stride);
+      v1 += __ldcg(src + (size_t)(c + 1) * p.copy_stride);
+      v2 += __ldcg(src + (size_t)(c + 2) * p.copy_stride);
+      v3 += __ldcg(src + (size_t)(c + 3) * p.copy_stride);
+    }
+    for (; c < p.ncopies; ++c) v0 += __ldcg(src + (size_t)c * p.copy_stride);
+    p.lcounts[e - n_sum] = (v0 + v1) + (v2 + v3);
   }
 }
 

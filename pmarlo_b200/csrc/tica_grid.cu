@@ -676,7 +676,7 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
                   (void*)&blk, (void*)&cluster_mode};
   // Preferred: one cluster of 16 CTAs (non-portable size), hardware cluster barriers.
   static const int allow_cluster = [] { const char* e = getenv("PMB_TICA_CLUSTER"); return e ? atoi(e) : 1; }();
-  if (allow_cluster && nb / 2 <= 16) {
+  if (allow_cluster && nb / 2 <= 16 && d <= 128) {   // d = 256: the dense phases on 16 SMs cost what the barriers save (8.3 vs 7.9 ms in the bench)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(16);
     cfg.blockDim = dim3(kTgThreads);
