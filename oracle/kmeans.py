@@ -74,8 +74,11 @@ def lloyd(Y: np.ndarray, initial_centers: np.ndarray, max_iter: int = 500,
     while True:
         labels, _ = assign(Y, centers)
         centers, _ = _update(Y, labels, centers)
-        _, dmin = assign(Y, centers)
-        cost = float(dmin.sum())
+        # deeptime kmeans.h cluster_loop: costAssignFunction(data, NEW centres, the assignments of the cluster
+        # step), i.e. the inertia of the updated centres under the labels that produced them -- not under a
+        # re-assignment (restated from the published source; deeptime is absent from the image: unpinned)
+        diff = Y - centers[labels]
+        cost = float(np.sum(diff * diff))
         rel = abs(cost - prev_cost) / cost if cost != 0.0 else 0.0
         prev_cost = cost
         it += 1

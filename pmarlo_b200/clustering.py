@@ -125,7 +125,6 @@ def lloyd_device(Y: torch.Tensor, initial_centers: torch.Tensor, max_iter: int =
     if labels is None:
         labels = torch.empty((int(Y.shape[0]),), dtype=torch.int32, device=Y.device)
     prev_cost, cost, it, converged = 0.0, None, 0, False
-    pending = False  # an update whose cost has not been measured yet
     # the first iteration starts from the labels of a 1-in-16 subsample; later ones pass the previous labels as hints
     hints = subsampled_hints(Y, centers) if (Y.dtype == torch.float32 and int(Y.shape[0]) >= _HINT_MIN_FRAMES) else None
     while True:
@@ -135,18 +134,25 @@ def lloyd_device(Y: torch.Tensor, initial_centers: torch.Tensor, max_iter: int =
                                   inertia=acc.inertia, hints=hints)
         hints = labels
         acc.allreduce(comm)
-        if pending and tolerance is not None:
-            cost = float(acc.inertia.item())   # cost of the centres produced by iteration `it`
+        old = centers.clone() if tolerance is not None else None
+        kernels.kmeans_update(centers, acc.sums, acc.counts)
+        it += 1
+        if tolerance is not None:
+            # deeptime's cluster_loop measures the NEW centres under the assignments that produced them
+            # (costAssignFunction(data, newCenters, assignments)): with S_k, n_k of this iteration
+            #   cost = sum |y|^2 + sum_k (n_k |c_k|^2 - 2 c_k . S_k),
+            # and the kernel's inertia is the same expression at the old centres -- no second assignment.
+            nk = acc.counts.to(torch.float64)
+
+            def _centre_term(c):
+                return (nk * (c * c).sum(dim=1) - 2.0 * (c * acc.sums).sum(dim=1)).sum()
+
+            cost = float((acc.inertia[0] - _centre_term(old) + _centre_term(centers)).item())
             rel = abs(cost - prev_cost) / cost if cost != 0.0 else 0.0
             prev_cost = cost
             if rel <= tolerance:
                 converged = True
         if converged or it >= max_iter:
-            break
-        kernels.kmeans_update(centers, acc.sums, acc.counts)
-        it += 1
-        pending = True
-        if tolerance is None and it >= max_iter:
             break
     return LloydResult(centers, it, cost, converged)
 
