@@ -392,6 +392,144 @@ __device__ int jacobi_grid(TgBar& grid, double* W, int n, int b, int* flags, dou
   return sweep;
 }
 
+// Pivoted Cholesky A = G G^T of a symmetric positive semidefinite n x n matrix, on ONE CTA, without
+// interchanges: a step takes a large residual diagonal entry p, g = (A[:, p] - sum_{j<k} g_j g_j[p]) /
+// sqrt(residual_pp), entries of already chosen indices are exactly zero.  W[k][:] = g_k^T for k < r (the numerical
+// rank: the point at which the largest residual diagonal falls below n eps max diag), zero rows after.
+// Why: the one-sided Jacobi sweeps orthogonalise the ROWS of W.  Started from W = A their Gram matrix is A^2 (the
+// condition number squared: 18-19 sweeps for the bench's C00, cond ~1e8); started from W = G^T the Gram matrix
+// G^T G is similar to A itself and pivoting has already ordered and nearly orthogonalised the rows: 11 sweeps
+// (Drmac / Veselic preconditioning).  At convergence row j is sqrt(lambda_j) v_j^T instead of lambda_j v_j^T: the
+// caller takes v_j = w_j / |w_j| and the Rayleigh quotient as before.
+// Blocked by 8: the pivots of a block are the 8 largest residual diagonals at its start, their 8 columns come
+// from ONE pass over the k rows already in W (a column-at-a-time version paid one chain of L2 round trips per
+// column: 2.3 ms for n = 256, more than the sweeps it saved), then the block is factorised in registers / shared
+// memory; a candidate whose residual has collapsed inside the block (< 1/4 of its value at the start: nearly
+// dependent on an earlier pivot of the block) is left for a later block.  Any order of positive pivots gives a
+// valid factorisation; the order only matters for the preconditioning.
+// NQ threads per column index i (n <= 512 / NQ), each owning 8 / NQ of the block's columns.
+// Shared memory: diag[n], gcol[n], gp[8][n] doubles, done[n], sel[n] ints (11 n doubles).
+template <int NQ>
+__device__ int chol_pivoted_cta(const double* __restrict__ A, int n, double* __restrict__ W, double* sm) {
+  constexpr int B = 8, BQ = B / NQ;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double s_val[kTgThreads / 32];
+  __shared__ int s_idx[kTgThreads / 32];
+  __shared__ int s_cand[B];
+  __shared__ double s_d0[B], s_pivot[B];
+  __shared__ int s_accept[B];
+  __shared__ int s_nb;
+  __shared__ double s_thresh;
+  double* diag = sm;
+  double* gcol = sm + n;
+  double* gp = sm + 2 * (size_t)n;
+  int* done = reinterpret_cast<int*>(gp + (size_t)B * n);
+  int* sel = done + n;
+  const int i = tid % n, q = tid / n;
+  const bool act = q < NQ;
+  for (int e = tid; e < n; e += T) { diag[e] = ldg_cg(A + (size_t)e * n + e); done[e] = 0; }
+  if (tid == 0) s_thresh = -1.0;
+  __syncthreads();
+  int kk = 0;
+  while (kk < n) {
+    // 1. up to B candidates: the largest residual diagonals among the indices not chosen yet
+    for (int e = tid; e < n; e += T) sel[e] = 0;
+    if (tid == 0) s_nb = 0;
+    __syncthreads();
+    for (int t = 0; t < B; ++t) {
+      double bv = -1.0;
+      int bi = 0x7fffffff;
+      for (int e = tid; e < n; e += T) {
+        const double v = (done[e] || sel[e]) ? -1.0 : diag[e];
+        if (v > bv) { bv = v; bi = e; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        double v = s_val[0];
+        int ix = s_idx[0];
+        for (int w = 1; w < (T >> 5); ++w)
+          if (s_val[w] > v || (s_val[w] == v && s_idx[w] < ix)) { v = s_val[w]; ix = s_idx[w]; }
+        if (s_thresh < 0.0) s_thresh = fmax(v, 0.0) * (double)n * 2.220446049250313e-16;
+        if (v > s_thresh && ix < n) { s_cand[t] = ix; s_d0[t] = v; sel[ix] = 1; s_nb = t + 1; }
+      }
+      __syncthreads();
+      if (s_nb != t + 1) break;   // uniform: nothing left above the threshold
+    }
+    const int nb = s_nb;
+    if (nb == 0) break;
+    const double thresh = s_thresh;
+    // 2. the pivots' rows of G (gp[t][j] = W[j][p_t], j < kk) and their columns of A
+    for (int e = tid; e < nb * kk; e += T) {
+      const int t = e / kk, j = e - t * kk;
+      gp[(size_t)t * n + j] = ldg_cg(W + (size_t)j * n + s_cand[t]);
+    }
+    double c[BQ];
+#pragma unroll
+    for (int u = 0; u < BQ; ++u) {
+      const int t = q * BQ + u;
+      c[u] = 0.0;
+      if (act && t < nb) {
+        const int pt = s_cand[t];
+        c[u] = 0.5 * (ldg_cg(A + (size_t)i * n + pt) + ldg_cg(A + (size_t)pt * n + i));
+      }
+    }
+    __syncthreads();
+    // 3. one pass over the rows already in W for all columns of the block
+    if (act) {
+      const double* gq = gp + (size_t)q * BQ * n;
+#pragma unroll 8
+      for (int j = 0; j < kk; ++j) {
+        const double w = ldg_cg(W + (size_t)j * n + i);
+#pragma unroll
+        for (int u = 0; u < BQ; ++u) c[u] = fma(-w, gq[(size_t)u * n + j], c[u]);
+      }
+    }
+    // 4. factorise the block
+    for (int t = 0; t < nb; ++t) {
+      const int pt = s_cand[t], tq = t / BQ, tu = t - tq * BQ;
+      double ct = 0.0;
+#pragma unroll
+      for (int u = 0; u < BQ; ++u) ct = (u == tu) ? c[u] : ct;
+      if (act && q == tq && i == pt) {
+        s_pivot[t] = ct;
+        s_accept[t] = (ct > thresh && ct >= 0.25 * s_d0[t]) ? 1 : 0;
+      }
+      __syncthreads();
+      if (!s_accept[t]) continue;   // uniform; the index stays available for a later block
+      const double root = sqrt(s_pivot[t]), rinv = 1.0 / root;
+      if (act && q == tq) {
+        double g = done[i] ? 0.0 : ct * rinv;
+        if (i == pt) g = root;
+        W[(size_t)kk * n + i] = g;
+        gcol[i] = g;
+        diag[i] -= g * g;
+      }
+      __syncthreads();
+      if (act) {
+        const double gi = gcol[i];
+#pragma unroll
+        for (int u = 0; u < BQ; ++u) {
+          const int tt = q * BQ + u;
+          if (tt > t && tt < nb) c[u] = fma(-gi, gcol[s_cand[tt]], c[u]);
+        }
+      }
+      if (tid == 0) done[pt] = 1;
+      ++kk;
+      __syncthreads();
+    }
+  }
+  for (size_t idx = (size_t)kk * n + tid; idx < (size_t)n * n; idx += T) W[idx] = 0.0;
+  __syncthreads();
+  return kk;
+}
+
 // order[rk] = index of the rk-th largest |vals| (stable); one value per thread over the grid, then a grid barrier
 __device__ void rank_grid(TgBar& grid, const double* vals, int n, int* order) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -411,7 +549,7 @@ template <int NPL>
 __global__ void __launch_bounds__(kTgThreads, 1) tica_solve_grid_kernel(
     const double* __restrict__ C00, const double* __restrict__ C0t, int d, double eps,
     double* __restrict__ evals, double* __restrict__ evecs, int32_t* __restrict__ rank_out, TicaGridWs ws,
-    int blk, int cluster_mode) {
+    int blk, int cluster_mode, int use_chol) {
   extern __shared__ __align__(16) double tg_sm[];
   TgBar grid{cluster_mode != 0};
   const long long t_begin = clock64();
@@ -432,13 +570,24 @@ __global__ void __launch_bounds__(kTgThreads, 1) tica_solve_grid_kernel(
   // 1. eig(C00)
   for (size_t i = gtid; i < dd; i += gnt) {
     const int r = (int)(i / d), c = (int)(i - (size_t)r * d);
-    ws.W[i] = 0.5 * (C00[i] + C00[(size_t)c * d + r]);
+    const double a = 0.5 * (C00[i] + C00[(size_t)c * d + r]);
+    ws.W[i] = a;
+    if (use_chol) ws.TMP[i] = a;
   }
   grid.sync();
   // Rotations are NOT accumulated: at convergence row j of W is lambda_j v_j^T, so v_j = w_j / |w_j| and the
   // signed eigenvalue is the Rayleigh quotient v_j^T C00 v_j.  (Rows whose norm is at rounding level carry no
   // direction; they get eigenvalue 0 and are removed by the rank cut.)  This halves the shared-memory
   // traffic that bounds a local Jacobi round.
+  if (use_chol) {
+    // W <- G^T of the pivoted Cholesky factorisation of sym(C00) (one CTA; see chol_pivoted_cta).  ws.W holds
+    // sym(C00) at this point and is the output: the input is read from the TMP copy made above.
+    if (blockIdx.x == 0) {
+      if (d <= kTgThreads / 2) chol_pivoted_cta<2>(ws.TMP, d, ws.W, tg_sm);
+      else chol_pivoted_cta<1>(ws.TMP, d, ws.W, tg_sm);
+    }
+    grid.sync();
+  }
   const int sweeps1 = jacobi_grid<NPL>(grid, ws.W, d, blk, ws.ctrl + 1, tg_sm);
   for (int j = gwarp; j < d; j += nwarps) {
     double acc = 0.0;
@@ -571,9 +720,11 @@ __global__ void __launch_bounds__(kTgThreads, 1) tica_solve_grid_kernel(
   grid.sync();   // everyone has read M before W/V are overwritten
   for (size_t i = gtid; i < (size_t)m * m; i += gnt) {
     const int r = (int)(i / m), c = (int)(i - (size_t)r * m);
-    ws.W[i] = 0.5 * (ldg_cg(ws.M + i) + ldg_cg(ws.M + (size_t)c * m + r)) + ((r == c) ? sigma : 0.0);
+    const double a = 0.5 * (ldg_cg(ws.M + i) + ldg_cg(ws.M + (size_t)c * m + r)) + ((r == c) ? sigma : 0.0);
+    ws.W[i] = a;
   }
   grid.sync();
+  // (the Cholesky preconditioner does not pay here: sym(M) + sigma I has condition ~30, 12 sweeps either way)
   // W = sym(M) + sigma I is positive definite: eigenvalue_j = |w_j| - sigma, v_j = w_j / |w_j|
   const int sweeps2 = jacobi_grid<NPL>(grid, ws.W, m, blk, ws.ctrl + 1, tg_sm);
   for (int j = gwarp; j < m; j += nwarps) {
@@ -672,8 +823,10 @@ int tica_solve_grid_launch(const double* C00, const double* C0t, int d, double e
   // shows the kernel at the full SM clock in every run; stage-time outliers seen in round 1 were host-side
   // allocator stalls in front of the launch, not the kernel.)
   int cluster_mode = 0;
+  static const int chol_env = [] { const char* e = getenv("PMB_TICA_CHOL"); return e ? atoi(e) : 1; }();
+  int use_chol = (chol_env && d <= kTgThreads) ? 1 : 0;
   void* args[] = {(void*)&C00, (void*)&C0t, (void*)&d, (void*)&eps, (void*)&evals, (void*)&evecs, (void*)&rank, (void*)&w,
-                  (void*)&blk, (void*)&cluster_mode};
+                  (void*)&blk, (void*)&cluster_mode, (void*)&use_chol};
   // Preferred: one cluster of 16 CTAs (non-portable size), hardware cluster barriers.
   static const int allow_cluster = [] { const char* e = getenv("PMB_TICA_CLUSTER"); return e ? atoi(e) : 1; }();
   if (allow_cluster && nb / 2 <= 16 && d <= 128) {   // d = 256: the dense phases on 16 SMs cost what the barriers save (8.3 vs 7.9 ms in the bench)

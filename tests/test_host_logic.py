@@ -538,6 +538,79 @@ def test_numpy_model_of_the_ritz_value_multisection():
         assert passes <= 12
 
 
+def test_numpy_model_of_the_cholesky_preconditioned_jacobi():
+    """tica_grid.cu: the one-sided Jacobi sweeps for eig(C00) start from W = G^T of a pivoted Cholesky
+    factorisation C00 = G G^T (chol_pivoted_cta: no interchanges, blocks of 8 pivots chosen by residual
+    diagonal, a collapsed candidate deferred) instead of from W = C00.  The model restates the blocked
+    factorisation and the row sweeps with the kernel's stopping rule on an ill-conditioned correlation matrix:
+    G G^T = C00 to rounding, the eigenvalues |w_j|^2 match eigvalsh, and the sweep count drops."""
+    rng = np.random.default_rng(0)
+    d, n = 64, 4000
+    x = rng.standard_normal((n, d)).cumsum(axis=0) * 0.02 + rng.standard_normal((n, d))
+    x[:, d // 2:] = 0.9 * x[:, :d - d // 2] + 0.1 * x[:, d // 2:]      # nearly dependent pairs of columns
+    x -= x.mean(0)
+    x /= x.std(0)
+    C = x.T @ x / n
+
+    def chol_blocked(A, B=8):
+        n_ = A.shape[0]
+        diag = np.diag(A).copy()
+        done = np.zeros(n_, dtype=bool)
+        rows = []
+        thresh = diag.max() * n_ * 2.220446049250313e-16
+        while len(rows) < n_:
+            cand_val = np.where(done, -1.0, diag)
+            cand = [int(i) for i in np.argsort(-cand_val, kind="stable")[:B] if cand_val[i] > thresh]
+            if not cand:
+                break
+            G = np.array(rows) if rows else np.zeros((0, n_))
+            cols = {p: A[:, p] - G.T @ G[:, p] for p in cand}
+            d0 = {p: diag[p] for p in cand}
+            for t, p in enumerate(cand):
+                piv = cols[p][p]
+                if not (piv > thresh and piv >= 0.25 * d0[p]):
+                    continue
+                g = np.where(done, 0.0, cols[p] / np.sqrt(piv))
+                g[p] = np.sqrt(piv)
+                rows.append(g)
+                diag -= g * g
+                done[p] = True
+                for p2 in cand[t + 1:]:
+                    cols[p2] = cols[p2] - g * g[p2]
+        return np.array(rows)
+
+    def sweeps(W, tol=4.5e-16):
+        W = W.copy()
+        m = W.shape[0]
+        tol2 = tol * tol * W.shape[1]
+        for s_ in range(60):
+            rot = big = 0
+            for i in range(m - 1):
+                for j in range(i + 1, m):
+                    a, b, g = W[i] @ W[i], W[j] @ W[j], W[i] @ W[j]
+                    if g * g <= tol2 * a * b:
+                        continue
+                    rot += 1
+                    big += g * g > 1e-20 * a * b
+                    zeta = (b - a) / (2 * g)
+                    t = np.sign(zeta) / (abs(zeta) + np.sqrt(1 + zeta * zeta)) if zeta != 0 else 1.0
+                    c = 1 / np.sqrt(1 + t * t)
+                    W[i], W[j] = c * W[i] - c * t * W[j], c * t * W[i] + c * W[j]
+            if rot == 0 or big == 0:
+                return s_ + 1, W
+        return 60, W
+
+    G = chol_blocked(C)
+    assert G.shape[0] == d
+    np.testing.assert_allclose(G.T @ G, C, rtol=0, atol=1e-13)
+    ref = np.sort(np.linalg.eigvalsh(C))[::-1]
+    s_plain, W1 = sweeps(C)
+    s_chol, W2 = sweeps(G)
+    np.testing.assert_allclose(np.sort(np.linalg.norm(W1, axis=1))[::-1], ref, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np.sort(np.linalg.norm(W2, axis=1) ** 2)[::-1], ref, rtol=0, atol=1e-12)
+    assert s_chol + 2 <= s_plain, (s_chol, s_plain)
+
+
 def test_candidate_lag_ladder_matches_reference_golden(golden):
     """utils/msm_utils.py:21-105 -- outputs of the genuine reference function (tests/golden/make_golden.py::make_ladders)."""
     from pmarlo_b200 import candidate_lag_ladder

@@ -34,5 +34,5 @@ for it in range(reps):
 import scipy.linalg as sl
 ref = np.sort(sl.eigh(C0t.cpu().numpy(), C00.cpu().numpy(), eigvals_only=True))[::-1]
 got = np.sort(ev.cpu().numpy())[::-1]
-print(f"cluster={os.environ.get('PMB_TICA_CLUSTER', '1')} d={d}: {np.median(ts[1:]):.3f} ms  rank={int(rank[0])}  "
+print(f"cluster={os.environ.get('PMB_TICA_CLUSTER', '1')} chol={os.environ.get('PMB_TICA_CHOL', '1')} d={d}: {np.median(ts[1:]):.3f} ms  rank={int(rank[0])} sweeps={int(rank[1])}+{int(rank[2])}  "
       f"max |ev - scipy| = {np.abs(got - ref).max():.2e}  checksum={float(ev.sum()):.17g} {float(V.abs().sum()):.17g}")
