@@ -295,7 +295,8 @@ static int launch_project_warp_mpf(const float* X, int64_t n, int d, int64_t ld,
   // 3 CTAs of 4 warps at 168 registers 2.70 ms, 2 frames in flight 3.8 ms (bytes in flight bound it); staging
   // the rows through a bulk-copy ring in shared memory gave 2.77 ms for 2..6 stages (issue-bound by then).
   // The 168-register form spills for the wide slices, which stay on one CTA of 8 warps.
-  if (J * MPF <= 20) return launch_project_warp_cfg<J, MPF, 4, 3, 4>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+  if constexpr (J * MPF <= 20) return launch_project_warp_cfg<J, MPF, 4, 3, 4>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
+  else
   return launch_project_warp_cfg<J, MPF, 8, 1, 4>(X, n, d, ld, a, nanfill, W, m, Y, ldy, st);
 }
 
