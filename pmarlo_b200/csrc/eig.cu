@@ -11,10 +11,12 @@
 //    orthogonality nears sqrt(eps), the three-term recurrence in between) in
 //    ONE cooperative kernel: the mat-vec streams T once per step
 //    (8 K^2 bytes, L2-resident for K = 1000), a step costs 3-5 grid barriers and
-//    is latency-bound; the Ritz values of the m x m
-//    tridiagonal matrix come from Sturm-sequence bisection (one thread per
-//    eigenvalue).  Convergence flag: the k leading Ritz values of T_m and of
-//    T_{m - m/8} agree to 1e-10.
+//    is latency-bound; the Ritz values wanted are the two ends of the spectrum
+//    of the m x m tridiagonal matrix: one warp per eigenvalue, 32-way
+//    multisection with a division-free Sturm count (sturm_count_minors); the
+//    one-thread-per-eigenvalue quotient-form bisection remains for k > 32.
+//    Convergence flag: the k leading Ritz values of T_m and of T_{m - m/8}
+//    agree to 1e-10.
 #include <cooperative_groups.h>
 
 #include "common.cuh"

@@ -25,7 +25,8 @@
 //   warp  16     MMA issuer: per chunk KS/16 tcgen05.mma (M 128, N 128) into the next of FOUR TMEM buffers
 //   warp  17     loader    : bulk copies of centre chunks into the shared-memory ring
 //   warps 18-21  producers : build the A tile (128 frames x KS slots, K-major core-matrix layout) and the
-//                            per-row screening threshold from the hinted centre (rows prefetched)
+//                            per-row screening threshold from the hinted centre (hint prefetched two tiles
+//                            ahead, row and hinted centre one tile ahead)
 //   warps 22-25  finalisers: merge the groups, certainty test, labels, fused Lloyd accumulation
 //
 // Exactness: a frame whose best and second-best scores are closer than a bound on the arithmetic
@@ -55,7 +56,8 @@ __device__ long long g_km_dbg[16];
 #endif
 
 #ifndef PMB_KM_EPI
-#define PMB_KM_EPI 1   // 0: every epilogue warp reads one block of every buffer; 1: one warp group per ring slot
+#define PMB_KM_EPI 1   // 0: every epilogue warp reads one block of every buffer; 1: one warp group per ring slot;
+                       // 2: two super-groups of eight warps on two ring slots each (measured slower, DESIGN.md 3.2 g)
 #endif
 constexpr int kTcTile = 128;     // frames per tile  (MMA M)
 constexpr int kTcChunk = 128;    // centres per MMA  (MMA N) = columns of one TMEM buffer

@@ -1,11 +1,13 @@
 // project.cu -- K5: TICA projection  y = (x_imputed - a) W  (skinny GEMM, HBM-bound).
 //
-// Reads 4*d bytes and writes 4*m (or 8*m) bytes per frame.  A CTA owns 256
-// consecutive frames; the feature axis is streamed through shared memory in
-// chunks of 32 columns (every warp load is one 128-byte line), stored with a
-// padded stride so that the thread-per-frame reads are bank-conflict free.
-// Arithmetic is fp64 (W, a in shared memory, broadcast reads) so that the
-// projection itself adds no error beyond the fp32 input.
+// Reads 4*d bytes and writes 4*m (or 8*m) bytes per frame.  Three kernels:
+//  * project_warp_kernel (the pipeline's path: d <= 256, m <= 16, fp32 output): a warp per frame, the lane's
+//    slice of W in registers, packed fp32 FMAs, recursive-halving reduction over the lanes;
+//  * project_fast_kernel (wider d, fp32 output): a thread per frame, W in shared memory as fp32;
+//  * project_kernel (fp64 output or m > 16): a CTA owns 256 consecutive frames; the feature axis is streamed
+//    through shared memory in chunks of 32 columns (every warp load is one 128-byte line), stored with a
+//    padded stride so that the thread-per-frame reads are bank-conflict free; arithmetic is fp64 (W, a in
+//    shared memory, broadcast reads) so that the projection itself adds no error beyond the fp32 input.
 #include "common.cuh"
 
 namespace pmb {
