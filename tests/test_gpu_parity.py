@@ -295,6 +295,62 @@ def test_maybe_apply_tica_drops_lag_frames():
     assert Y.shape == Yo.shape and parity.rel_err(Y, Yo) < 5e-6
 
 
+@pytest.mark.parametrize("d,m,n", [(256, 10, 5003), (256, 16, 4100), (256, 1, 777), (256, 13, 3000), (128, 4, 6001),
+                                   (64, 3, 2500), (200, 7, 3333), (84, 3, 1000), (320, 10, 2048)])
+def test_project_fp32_paths_vs_fp64(d, m, n):
+    """K5 with fp32 output: the warp-per-frame kernel (packed fp32 FMAs over m rounded up to even, the
+    lane-halving reduction with compile-time-zero slots skipped) for d <= 256 and the thread-per-frame kernel
+    beyond, against (impute(X) - a) W in fp64; NaN entries take the imputation value.  Tolerance: fp32
+    products summed pairwise, 1e-6 of the scale of the output."""
+    from pmarlo_b200 import kernels
+
+    g = torch.Generator(device=dev()).manual_seed(d * 1000 + m)
+    X = torch.randn((n, d), generator=g, device=dev(), dtype=torch.float32) * 0.7 + 0.3
+    X[5, min(7, d - 1)] = float("nan")
+    X[n - 1, 0] = float("nan")
+    a = 0.3 + 1e-3 * torch.randn(d, generator=g, device=dev(), dtype=torch.float64)
+    fill = a + 0.01
+    W = torch.randn((d, m), generator=g, device=dev(), dtype=torch.float64) / d ** 0.5
+    Y = kernels.project(X, a, fill, W)
+    assert Y.dtype == torch.float32 and tuple(Y.shape) == (n, m)
+    Xd = X.double()
+    Xd = torch.where(torch.isnan(Xd), fill.expand_as(Xd), Xd)
+    ref = (Xd - a) @ W
+    err = float((Y.double() - ref).abs().max().item()) / float(ref.abs().max().item())
+    assert err < 1e-6, err
+    Y64 = kernels.project(X, a, fill, W, out_f64=True)
+    assert float((Y64 - ref).abs().max().item()) / float(ref.abs().max().item()) < 1e-12
+
+
+def test_subsampled_hints_never_change_labels():
+    """clustering.subsampled_hints: the labels of a 1-in-16 subsample repeated over the frames in between are
+    hints for the first (otherwise cold) Lloyd assignment.  Labels with the hints equal the cold labels on a
+    slow trajectory (hints kept) and on the same frames shuffled (hints withdrawn on the device: all -1)."""
+    from pmarlo_b200 import kernels
+    from pmarlo_b200.clustering import subsampled_hints
+
+    n, D, K = 300_000, 10, 300
+    rng = np.random.default_rng(3)
+    e = rng.standard_normal((n, D)).astype(np.float32)
+    y = np.empty((n, D), dtype=np.float32)
+    y[0] = e[0]
+    rho = np.float32(0.999)
+    s = np.float32(np.sqrt(1 - 0.999 ** 2))
+    for t in range(1, n):
+        y[t] = rho * y[t - 1] + s * e[t]
+    for Yh in (y, y[rng.permutation(n)]):
+        Y = torch.from_numpy(np.ascontiguousarray(Yh)).to(dev())
+        C = Y[torch.from_numpy(np.sort(rng.choice(n, K, replace=False))).to(dev())].double().contiguous()
+        hints = subsampled_hints(Y, C)
+        cold = kernels.kmeans_assign(Y, C, impl=2)
+        warm = kernels.kmeans_assign(Y, C, impl=2, hints=hints)
+        assert torch.equal(cold, warm)
+        kept = bool((hints >= 0).all().item())
+        assert kept == (Yh is y), "hints are kept for the trajectory and withdrawn for the shuffled frames"
+        if kept:
+            assert torch.equal(hints[::16], cold[::16])
+
+
 # ----------------------------------------------------------------------------- k-means
 @pytest.mark.parametrize("D,K,n", [(2, 200, 20000), (3, 17, 5000), (10, 1000, 30000), (10, 3000, 8000),
                                    (16, 64, 4000), (64, 300, 3000)])
@@ -624,6 +680,29 @@ def test_eigenvalues_lanczos_large_K():
     evo = oracle.msm.eigenvalues_rev(To, pio, 10)
     assert int(info[0].item()) > 0, "expected the Lanczos path"
     np.testing.assert_allclose(ev.cpu().numpy(), evo, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("K,k", [(2000, 10), (1500, 6)])
+def test_eigenvalues_lanczos_narrow_bulk(K, k):
+    """A reversible chain of five weakly coupled dense blocks: the bulk of the spectrum narrows like
+    1 / sqrt(K), so orthogonality lost to the converged Perron vector grows ~50x per local Lanczos step.  The
+    fixed re-orthogonalisation period this kernel once used returned eigenvalues of the order of 1e3 for
+    K = 2000, k = 10 (tools/eig_dump.py); the partial re-orthogonalisation must agree with eigvalsh."""
+    from pmarlo_b200 import kernels
+
+    rng = np.random.default_rng(0)
+    C = rng.random((K, K)) * 0.02
+    b = K // 5
+    for i in range(5):
+        C[i * b:(i + 1) * b, i * b:(i + 1) * b] += rng.random((b, b))
+    C = C + C.T
+    T, pi = C / C.sum(1, keepdims=True), C.sum(1) / C.sum()
+    sq = np.sqrt(pi)
+    ref = np.linalg.eigvalsh(sq[:, None] * T / sq[None, :])
+    ref = ref[np.argsort(-np.abs(ref))][:k]
+    ev, info = kernels.eig_rev_topk(torch.from_numpy(T).to(dev()), torch.from_numpy(pi).to(dev()), k)
+    assert int(info[0].item()) > 0 and int(info[1].item()) == 1, info
+    np.testing.assert_allclose(ev.cpu().numpy(), ref, rtol=0, atol=1e-12)
 
 
 def test_implied_timescales_sweep():

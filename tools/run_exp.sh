@@ -1,5 +1,1 @@
-PMB_TICA_CHOL=0 python tools/tica_bench.py 256
-PMB_TICA_CHOL=1 python tools/tica_bench.py 256
-PMB_TICA_CHOL=1 python tools/tica_bench.py 84
-PMB_TICA_CHOL=1 python tools/tica_bench.py 400 3
-timeout 600 python -m pytest tests -x -q -m gpu -k "tica or vamp or reduce or c1 or c3" 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "narrow_bulk or project_fp32 or subsampled_hints" 2>&1 | tail -15
