@@ -1,4 +1,6 @@
-mkdir -p /tmp/ncu
-timeout 400 ncu --set full --clock-control none -k regex:"mle_grid_kernel" -c 1 -f -o /tmp/ncu/mle5 python bench.py --config C5 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_mle_c5.log 2>&1; echo "ncu=$?"
-ncu -i /tmp/ncu/mle5.ncu-rep --page raw --csv > gpurun_out/ncu_mle_c5_raw.csv 2>/dev/null
-cat gpurun_out/ncu_mle_c5_raw.csv | python tools/ncu_summary.py
+# Scratch script for one-off GPU experiments (run through gpurun from the repo root).  The micro-benchmarks
+# of the round, each printing one line per configuration:
+python tools/prj_bench.py            # K5 projection, 10 M x 256 -> 10
+python tools/tica_bench.py 256       # K4 TICA solve (PMB_TICA_CHOL=0 / PMB_TICA_CLUSTER=0 for the A/B forms)
+python tools/eig_bench.py 1000 6 4   # K9 Lanczos, top-6 of a 1000-state reversible chain
+python tools/km_bench.py c4 2>&1 | tail -5   # K6 k-means assignment: cold / subsampled hints / warm / with accumulation
