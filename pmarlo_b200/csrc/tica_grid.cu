@@ -486,7 +486,7 @@ __device__ int chol_pivoted_cta(const double* __restrict__ A, int n, double* __r
     // 3. one pass over the rows already in W for all columns of the block
     if (act) {
       const double* gq = gp + (size_t)q * BQ * n;
-#pragma unroll 8
+#pragma unroll 16
       for (int j = 0; j < kk; ++j) {
         const double w = ldg_cg(W + (size_t)j * n + i);
 #pragma unroll
